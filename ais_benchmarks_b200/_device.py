@@ -1,0 +1,335 @@
+"""Device plumbing between the Python API and libais_b200.so.
+
+PyTorch is used for device memory, streams and (in parallel.py) torch.distributed only; every
+arithmetic step of the hot path is a call into the C ABI (include/ais_b200.h). Nothing in here
+falls back to the CPU: without a CUDA device or without the built library the calls raise.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import AisbError, PackedMixture, COV_ISO_SHARED, COV_DIAG, COV_FULL, check
+
+LOG2E = 1.4426950408889634074
+LOG_2PI = 1.8378770664093454836
+
+_workspaces = {}
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise AisbError("ais_benchmarks_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return _lib.load()
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def device():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def is_tensor(x):
+    return isinstance(x, torch.Tensor)
+
+
+def check_points(x, dims):
+    """Shape contract of CDistribution._check_shape (reference distributions/distributions.py:128-147):
+    1-D input -> (1, dims); 2-D input must have shape[1] == dims; anything else raises ValueError."""
+    shape = tuple(x.shape)
+    if len(shape) == 1:
+        if shape[0] != dims:
+            raise ValueError("cannot reshape array of size %d into shape (1,%d)" % (shape[0], dims))
+        return x.reshape(1, dims)
+    if len(shape) == 2:
+        if shape[1] != dims:
+            raise ValueError("Shape of x does not match self.dims = %d. is Nx%d array that contains N points of %d "
+                             "dimensions. x.shape=%s" % (dims, dims, dims, str(shape)))
+        return x
+    raise ValueError("Shape of x does not match self.dims = %d. is Nx%d array that contains N points of %d "
+                     "dimensions. x.shape=%s" % (dims, dims, dims, str(shape)))
+
+
+def to_device_points(x, dims):
+    """-> (float32 contiguous CUDA tensor [n, dims], was_numpy). Accepts numpy arrays, lists or torch tensors."""
+    if not is_tensor(x):
+        x = np.asarray(x)
+        if x.dtype == object:
+            raise ValueError("Unsupported samples data format")
+    x = check_points(x, dims)
+    require_cuda()
+    if is_tensor(x):
+        return x.to(device=device(), dtype=torch.float32).contiguous(), False
+    host = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    return host.to(device(), non_blocking=False), True
+
+
+def from_device(t, as_numpy):
+    """float32 device vector -> numpy float64 (reference dtype) or the tensor itself."""
+    if as_numpy:
+        return t.detach().cpu().numpy().astype(np.float64)
+    return t
+
+
+def exp_from_device(t, as_numpy):
+    """exp of a float32 device log-density vector: float64 numpy (so that values below the float32 range survive,
+    as in the reference's float64 prob) or a float32 tensor."""
+    if as_numpy:
+        return torch.exp(t.detach().double()).cpu().numpy()
+    return torch.exp(t)
+
+
+def workspace(nbytes):
+    dev = torch.cuda.current_device()
+    ws = _workspaces.get(dev)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device())
+        _workspaces[dev] = ws
+    return ws
+
+
+def workspace_for(n, K, D):
+    lib = require_cuda()
+    need = C.c_size_t(0)
+    check(lib.aisb_workspace_bytes(int(n), int(K), int(D), C.byref(need)), "aisb_workspace_bytes")
+    return workspace(need.value)
+
+
+class DeviceMixture:
+    """A packed Gaussian mixture resident in HBM (layout: include/ais_b200.h "Packed mixture layout")."""
+
+    def __init__(self, rows, offsets, K, D, kind, iso_scale=0.0, uniform_offset=0.0):
+        self.rows, self.offsets = rows, offsets
+        self.K, self.D, self.kind = int(K), int(D), int(kind)
+        self.iso_scale, self.uniform_offset = float(iso_scale), float(uniform_offset)
+        self._struct = PackedMixture(_ptr(rows), _ptr(offsets), self.K, self.D, self.kind, self.iso_scale,
+                                     self.uniform_offset)
+
+    def ref(self):
+        return C.byref(self._struct)
+
+    @staticmethod
+    def pack_host(means, cov, weights, kind):
+        """float64 host parameters -> (rows float32 [KP, RF], offsets float32 [KP], iso_scale). No CUDA needed."""
+        lib = _lib.load()
+        means = np.ascontiguousarray(means, dtype=np.float64)
+        K, D = means.shape
+        cov = np.ascontiguousarray(cov, dtype=np.float64)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        expect = {COV_ISO_SHARED: 1, COV_DIAG: K * D, COV_FULL: K * D * D}[kind]
+        if cov.size != expect:
+            raise ValueError("covariance parameter has %d elements, expected %d" % (cov.size, expect))
+        if w is not None and w.size != K:
+            raise ValueError("len(models)=%d , len(weights)=%d" % (K, w.size))
+        RF = lib.aisb_packed_row_floats(kind, D)
+        if RF == 0:
+            raise AisbError("unsupported mixture shape: D=%d cov_kind=%d (D <= 64; full covariance D <= 32)" % (D, kind))
+        KP = lib.aisb_padded_components(K)
+        rows = np.empty((KP, RF), dtype=np.float32)
+        offs = np.empty(KP, dtype=np.float32)
+        iso = C.c_float(0.0)
+        rc = lib.aisb_pack_mixture_f64(means.ctypes.data, cov.ctypes.data, None if w is None else w.ctypes.data, K, D,
+                                       kind, rows.ctypes.data, offs.ctypes.data, C.byref(iso))
+        if rc != 0:
+            msg = lib.aisb_last_error().decode()
+            # the reference asserts det > 0 (CMultivariateNormal.py:48,56)
+            raise AssertionError(msg)
+        return rows, offs, iso.value
+
+    @classmethod
+    def from_params(cls, means, cov, weights, kind):
+        rows, offs, iso = cls.pack_host(means, cov, weights, kind)
+        require_cuda()
+        K, D = np.asarray(means).shape
+        dev = device()
+        return cls(torch.from_numpy(rows).to(dev), torch.from_numpy(offs).to(dev), K, D, kind, iso, 0.0)
+
+    @classmethod
+    def kde(cls, samples, idx, n_c, bw):
+        """KDE of sampling_methods/base.py:162-179 built on device: centres samples[idx], covariance bw*I, weights 1/n_c."""
+        lib = require_cuda()
+        n, D = samples.shape
+        DP = lib.aisb_padded_dims(D)
+        KP = lib.aisb_padded_components(n_c)
+        rows = torch.empty((KP, DP), dtype=torch.float32, device=samples.device)
+        check(lib.aisb_kde_pack_f32(_ptr(samples), n, D, _ptr(idx), int(n_c), float(bw), _ptr(rows), stream_ptr()),
+              "aisb_kde_pack_f32")
+        uo = -math.log(n_c) - 0.5 * D * (LOG_2PI + math.log(bw))
+        return cls(rows, None, n_c, D, COV_ISO_SHARED, lib.aisb_iso_scale(float(bw)), uo)
+
+
+def mixture_logpdf(x, mix, out=None):
+    """x: float32 CUDA [n, D]; returns float32 CUDA [n] natural-log densities (C ABI: aisb_mixture_logpdf_f32)."""
+    lib = require_cuda()
+    n = x.shape[0]
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=x.device)
+    if n == 0:
+        return out
+    ws = workspace_for(n, mix.K, mix.D)
+    check(lib.aisb_mixture_logpdf_f32(_ptr(x), n, mix.ref(), _ptr(out), _ptr(ws), ws.numel(), stream_ptr()),
+          "aisb_mixture_logpdf_f32")
+    return out
+
+
+def dm_weights(x, target, logp_in, proposals, want_logp=False, want_logq=False):
+    """Fused DM weights (C ABI: aisb_dm_weights_f32). Returns (logw, logp|None, logq|None, partials[4] device f64)."""
+    lib = require_cuda()
+    n = x.shape[0]
+    dev = x.device
+    logw = torch.empty(n, dtype=torch.float32, device=dev)
+    logp = torch.empty(n, dtype=torch.float32, device=dev) if want_logp else None
+    logq = torch.empty(n, dtype=torch.float32, device=dev) if want_logq else None
+    partials = torch.empty(4, dtype=torch.float64, device=dev)
+    Kmax = max(proposals.K, target.K if target is not None else 1)
+    ws = workspace_for(max(n, 1), Kmax, proposals.D)
+    check(lib.aisb_dm_weights_f32(_ptr(x), n, target.ref() if target is not None else None, _ptr(logp_in),
+                                  proposals.ref(), _ptr(logw), _ptr(logp), _ptr(logq), _ptr(partials), _ptr(ws),
+                                  ws.numel(), stream_ptr()), "aisb_dm_weights_f32")
+    return logw, logp, logq, partials
+
+
+def logw_partials(logw):
+    lib = require_cuda()
+    n = logw.shape[0]
+    partials = torch.empty(4, dtype=torch.float64, device=logw.device)
+    ws = workspace(32 * (n // 2048 + 2) + 512)
+    check(lib.aisb_logw_partials_f32(_ptr(logw), n, _ptr(partials), _ptr(ws), ws.numel(), stream_ptr()),
+          "aisb_logw_partials_f32")
+    return partials
+
+
+def normalize_weights(logw, partials_host):
+    lib = require_cuda()
+    n = logw.shape[0]
+    out = torch.empty(n, dtype=torch.float32, device=logw.device)
+    p = (C.c_double * 4)(*[float(v) for v in partials_host])
+    check(lib.aisb_normalize_weights_f32(_ptr(logw), n, p, _ptr(out), stream_ptr()), "aisb_normalize_weights_f32")
+    return out
+
+
+def kld_partials(lp, lq):
+    lib = require_cuda()
+    n = lp.shape[0]
+    partials = torch.empty(8, dtype=torch.float64, device=lp.device)
+    ws = workspace(64 * (n // 2048 + 2) + 512)
+    check(lib.aisb_kld_partials_f32(_ptr(lp), _ptr(lq), n, _ptr(partials), _ptr(ws), ws.numel(), stream_ptr()),
+          "aisb_kld_partials_f32")
+    return partials
+
+
+def kld_finalize(partials_host):
+    lib = _lib.load()
+    p = (C.c_double * 8)(*[float(v) for v in partials_host])
+    return float(lib.aisb_kld_finalize(p))
+
+
+def kld_merge(a, b):
+    lib = _lib.load()
+    pa = (C.c_double * 8)(*[float(v) for v in a])
+    pb = (C.c_double * 8)(*[float(v) for v in b])
+    out = (C.c_double * 8)()
+    lib.aisb_kld_partials_merge(pa, pb, out)
+    return np.array(list(out), dtype=np.float64)
+
+
+def weight_merge(a, b):
+    lib = _lib.load()
+    pa = (C.c_double * 4)(*[float(v) for v in a])
+    pb = (C.c_double * 4)(*[float(v) for v in b])
+    out = (C.c_double * 4)()
+    lib.aisb_weight_partials_merge(pa, pb, out)
+    return np.array(list(out), dtype=np.float64)
+
+
+def weight_ess(p):
+    lib = _lib.load()
+    return float(lib.aisb_weight_partials_ess((C.c_double * 4)(*[float(v) for v in p])))
+
+
+def weight_logsum(p):
+    lib = _lib.load()
+    return float(lib.aisb_weight_partials_logsum((C.c_double * 4)(*[float(v) for v in p])))
+
+
+def mpmc_moments(x, proposals, logq, logw, log_norm):
+    """-> float64 CUDA [K, D+1]: column 0 = sum_i w~_i rho_di, columns 1.. = sum_i w~_i rho_di x_i."""
+    lib = require_cuda()
+    out = torch.zeros((proposals.K, proposals.D + 1), dtype=torch.float64, device=x.device)
+    check(lib.aisb_mpmc_moments_f32(_ptr(x), x.shape[0], proposals.ref(), _ptr(logq), _ptr(logw), float(log_norm),
+                                    _ptr(out), stream_ptr()), "aisb_mpmc_moments_f32")
+    return out
+
+
+def raw_moments(x):
+    """-> (sum x [D], sum x x^T [D, D]) float64 CUDA."""
+    lib = require_cuda()
+    n, D = x.shape
+    out = torch.zeros(D + D * D, dtype=torch.float64, device=x.device)
+    check(lib.aisb_raw_moments_f32(_ptr(x), n, D, _ptr(out), stream_ptr()), "aisb_raw_moments_f32")
+    return out[:D], out[D:].reshape(D, D)
+
+
+def lais_mh(means, target, delta, u, lo, hi):
+    """In-place: N chains x L Metropolis-Hastings steps on `means` [N, D] (C ABI: aisb_lais_mh_f32)."""
+    lib = require_cuda()
+    N, D = means.shape
+    L = delta.shape[0]
+    check(lib.aisb_lais_mh_f32(_ptr(means), N, target.ref(), _ptr(delta), _ptr(u), L, _ptr(lo), _ptr(hi),
+                               stream_ptr()), "aisb_lais_mh_f32")
+    return means
+
+
+def box_mixture_logpdf(x, lo, hi, logw_over_vol, open_upper):
+    lib = require_cuda()
+    n, D = x.shape
+    out = torch.empty(n, dtype=torch.float32, device=x.device)
+    check(lib.aisb_box_mixture_logpdf_f32(_ptr(x), n, D, _ptr(lo), _ptr(hi), _ptr(logw_over_vol), lo.shape[0],
+                                          1 if open_upper else 0, _ptr(out), stream_ptr()),
+          "aisb_box_mixture_logpdf_f32")
+    return out
+
+
+_rng_state = {"seed": 0x5EED_B200, "offset": 0}
+
+
+def seed(s):
+    """Seed the device sampling kernels (Philox). Streams are not comparable with numpy's."""
+    _rng_state["seed"] = int(s) & 0xFFFFFFFFFFFFFFFF
+    _rng_state["offset"] = 0
+
+
+def _next_offset(n_values):
+    off = _rng_state["offset"]
+    _rng_state["offset"] = off + (n_values + 3) // 4 + 1
+    return off
+
+
+def sample_iso(means, per, var):
+    """means [K, D] float32 CUDA -> [K*per, D]: `per` draws from N(means[k], var*I) for every k, k-major."""
+    lib = require_cuda()
+    K, D = means.shape
+    out = torch.empty((K * per, D), dtype=torch.float32, device=means.device)
+    off = _next_offset(K * per * D)
+    check(lib.aisb_sample_iso_f32(_ptr(means), K, D, int(per), float(var), _rng_state["seed"], off, _ptr(out),
+                                  stream_ptr()), "aisb_sample_iso_f32")
+    return out
+
+
+def uniform_box(lo, hi, n):
+    """lo, hi [D] float32 CUDA -> [n, D] uniform draws."""
+    lib = require_cuda()
+    D = lo.shape[0]
+    out = torch.empty((n, D), dtype=torch.float32, device=lo.device)
+    off = _next_offset(n * D)
+    check(lib.aisb_uniform_box_f32(_ptr(lo), _ptr(hi), D, int(n), _rng_state["seed"], off, _ptr(out), stream_ptr()),
+          "aisb_uniform_box_f32")
+    return out

@@ -1,0 +1,292 @@
+// Adaptation-step kernels: M-PMC Rao-Blackwellised moments, raw moments, LAIS MH chains.
+#include "pairwise.cuh"
+
+namespace aisb {
+
+// ---------------------------------------------------------------------------------------------
+// M-PMC moments (reference sampling_methods/m_pmc.py:57-61,102-105)
+//   a_{d,i} = w~_i rho_{d,i} = 2^( t_d(x_i) - log2 q(x_i) + log2 w~_i ),  t_d = c_d - ||A_d x_i + b_d||^2
+//   out[d][0] += sum_i a_{d,i},  out[d][1+j] += sum_i a_{d,i} x_ij
+// Points live in registers (same tiling as the density kernels); the sum over points is a warp
+// shuffle reduction followed by one shared-memory double atomic per (component, column) per warp,
+// flushed to global memory with double atomics once per chunk.
+// ---------------------------------------------------------------------------------------------
+template <int KIND, int DP>
+__global__ void __launch_bounds__(kThreads)
+    mpmc_moments_kernel(const float* __restrict__ x, int64_t n, int D, int vec_ok, const float* __restrict__ rows,
+                        const float* __restrict__ offs, int64_t KP, int64_t K, float a_iso,
+                        const float* __restrict__ logq, const float* __restrict__ logw, float log2_norm,
+                        double* __restrict__ out) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bars[kStages];
+  constexpr int E = points_per_thread(DP);
+  constexpr int J = chunk_comps(KIND, DP);
+  constexpr int ROW = row_floats(KIND, DP);
+  // accumulators for one chunk live after the staging ring
+  double* sacc = reinterpret_cast<double*>(smem + kStages * stage_floats(KIND, DP, true));
+
+  ring_init(bars);
+  float xr[E][DP];
+  int64_t pidx[E];
+  load_points<DP, E>(x, n, D, vec_ok, static_cast<int64_t>(blockIdx.x) * (kThreads * E), xr, pidx);
+  float shift[E];  // log2 w~_i - log2 q(x_i); -inf for out-of-range or zero-weight points
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    if (pidx[e] < n) {
+      const float lw = __ldg(logw + pidx[e]), lq = __ldg(logq + pidx[e]);
+      shift[e] = (lw - lq) * 1.4426950408889634f - log2_norm;
+      if (!(shift[e] == shift[e]) || shift[e] == INFINITY) shift[e] = -INFINITY;
+    } else {
+      shift[e] = -INFINITY;
+    }
+  }
+  for (int i = threadIdx.x; i < J * (DP + 1); i += kThreads) sacc[i] = 0.0;
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  uint32_t it = 0;
+  stream_components<KIND, DP, true>(
+      rows, offs, 0, KP, smem, bars, it, [&](const float* srows, const float* soffs, int cnt, int64_t k0) {
+#pragma unroll 1
+        for (int j = 0; j < cnt; ++j) {
+          if (k0 + j >= K) break;  // padding components (uniform across the CTA)
+          float t[E];
+          comp_eval<KIND, DP, E>(srows + j * ROW, soffs[j], a_iso, xr, t);
+          float v[DP + 1];
+#pragma unroll
+          for (int d = 0; d <= DP; ++d) v[d] = 0.f;
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const float a = ex2(t[e] + shift[e]);
+            v[0] += a;
+#pragma unroll
+            for (int d = 0; d < DP; ++d) v[1 + d] = fmaf(a, xr[e][d], v[1 + d]);
+          }
+#pragma unroll
+          for (int d = 0; d <= DP; ++d) v[d] = warp_sum(v[d]);
+          if (lane == 0) {
+#pragma unroll
+            for (int d = 0; d <= DP; ++d) atomicAdd(&sacc[j * (DP + 1) + d], static_cast<double>(v[d]));
+          }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * (DP + 1); i += kThreads) {
+          const int j = i / (DP + 1), d = i % (DP + 1);
+          if (k0 + j < K && d <= D) {
+            const double val = sacc[i];
+            if (val != 0.0) atomicAdd(&out[(k0 + j) * (D + 1) + d], val);
+          }
+          sacc[i] = 0.0;
+        }
+        // the __syncthreads() at the end of the stage protects sacc for the next chunk
+      });
+}
+
+template <int KIND, int DP>
+static int launch_mpmc_t(const float* x, int64_t n, int D, int vec_ok, const aisb_packed_mixture* mix,
+                         const float* logq, const float* logw, float log2_norm, double* out, cudaStream_t st) {
+  constexpr int E = points_per_thread(DP);
+  constexpr size_t smem = pass_smem_bytes(KIND, DP, true) + sizeof(double) * chunk_comps(KIND, DP) * (DP + 1);
+  auto kern = mpmc_moments_kernel<KIND, DP>;
+  if (smem > 48 * 1024) AISB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int64_t ntiles = (n + kThreads * E - 1) / (kThreads * E);
+  kern<<<static_cast<unsigned>(ntiles), kThreads, smem, st>>>(x, n, D, vec_ok, mix->d_rows, mix->d_offsets,
+                                                             aisb_padded_components(mix->K), mix->K, mix->iso_scale,
+                                                             logq, logw, log2_norm, out);
+  AISB_LAUNCH_CHECK("mpmc_moments_kernel");
+  return AISB_OK;
+}
+
+template <int KIND>
+static int launch_mpmc_dp(int DP, const float* x, int64_t n, int D, int vec_ok, const aisb_packed_mixture* mix,
+                          const float* logq, const float* logw, float log2_norm, double* out, cudaStream_t st) {
+  switch (DP) {
+    case 1: return launch_mpmc_t<KIND, 1>(x, n, D, vec_ok, mix, logq, logw, log2_norm, out, st);
+    case 2: return launch_mpmc_t<KIND, 2>(x, n, D, vec_ok, mix, logq, logw, log2_norm, out, st);
+    case 4: return launch_mpmc_t<KIND, 4>(x, n, D, vec_ok, mix, logq, logw, log2_norm, out, st);
+    case 8: return launch_mpmc_t<KIND, 8>(x, n, D, vec_ok, mix, logq, logw, log2_norm, out, st);
+    case 16: return launch_mpmc_t<KIND, 16>(x, n, D, vec_ok, mix, logq, logw, log2_norm, out, st);
+    case 32: return launch_mpmc_t<KIND, 32>(x, n, D, vec_ok, mix, logq, logw, log2_norm, out, st);
+    default: break;
+  }
+  set_error("mpmc_moments: unsupported D=%d (max 32)", D);
+  return AISB_ERR_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Raw first and second moments in float64: out = { sum x [D], sum x x^T [D*D] }
+// ---------------------------------------------------------------------------------------------
+constexpr int kRawChunk = 128;
+
+__global__ void __launch_bounds__(256) raw_moments_kernel(const float* __restrict__ x, int64_t n, int D,
+                                                          double* __restrict__ out) {
+  __shared__ float tile[kRawChunk * AISB_MAX_DIMS];
+  const int64_t nchunks = (n + kRawChunk - 1) / kRawChunk;
+  const int nq = D + D * D;
+  // each thread owns output entries q = tid, tid+256, ... and keeps their sums across its chunks
+  double acc[(AISB_MAX_DIMS + AISB_MAX_DIMS * AISB_MAX_DIMS + 255) / 256];
+#pragma unroll
+  for (int s = 0; s < (AISB_MAX_DIMS + AISB_MAX_DIMS * AISB_MAX_DIMS + 255) / 256; ++s) acc[s] = 0.0;
+  for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int64_t p0 = c * kRawChunk;
+    const int cnt = static_cast<int>(n - p0 < kRawChunk ? n - p0 : kRawChunk);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt * D; i += 256) tile[i] = x[p0 * D + i];
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < (AISB_MAX_DIMS + AISB_MAX_DIMS * AISB_MAX_DIMS + 255) / 256; ++s) {
+      const int q = threadIdx.x + s * 256;
+      if (q < nq) {
+        double a = 0.0;
+        if (q < D) {
+          for (int p = 0; p < cnt; ++p) a += tile[p * D + q];
+        } else {
+          const int i = (q - D) / D, j = (q - D) % D;
+          for (int p = 0; p < cnt; ++p) a += static_cast<double>(tile[p * D + i]) * static_cast<double>(tile[p * D + j]);
+        }
+        acc[s] += a;
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < (AISB_MAX_DIMS + AISB_MAX_DIMS * AISB_MAX_DIMS + 255) / 256; ++s) {
+    const int q = threadIdx.x + s * 256;
+    if (q < nq && acc[s] != 0.0) atomicAdd(&out[q], acc[s]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic (runtime-shaped) natural-log mixture density of one point, parameters read from global
+// memory. Used where the batch is tiny (LAIS chains) and launch count, not throughput, matters.
+// ---------------------------------------------------------------------------------------------
+__device__ float mixture_logpdf_point(const float* xp, int D, int DP, int kind, const float* __restrict__ rows,
+                                      const float* __restrict__ offs, int64_t K, float a_iso, float uniform_offset) {
+  const int ROW = row_floats(kind, DP);
+  float m = kNegBig, S = 0.f;
+  for (int64_t k = 0; k < K; ++k) {
+    const float* row = rows + k * ROW;
+    float t = offs ? offs[k] : 0.f;
+    if (kind == AISB_COV_ISO_SHARED) {
+      for (int d = 0; d < D; ++d) {
+        const float dl = fmaf(xp[d], a_iso, row[d]);
+        t = fmaf(-dl, dl, t);
+      }
+    } else if (kind == AISB_COV_DIAG) {
+      for (int d = 0; d < D; ++d) {
+        const float dl = fmaf(xp[d], row[d], row[DP + d]);
+        t = fmaf(-dl, dl, t);
+      }
+    } else {
+      const int TRI = DP * (DP + 1) / 2;
+      for (int r = 0; r < D; ++r) {
+        float z = row[TRI + r];
+        for (int c = 0; c <= r; ++c) z = fmaf(row[r * (r + 1) / 2 + c], xp[c], z);
+        t = fmaf(-z, z, t);
+      }
+    }
+    const float mn = fmaxf(m, t);
+    S = S * ex2(m - mn) + ex2(t - mn);
+    m = mn;
+  }
+  return lse_finish(m, S) + (offs ? 0.f : uniform_offset);
+}
+
+// One thread per chain; L sequential Metropolis-Hastings steps (reference layered_ais.py:54-68).
+__global__ void lais_mh_kernel(float* __restrict__ means, int64_t N, int D, int DP, int kind,
+                               const float* __restrict__ rows, const float* __restrict__ offs, int64_t K, float a_iso,
+                               float uniform_offset, const float* __restrict__ delta, const float* __restrict__ u,
+                               int L, const float* __restrict__ lo, const float* __restrict__ hi) {
+  const int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (c >= N) return;
+  float xc[AISB_MAX_DIMS], xh[AISB_MAX_DIMS];
+  for (int d = 0; d < D; ++d) xc[d] = means[c * D + d];
+  for (int l = 0; l < L; ++l) {
+    // the reference re-evaluates pi(x) every step (2 target evaluations per step)
+    const float lp_old = mixture_logpdf_point(xc, D, DP, kind, rows, offs, K, a_iso, uniform_offset);
+    const float* dl = delta + (static_cast<int64_t>(l) * N + c) * D;
+    for (int d = 0; d < D; ++d) xh[d] = fminf(fmaxf(xc[d] + dl[d], lo[d]), hi[d]);
+    const float lp_new = mixture_logpdf_point(xh, D, DP, kind, rows, offs, K, a_iso, uniform_offset);
+    // linear-domain ratio in float64, including its underflow behaviour (0/0 -> NaN -> reject, x/0 -> accept)
+    const double ratio = exp(static_cast<double>(lp_new)) / exp(static_cast<double>(lp_old));
+    if (ratio > static_cast<double>(u[static_cast<int64_t>(l) * N + c]))
+      for (int d = 0; d < D; ++d) xc[d] = xh[d];
+  }
+  for (int d = 0; d < D; ++d) means[c * D + d] = xc[d];
+}
+
+}  // namespace aisb
+
+using namespace aisb;
+
+static int check_mix_basic(const aisb_packed_mixture* mix, const char* who) {
+  if (!mix || !mix->d_rows || mix->K < 1 || aisb_packed_row_floats(mix->cov_kind, mix->D) == 0) {
+    set_error("%s: invalid mixture", who);
+    return AISB_ERR_INVALID;
+  }
+  return AISB_OK;
+}
+
+extern "C" int aisb_mpmc_moments_f32(const float* d_x, int64_t n, const aisb_packed_mixture* proposals,
+                                     const float* d_logq, const float* d_logw, double log_norm, double* d_out,
+                                     void* stream) {
+  int rc = check_mix_basic(proposals, "mpmc_moments");
+  if (rc) return rc;
+  if (!proposals->d_offsets) {
+    set_error("mpmc_moments: proposals need per-component offsets (log2 alpha_d + normaliser)");
+    return AISB_ERR_INVALID;
+  }
+  if (n < 0 || !d_out || (n > 0 && (!d_x || !d_logq || !d_logw))) {
+    set_error("mpmc_moments: null pointer or negative n");
+    return AISB_ERR_INVALID;
+  }
+  if (n == 0) return AISB_OK;
+  const int D = proposals->D, DP = aisb_padded_dims(D);
+  int vec_ok = 0;
+  if (D == DP && DP >= 4) vec_ok = reinterpret_cast<uintptr_t>(d_x) % 16 == 0;
+  if (D == DP && DP == 2) vec_ok = reinterpret_cast<uintptr_t>(d_x) % 8 == 0;
+  const float l2n = static_cast<float>(log_norm * kLog2e);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (proposals->cov_kind) {
+    case AISB_COV_ISO_SHARED: return launch_mpmc_dp<AISB_COV_ISO_SHARED>(DP, d_x, n, D, vec_ok, proposals, d_logq, d_logw, l2n, d_out, st);
+    case AISB_COV_DIAG: return launch_mpmc_dp<AISB_COV_DIAG>(DP, d_x, n, D, vec_ok, proposals, d_logq, d_logw, l2n, d_out, st);
+    case AISB_COV_FULL: return launch_mpmc_dp<AISB_COV_FULL>(DP, d_x, n, D, vec_ok, proposals, d_logq, d_logw, l2n, d_out, st);
+    default: break;
+  }
+  set_error("mpmc_moments: unknown cov_kind %d", proposals->cov_kind);
+  return AISB_ERR_INVALID;
+}
+
+extern "C" int aisb_raw_moments_f32(const float* d_x, int64_t n, int32_t D, double* d_out, void* stream) {
+  if (D < 1 || D > AISB_MAX_DIMS || n < 0 || !d_out || (n > 0 && !d_x)) {
+    set_error("raw_moments: invalid argument (n=%lld D=%d)", static_cast<long long>(n), D);
+    return AISB_ERR_INVALID;
+  }
+  if (n == 0) return AISB_OK;
+  const int64_t nchunks = (n + kRawChunk - 1) / kRawChunk;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  const unsigned grid = static_cast<unsigned>(nchunks < cap ? nchunks : cap);
+  raw_moments_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, n, D, d_out);
+  AISB_LAUNCH_CHECK("raw_moments_kernel");
+  return AISB_OK;
+}
+
+extern "C" int aisb_lais_mh_f32(float* d_means, int64_t N, const aisb_packed_mixture* target, const float* d_delta,
+                                const float* d_u, int32_t L, const float* d_lo, const float* d_hi, void* stream) {
+  int rc = check_mix_basic(target, "lais_mh");
+  if (rc) return rc;
+  if (target->cov_kind != AISB_COV_ISO_SHARED && !target->d_offsets) {
+    set_error("lais_mh: offsets are required for cov_kind %d", target->cov_kind);
+    return AISB_ERR_INVALID;
+  }
+  if (N < 0 || L < 0 || (N > 0 && L > 0 && (!d_means || !d_delta || !d_u || !d_lo || !d_hi))) {
+    set_error("lais_mh: null pointer or negative size");
+    return AISB_ERR_INVALID;
+  }
+  if (N == 0 || L == 0) return AISB_OK;
+  const int D = target->D;
+  lais_mh_kernel<<<static_cast<unsigned>((N + 63) / 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_means, N, D, aisb_padded_dims(D), target->cov_kind, target->d_rows, target->d_offsets, target->K,
+      target->iso_scale, target->uniform_offset, d_delta, d_u, L, d_lo, d_hi);
+  AISB_LAUNCH_CHECK("lais_mh_kernel");
+  return AISB_OK;
+}

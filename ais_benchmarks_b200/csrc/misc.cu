@@ -1,0 +1,243 @@
+// Box-mixture ("haar") density, device-side sampling, and the FP32 / MUFU peak micro-benchmarks.
+#include "common.cuh"
+
+namespace aisb {
+
+// ---------------------------------------------------------------------------------------------
+// log sum_k w_k [x in box_k] / vol_k  over axis-aligned boxes.
+// Replaces the per-sample, per-node Python scan of CTreePyramidSampling.prob/log_prob (haar kernel)
+// (reference sampling_methods/tree_pyramid.py:587-603) and CMultivariateUniform.log_prob
+// (distributions/parametric/CMultivariateUniform.py:38-47). One thread per point, boxes staged
+// through shared memory in chunks.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBoxChunk = 128;
+
+template <int DP>
+__global__ void __launch_bounds__(128) box_mixture_kernel(const float* __restrict__ x, int64_t n, int D,
+                                                         const float* __restrict__ lo, const float* __restrict__ hi,
+                                                         const float* __restrict__ lwv, int64_t K, int open_upper,
+                                                         float* __restrict__ out) {
+  __shared__ float s_lo[kBoxChunk * DP], s_hi[kBoxChunk * DP], s_w[kBoxChunk];
+  const int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t pc = p < n ? p : n - 1;
+  float xr[DP];
+#pragma unroll
+  for (int d = 0; d < DP; ++d) xr[d] = d < D ? x[pc * D + d] : 0.f;
+  float m = kNegBig, S = 0.f;
+  bool has_nan = false;
+#pragma unroll
+  for (int d = 0; d < DP; ++d) has_nan |= !(xr[d] == xr[d]);
+  for (int64_t k0 = 0; k0 < K; k0 += kBoxChunk) {
+    const int cnt = static_cast<int>(K - k0 < kBoxChunk ? K - k0 : kBoxChunk);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt * DP; i += blockDim.x) {
+      const int j = i / DP, d = i % DP;
+      // padding dims: (-inf, +inf) always contains 0
+      s_lo[i] = d < D ? lo[(k0 + j) * D + d] : -INFINITY;
+      s_hi[i] = d < D ? hi[(k0 + j) * D + d] : INFINITY;
+    }
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) s_w[i] = lwv[k0 + i];
+    __syncthreads();
+    for (int j = 0; j < cnt; ++j) {
+      bool in = true;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) {
+        const float l = s_lo[j * DP + d], h = s_hi[j * DP + d];
+        in = in && (l < xr[d]) && (open_upper ? xr[d] < h : xr[d] <= h);
+      }
+      const float t = s_w[j] * 1.4426950408889634f;
+      if (in && t > -INFINITY) {
+        const float mn = fmaxf(m, t);
+        S = S * ex2(m - mn) + ex2(t - mn);
+        m = mn;
+      }
+    }
+  }
+  if (p < n) out[p] = has_nan ? -INFINITY : (m + log2f(S)) * 0.69314718055994530942f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (Salmon et al. 2011) + Box-Muller
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01_open(uint32_t v) { return (static_cast<float>(v >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+__device__ __forceinline__ void normal4(uint64_t counter, uint64_t seed, float (&z)[4]) {
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(counter), static_cast<uint32_t>(counter >> 32), 0u, 0u),
+                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  const float r0 = sqrtf(-2.f * logf(u01_open(r.x))), r1 = sqrtf(-2.f * logf(u01_open(r.z)));
+  float s0, c0, s1, c1;
+  sincospif(2.f * u01_open(r.y), &s0, &c0);
+  sincospif(2.f * u01_open(r.w), &s1, &c1);
+  z[0] = r0 * c0;
+  z[1] = r0 * s0;
+  z[2] = r1 * c1;
+  z[3] = r1 * s1;
+}
+
+// out[(k*per + j)*D + d] = means[k*D + d] + sd * z
+__global__ void sample_iso_kernel(const float* __restrict__ means, int64_t K, int D, int64_t per, float sd,
+                                  uint64_t seed, uint64_t offset, float* __restrict__ out) {
+  const int64_t total = K * per * D;
+  const int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;  // group of 4 outputs
+  if (q * 4 >= total) return;
+  float z[4];
+  normal4(static_cast<uint64_t>(q) + offset, seed, z);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t e = q * 4 + i;
+    if (e < total) {
+      const int64_t row = e / D;
+      const int d = static_cast<int>(e % D);
+      out[e] = fmaf(sd, z[i], means[(row / per) * D + d]);
+    }
+  }
+}
+
+__global__ void uniform_box_kernel(const float* __restrict__ lo, const float* __restrict__ hi, int D, int64_t n,
+                                   uint64_t seed, uint64_t offset, float* __restrict__ out) {
+  const int64_t total = n * D;
+  const int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (q * 4 >= total) return;
+  const uint64_t counter = static_cast<uint64_t>(q) + offset;
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(counter), static_cast<uint32_t>(counter >> 32), 1u, 0u),
+                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  const uint32_t rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t e = q * 4 + i;
+    if (e < total) {
+      const int d = static_cast<int>(e % D);
+      out[e] = fmaf(hi[d] - lo[d], u01_open(rv[i]), lo[d]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Peak micro-benchmarks: 8 independent dependent-chains per thread, no memory traffic
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) peak_fma_kernel(int64_t iters, float* sink) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 0.001f * (threadIdx.x + i);
+  const float m = 0.999999f, c = 1.0e-7f;
+  for (int64_t it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], m, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == 123456.789f) sink[0] = s;  // never true; keeps the chains alive
+}
+
+__global__ void __launch_bounds__(256) peak_ex2_kernel(int64_t iters, float* sink) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 0.1f + 0.001f * (threadIdx.x + i);
+  for (int64_t it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = ex2(-a[i]);  // contraction towards ~0.641; stays in (0.5, 1]
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == 123456.789f) sink[0] = s;
+}
+
+template <int DP>
+static int launch_box(const float* x, int64_t n, int D, const float* lo, const float* hi, const float* lwv, int64_t K,
+                      int open_upper, float* out, cudaStream_t st) {
+  box_mixture_kernel<DP><<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(x, n, D, lo, hi, lwv, K, open_upper, out);
+  AISB_LAUNCH_CHECK("box_mixture_kernel");
+  return AISB_OK;
+}
+
+}  // namespace aisb
+
+using namespace aisb;
+
+extern "C" int aisb_box_mixture_logpdf_f32(const float* d_x, int64_t n, int32_t D, const float* d_lo,
+                                           const float* d_hi, const float* d_logw_over_vol, int64_t K,
+                                           int32_t open_upper, float* d_out_logp, void* stream) {
+  const int DP = aisb_padded_dims(D);
+  if (DP == 0 || DP > 32 || n < 0 || K < 1 || !d_lo || !d_hi || !d_logw_over_vol || (n > 0 && (!d_x || !d_out_logp))) {
+    set_error("box_mixture_logpdf: invalid argument (n=%lld K=%lld D=%d; D <= 32)", static_cast<long long>(n),
+              static_cast<long long>(K), D);
+    return AISB_ERR_INVALID;
+  }
+  if (n == 0) return AISB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (DP) {
+    case 1: return launch_box<1>(d_x, n, D, d_lo, d_hi, d_logw_over_vol, K, open_upper, d_out_logp, st);
+    case 2: return launch_box<2>(d_x, n, D, d_lo, d_hi, d_logw_over_vol, K, open_upper, d_out_logp, st);
+    case 4: return launch_box<4>(d_x, n, D, d_lo, d_hi, d_logw_over_vol, K, open_upper, d_out_logp, st);
+    case 8: return launch_box<8>(d_x, n, D, d_lo, d_hi, d_logw_over_vol, K, open_upper, d_out_logp, st);
+    case 16: return launch_box<16>(d_x, n, D, d_lo, d_hi, d_logw_over_vol, K, open_upper, d_out_logp, st);
+    default: return launch_box<32>(d_x, n, D, d_lo, d_hi, d_logw_over_vol, K, open_upper, d_out_logp, st);
+  }
+}
+
+extern "C" int aisb_sample_iso_f32(const float* d_means, int64_t K, int32_t D, int64_t per, double var, uint64_t seed,
+                                   uint64_t offset, float* d_out, void* stream) {
+  if (!d_means || !d_out || K < 1 || per < 0 || D < 1 || D > AISB_MAX_DIMS || !(var >= 0.0)) {
+    set_error("sample_iso: invalid argument");
+    return AISB_ERR_INVALID;
+  }
+  const int64_t total = K * per * D;
+  if (total == 0) return AISB_OK;
+  const int64_t groups = (total + 3) / 4;
+  sample_iso_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_means, K, D, per, static_cast<float>(sqrt(var)), seed, offset, d_out);
+  AISB_LAUNCH_CHECK("sample_iso_kernel");
+  return AISB_OK;
+}
+
+extern "C" int aisb_uniform_box_f32(const float* d_lo, const float* d_hi, int32_t D, int64_t n, uint64_t seed,
+                                    uint64_t offset, float* d_out, void* stream) {
+  if (!d_lo || !d_hi || !d_out || n < 0 || D < 1 || D > AISB_MAX_DIMS) {
+    set_error("uniform_box: invalid argument");
+    return AISB_ERR_INVALID;
+  }
+  const int64_t total = n * D;
+  if (total == 0) return AISB_OK;
+  const int64_t groups = (total + 3) / 4;
+  uniform_box_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_lo, d_hi, D, n, seed, offset, d_out);
+  AISB_LAUNCH_CHECK("uniform_box_kernel");
+  return AISB_OK;
+}
+
+static int peak_launch(void (*kern)(int64_t, float*), int64_t iters, float* d_sink, double* ops, void* stream) {
+  if (iters < 1 || !d_sink) {
+    set_error("peak: invalid argument");
+    return AISB_ERR_INVALID;
+  }
+  const int blocks = sm_count() * 8;
+  kern<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(iters, d_sink);
+  AISB_LAUNCH_CHECK("peak kernel");
+  if (ops) *ops = static_cast<double>(blocks) * 256.0 * static_cast<double>(iters) * 32.0;
+  return AISB_OK;
+}
+
+extern "C" int aisb_peak_fma_f32(int64_t iters, float* d_sink, double* ops, void* stream) {
+  return peak_launch(peak_fma_kernel, iters, d_sink, ops, stream);
+}
+extern "C" int aisb_peak_ex2_f32(int64_t iters, float* d_sink, double* ops, void* stream) {
+  return peak_launch(peak_ex2_kernel, iters, d_sink, ops, stream);
+}

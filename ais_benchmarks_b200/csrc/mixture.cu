@@ -1,0 +1,517 @@
+// Mixture log-density and fused DM-weight kernels + their C-ABI entry points.
+#include "pairwise.cuh"
+#include "reduce.cuh"
+
+namespace aisb {
+
+struct PassArgs {
+  const float* rows;
+  const float* offs;
+  int64_t KP;
+  float a_iso;
+  float uniform_offset;
+};
+
+// ---------------------------------------------------------------------------------------------
+// logp[i] = log sum_k w_k N(x_i; mu_k, Sigma_k)
+// grid.x = ntiles * nsplit; CTA b handles point tile (b % ntiles) against component range
+// split (b / ntiles). With nsplit > 1 the (m, S) partials go to the workspace and
+// lse_merge_kernel finishes.
+// ---------------------------------------------------------------------------------------------
+template <int KIND, int DP, bool HAS_C>
+__global__ void __launch_bounds__(kThreads)
+    logpdf_kernel(const float* __restrict__ x, int64_t n, int D, int vec_ok, PassArgs mix, int nsplit,
+                  int64_t comps_per_split, int64_t ntiles, float* __restrict__ out, float* __restrict__ ws_m,
+                  float* __restrict__ ws_S) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bars[kStages];
+  constexpr int E = points_per_thread(DP);
+
+  const int64_t tile = blockIdx.x % ntiles;
+  const int64_t split = blockIdx.x / ntiles;
+  ring_init(bars);
+
+  float xr[E][DP];
+  int64_t pidx[E];
+  load_points<DP, E>(x, n, D, vec_ok, tile * (kThreads * E), xr, pidx);
+
+  float m[E], S[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    m[e] = kNegBig;
+    S[e] = 0.f;
+  }
+  const int64_t k_begin = split * comps_per_split;
+  const int64_t k_end = k_begin + comps_per_split < mix.KP ? k_begin + comps_per_split : mix.KP;
+  uint32_t it = 0;
+  mixture_pass<KIND, DP, E, HAS_C>(mix.rows, mix.offs, k_begin, k_end, mix.a_iso, smem, bars, it, xr, m, S);
+
+  if (nsplit == 1) {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (pidx[e] < n) out[pidx[e]] = lse_finish(m[e], S[e]) + (HAS_C ? 0.f : mix.uniform_offset);
+  } else {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (pidx[e] < n) {
+        ws_m[split * n + pidx[e]] = m[e];
+        ws_S[split * n + pidx[e]] = S[e];
+      }
+  }
+}
+
+__global__ void lse_merge_kernel(const float* __restrict__ ws_m, const float* __restrict__ ws_S, int nsplit, int64_t n,
+                                 float add, float* __restrict__ out) {
+  const int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (p >= n) return;
+  float M = kNegBig;
+  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, ws_m[s * n + p]);
+  float S = 0.f;
+  for (int s = 0; s < nsplit; ++s) S += ws_S[s * n + p] * ex2(ws_m[s * n + p] - M);
+  out[p] = lse_finish(M, S) + add;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused DM weights: both mixtures evaluated against the register-resident points in one launch.
+// Target is packed DIAG with offsets (or absent: logp read from memory); proposals ISO/DIAG.
+// ---------------------------------------------------------------------------------------------
+template <int DP, int KIND_Q, bool HAS_C_Q>
+__global__ void __launch_bounds__(kThreads)
+    dm_weights_kernel(const float* __restrict__ x, int64_t n, int D, int vec_ok, PassArgs tgt,
+                      const float* __restrict__ logp_in, PassArgs prop, float* __restrict__ out_logw,
+                      float* __restrict__ out_logp, float* __restrict__ out_logq, double* __restrict__ block_partials) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bars[kStages];
+  __shared__ float red[kThreads / 32 * 4];
+  constexpr int E = points_per_thread(DP);
+
+  ring_init(bars);
+  float xr[E][DP];
+  int64_t pidx[E];
+  load_points<DP, E>(x, n, D, vec_ok, static_cast<int64_t>(blockIdx.x) * (kThreads * E), xr, pidx);
+
+  float m[E], S[E], logp[E], logq[E];
+  uint32_t it = 0;
+  if (tgt.rows != nullptr) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      m[e] = kNegBig;
+      S[e] = 0.f;
+    }
+    mixture_pass<AISB_COV_DIAG, DP, E, true>(tgt.rows, tgt.offs, 0, tgt.KP, 0.f, smem, bars, it, xr, m, S);
+#pragma unroll
+    for (int e = 0; e < E; ++e) logp[e] = lse_finish(m[e], S[e]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < E; ++e) logp[e] = pidx[e] < n ? __ldg(logp_in + pidx[e]) : 0.f;
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    m[e] = kNegBig;
+    S[e] = 0.f;
+  }
+  mixture_pass<KIND_Q, DP, E, HAS_C_Q>(prop.rows, prop.offs, 0, prop.KP, prop.a_iso, smem, bars, it, xr, m, S);
+
+  float lw[E];
+  bool ok[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    logq[e] = lse_finish(m[e], S[e]) + (HAS_C_Q ? 0.f : prop.uniform_offset);
+    lw[e] = logp[e] - logq[e];
+    const bool in = pidx[e] < n;
+    ok[e] = in && (lw[e] == lw[e]) && (lw[e] != INFINITY);
+    if (in) {
+      out_logw[pidx[e]] = lw[e];
+      if (out_logp) out_logp[pidx[e]] = logp[e];
+      if (out_logq) out_logq[pidx[e]] = logq[e];
+    }
+  }
+  block_weight_partials<E, kThreads>(lw, ok, red, block_partials + 4 * static_cast<int64_t>(blockIdx.x));
+}
+
+// logw = logp - logq on vectors + block partials (unfused fall-back path of aisb_dm_weights_f32)
+__global__ void __launch_bounds__(256) logw_combine_kernel(const float* __restrict__ logp, const float* __restrict__ logq,
+                                                           int64_t n, float* __restrict__ out_logw,
+                                                           double* __restrict__ block_partials) {
+  __shared__ float red[256 / 32 * 4];
+  constexpr int E = 8;
+  float lw[E];
+  bool ok[E];
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * (256 * E);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int64_t p = base + e * 256 + threadIdx.x;
+    const bool in = p < n;
+    lw[e] = in ? logp[p] - logq[p] : 0.f;
+    ok[e] = in && (lw[e] == lw[e]) && (lw[e] != INFINITY);
+    if (in) out_logw[p] = lw[e];
+  }
+  block_weight_partials<E, 256>(lw, ok, red, block_partials + 4 * static_cast<int64_t>(blockIdx.x));
+}
+
+// ---------------------------------------------------------------------------------------------
+// KDE pack: rows[j][d] = -a * samples[idx[j]][d], pad dims 0, pad components 1e18
+// ---------------------------------------------------------------------------------------------
+__global__ void kde_pack_kernel(const float* __restrict__ samples, int64_t n, int D, int DP,
+                                const int64_t* __restrict__ idx, int64_t n_c, int64_t KP, float a,
+                                float* __restrict__ rows) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= KP * DP) return;
+  const int64_t j = i / DP;
+  const int d = static_cast<int>(i % DP);
+  float v;
+  if (j >= n_c) {
+    v = 1.0e18f;
+  } else if (d >= D) {
+    v = 0.f;
+  } else {
+    int64_t src = idx ? idx[j] : j;
+    src = src < 0 ? 0 : (src >= n ? n - 1 : src);
+    v = -a * samples[src * D + d];
+  }
+  rows[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side planning and dispatch
+// ---------------------------------------------------------------------------------------------
+struct Plan {
+  int DP, E;
+  int64_t KP, ntiles, comps_per_split;
+  int nsplit;
+};
+
+static bool make_plan(int64_t n, int64_t K, int D, Plan* p) {
+  p->DP = aisb_padded_dims(D);
+  if (p->DP == 0 || n < 0 || K < 1) return false;
+  p->E = points_per_thread(p->DP);
+  p->KP = aisb_padded_components(K);
+  const int64_t tile_pts = static_cast<int64_t>(kThreads) * p->E;
+  p->ntiles = n > 0 ? (n + tile_pts - 1) / tile_pts : 0;
+  // Split the component range when the point tiles alone cannot fill ~32 waves of CTAs
+  // (4 resident CTAs per SM); keep >= 1024 components per split.
+  const int64_t target = static_cast<int64_t>(sm_count()) * 4 * 32;
+  int64_t max_split = p->KP / 1024;
+  if (max_split < 1) max_split = 1;
+  int64_t want = p->ntiles > 0 ? (target + p->ntiles - 1) / p->ntiles : 1;
+  if (want > max_split) want = max_split;
+  if (want < 1) want = 1;
+  const int64_t units = p->KP / AISB_COMP_ALIGN;
+  const int64_t units_per_split = (units + want - 1) / want;
+  p->comps_per_split = units_per_split * AISB_COMP_ALIGN;
+  p->nsplit = static_cast<int>((p->KP + p->comps_per_split - 1) / p->comps_per_split);
+  return true;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+  float* ws_m;
+  float* ws_S;
+  float* tmp_p;
+  float* tmp_q;
+  double* block_partials;
+  size_t bytes;
+};
+
+static void carve(void* base, int64_t n, int nsplit, int64_t nblocks, Workspace* w) {
+  size_t off = 0;
+  char* b = static_cast<char*>(base);
+  auto take = [&](size_t bytes) {
+    void* ptr = b ? b + off : nullptr;
+    off += align_up(bytes, 256);
+    return ptr;
+  };
+  w->ws_m = static_cast<float*>(take(sizeof(float) * n * nsplit));
+  w->ws_S = static_cast<float*>(take(sizeof(float) * n * nsplit));
+  w->tmp_p = static_cast<float*>(take(sizeof(float) * n));
+  w->tmp_q = static_cast<float*>(take(sizeof(float) * n));
+  w->block_partials = static_cast<double*>(take(sizeof(double) * 8 * (nblocks + 1)));
+  w->bytes = off;
+}
+
+static int64_t reduce_blocks(int64_t n) { return (n + 2047) / 2048; }
+
+using LogpdfFn = void (*)(const float*, int64_t, int, int, PassArgs, int, int64_t, int64_t, float*, float*, float*);
+using DmFn = void (*)(const float*, int64_t, int, int, PassArgs, const float*, PassArgs, float*, float*, float*,
+                      double*);
+
+template <int KIND, int DP, bool HAS_C>
+static int launch_logpdf_t(const float* x, int64_t n, int D, int vec_ok, const PassArgs& mix, const Plan& plan,
+                           float* out, const Workspace& ws, cudaStream_t st) {
+  constexpr size_t smem = pass_smem_bytes(KIND, DP, HAS_C);
+  const int64_t grid = plan.ntiles * plan.nsplit;
+  logpdf_kernel<KIND, DP, HAS_C><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(
+      x, n, D, vec_ok, mix, plan.nsplit, plan.comps_per_split, plan.ntiles, out, ws.ws_m, ws.ws_S);
+  AISB_LAUNCH_CHECK("logpdf_kernel");
+  if (plan.nsplit > 1) {
+    lse_merge_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ws.ws_m, ws.ws_S, plan.nsplit, n,
+                                                                             HAS_C ? 0.f : mix.uniform_offset, out);
+    AISB_LAUNCH_CHECK("lse_merge_kernel");
+  }
+  return AISB_OK;
+}
+
+template <int KIND, bool HAS_C>
+static int launch_logpdf_dp(int DP, const float* x, int64_t n, int D, int vec_ok, const PassArgs& mix,
+                            const Plan& plan, float* out, const Workspace& ws, cudaStream_t st) {
+  switch (DP) {
+    case 1: return launch_logpdf_t<KIND, 1, HAS_C>(x, n, D, vec_ok, mix, plan, out, ws, st);
+    case 2: return launch_logpdf_t<KIND, 2, HAS_C>(x, n, D, vec_ok, mix, plan, out, ws, st);
+    case 4: return launch_logpdf_t<KIND, 4, HAS_C>(x, n, D, vec_ok, mix, plan, out, ws, st);
+    case 8: return launch_logpdf_t<KIND, 8, HAS_C>(x, n, D, vec_ok, mix, plan, out, ws, st);
+    case 16: return launch_logpdf_t<KIND, 16, HAS_C>(x, n, D, vec_ok, mix, plan, out, ws, st);
+    case 32: return launch_logpdf_t<KIND, 32, HAS_C>(x, n, D, vec_ok, mix, plan, out, ws, st);
+    case 64:
+      if constexpr (KIND != AISB_COV_FULL) return launch_logpdf_t<KIND, 64, HAS_C>(x, n, D, vec_ok, mix, plan, out, ws, st);
+      break;
+    default: break;
+  }
+  set_error("mixture_logpdf: unsupported (cov_kind=%d, D=%d)", KIND, D);
+  return AISB_ERR_UNSUPPORTED;
+}
+
+static int check_mixture(const aisb_packed_mixture* mix, const char* who) {
+  if (!mix || !mix->d_rows) {
+    set_error("%s: null mixture", who);
+    return AISB_ERR_INVALID;
+  }
+  if (mix->D < 1 || mix->D > AISB_MAX_DIMS || mix->K < 1) {
+    set_error("%s: bad mixture shape K=%lld D=%d", who, static_cast<long long>(mix->K), mix->D);
+    return AISB_ERR_INVALID;
+  }
+  if (mix->cov_kind != AISB_COV_ISO_SHARED && !mix->d_offsets) {
+    set_error("%s: offsets are required for cov_kind %d", who, mix->cov_kind);
+    return AISB_ERR_INVALID;
+  }
+  if (mix->cov_kind == AISB_COV_FULL && mix->D > 32) {
+    set_error("%s: full covariance is limited to D <= 32 (got %d)", who, mix->D);
+    return AISB_ERR_UNSUPPORTED;
+  }
+  if (reinterpret_cast<uintptr_t>(mix->d_rows) % 16 || reinterpret_cast<uintptr_t>(mix->d_offsets) % 16) {
+    set_error("%s: packed buffers must be 16-byte aligned", who);
+    return AISB_ERR_INVALID;
+  }
+  return AISB_OK;
+}
+
+static PassArgs pass_args(const aisb_packed_mixture* mix) {
+  PassArgs a;
+  a.rows = mix->d_rows;
+  a.offs = mix->d_offsets;
+  a.KP = aisb_padded_components(mix->K);
+  a.a_iso = mix->iso_scale;
+  a.uniform_offset = mix->uniform_offset;
+  return a;
+}
+
+static int vec_ok_for(const float* x, int D) {
+  const int DP = aisb_padded_dims(D);
+  if (D != DP) return 0;
+  if (DP >= 4) return reinterpret_cast<uintptr_t>(x) % 16 == 0;
+  if (DP == 2) return reinterpret_cast<uintptr_t>(x) % 8 == 0;
+  return 0;
+}
+
+static int run_logpdf(const float* x, int64_t n, const aisb_packed_mixture* mix, float* out, const Plan& plan,
+                      const Workspace& ws, cudaStream_t st) {
+  const PassArgs a = pass_args(mix);
+  const int vec_ok = vec_ok_for(x, mix->D);
+  switch (mix->cov_kind) {
+    case AISB_COV_ISO_SHARED:
+      if (mix->d_offsets) return launch_logpdf_dp<AISB_COV_ISO_SHARED, true>(plan.DP, x, n, mix->D, vec_ok, a, plan, out, ws, st);
+      return launch_logpdf_dp<AISB_COV_ISO_SHARED, false>(plan.DP, x, n, mix->D, vec_ok, a, plan, out, ws, st);
+    case AISB_COV_DIAG:
+      return launch_logpdf_dp<AISB_COV_DIAG, true>(plan.DP, x, n, mix->D, vec_ok, a, plan, out, ws, st);
+    case AISB_COV_FULL:
+      return launch_logpdf_dp<AISB_COV_FULL, true>(plan.DP, x, n, mix->D, vec_ok, a, plan, out, ws, st);
+    default: break;
+  }
+  set_error("mixture_logpdf: unknown cov_kind %d", mix->cov_kind);
+  return AISB_ERR_INVALID;
+}
+
+template <int DP, int KIND_Q, bool HAS_C_Q>
+static int launch_dm_t(const float* x, int64_t n, int D, int vec_ok, const PassArgs& tgt, const float* logp_in,
+                       const PassArgs& prop, float* lw, float* lp, float* lq, double* bp, int64_t ntiles,
+                       cudaStream_t st) {
+  constexpr size_t s1 = pass_smem_bytes(AISB_COV_DIAG, DP, true);
+  constexpr size_t s2 = pass_smem_bytes(KIND_Q, DP, HAS_C_Q);
+  constexpr size_t smem = s1 > s2 ? s1 : s2;
+  dm_weights_kernel<DP, KIND_Q, HAS_C_Q>
+      <<<static_cast<unsigned>(ntiles), kThreads, smem, st>>>(x, n, D, vec_ok, tgt, logp_in, prop, lw, lp, lq, bp);
+  AISB_LAUNCH_CHECK("dm_weights_kernel");
+  return AISB_OK;
+}
+
+template <int KIND_Q, bool HAS_C_Q>
+static int launch_dm_dp(int DP, const float* x, int64_t n, int D, int vec_ok, const PassArgs& tgt,
+                        const float* logp_in, const PassArgs& prop, float* lw, float* lp, float* lq, double* bp,
+                        int64_t ntiles, cudaStream_t st) {
+  switch (DP) {
+    case 1: return launch_dm_t<1, KIND_Q, HAS_C_Q>(x, n, D, vec_ok, tgt, logp_in, prop, lw, lp, lq, bp, ntiles, st);
+    case 2: return launch_dm_t<2, KIND_Q, HAS_C_Q>(x, n, D, vec_ok, tgt, logp_in, prop, lw, lp, lq, bp, ntiles, st);
+    case 4: return launch_dm_t<4, KIND_Q, HAS_C_Q>(x, n, D, vec_ok, tgt, logp_in, prop, lw, lp, lq, bp, ntiles, st);
+    case 8: return launch_dm_t<8, KIND_Q, HAS_C_Q>(x, n, D, vec_ok, tgt, logp_in, prop, lw, lp, lq, bp, ntiles, st);
+    case 16: return launch_dm_t<16, KIND_Q, HAS_C_Q>(x, n, D, vec_ok, tgt, logp_in, prop, lw, lp, lq, bp, ntiles, st);
+    case 32: return launch_dm_t<32, KIND_Q, HAS_C_Q>(x, n, D, vec_ok, tgt, logp_in, prop, lw, lp, lq, bp, ntiles, st);
+    case 64: return launch_dm_t<64, KIND_Q, HAS_C_Q>(x, n, D, vec_ok, tgt, logp_in, prop, lw, lp, lq, bp, ntiles, st);
+    default: break;
+  }
+  set_error("dm_weights: unsupported D=%d", D);
+  return AISB_ERR_UNSUPPORTED;
+}
+
+}  // namespace aisb
+
+using namespace aisb;
+
+extern "C" int aisb_workspace_bytes(int64_t n, int64_t K, int32_t D, size_t* bytes) {
+  if (!bytes) {
+    set_error("workspace_bytes: null output");
+    return AISB_ERR_INVALID;
+  }
+  Plan plan;
+  if (!make_plan(n, K, D, &plan)) {
+    set_error("workspace_bytes: bad shape n=%lld K=%lld D=%d", static_cast<long long>(n), static_cast<long long>(K), D);
+    return AISB_ERR_INVALID;
+  }
+  Workspace w;
+  const int64_t nblocks = plan.ntiles > reduce_blocks(n) ? plan.ntiles : reduce_blocks(n);
+  carve(nullptr, n, plan.nsplit, nblocks, &w);
+  *bytes = w.bytes + 256;
+  return AISB_OK;
+}
+
+static int carve_checked(void* d_ws, size_t ws_bytes, int64_t n, const Plan& plan, Workspace* w, const char* who) {
+  const int64_t nblocks = plan.ntiles > reduce_blocks(n) ? plan.ntiles : reduce_blocks(n);
+  char* base = static_cast<char*>(d_ws);
+  const size_t mis = base ? (256 - reinterpret_cast<uintptr_t>(base) % 256) % 256 : 0;
+  carve(base ? base + mis : nullptr, n, plan.nsplit, nblocks, w);
+  if (!base || w->bytes + mis > ws_bytes) {
+    set_error("%s: workspace too small (%zu < %zu bytes)", who, ws_bytes, w->bytes + mis);
+    return AISB_ERR_WORKSPACE;
+  }
+  return AISB_OK;
+}
+
+extern "C" int aisb_mixture_logpdf_f32(const float* d_x, int64_t n, const aisb_packed_mixture* mix, float* d_out_logp,
+                                       void* d_workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_mixture(mix, "mixture_logpdf");
+  if (rc) return rc;
+  if (n == 0) return AISB_OK;
+  if (!d_x || !d_out_logp || n < 0) {
+    set_error("mixture_logpdf: null pointer or negative n");
+    return AISB_ERR_INVALID;
+  }
+  Plan plan;
+  if (!make_plan(n, mix->K, mix->D, &plan)) {
+    set_error("mixture_logpdf: unsupported D=%d", mix->D);
+    return AISB_ERR_UNSUPPORTED;
+  }
+  Workspace ws{};
+  if (plan.nsplit > 1) {
+    rc = carve_checked(d_workspace, workspace_bytes, n, plan, &ws, "mixture_logpdf");
+    if (rc) return rc;
+  }
+  return run_logpdf(d_x, n, mix, d_out_logp, plan, ws, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int aisb_dm_weights_f32(const float* d_x, int64_t n, const aisb_packed_mixture* target,
+                                   const float* d_logp_in, const aisb_packed_mixture* proposals, float* d_out_logw,
+                                   float* d_out_logp, float* d_out_logq, double* d_out_partials, void* d_workspace,
+                                   size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = check_mixture(proposals, "dm_weights(proposals)");
+  if (rc) return rc;
+  if (target) {
+    rc = check_mixture(target, "dm_weights(target)");
+    if (rc) return rc;
+    if (target->D != proposals->D) {
+      set_error("dm_weights: target D=%d != proposal D=%d", target->D, proposals->D);
+      return AISB_ERR_INVALID;
+    }
+  } else if (!d_logp_in) {
+    set_error("dm_weights: need a target mixture or d_logp_in");
+    return AISB_ERR_INVALID;
+  }
+  if (!d_out_partials || n < 0 || (n > 0 && (!d_x || !d_out_logw))) {
+    set_error("dm_weights: null pointer or negative n");
+    return AISB_ERR_INVALID;
+  }
+  if (n == 0) {
+    const double empty[4] = {static_cast<double>(kNegBig), 0.0, 0.0, 0.0};
+    AISB_CUDA_CHECK(cudaMemcpyAsync(d_out_partials, empty, sizeof(empty), cudaMemcpyHostToDevice, st));
+    AISB_CUDA_CHECK(cudaStreamSynchronize(st));  // `empty` is a stack buffer
+    return AISB_OK;
+  }
+  Plan plan_q, plan_t;
+  if (!make_plan(n, proposals->K, proposals->D, &plan_q)) {
+    set_error("dm_weights: unsupported D=%d", proposals->D);
+    return AISB_ERR_UNSUPPORTED;
+  }
+  plan_t = plan_q;
+  if (target) make_plan(n, target->K, target->D, &plan_t);
+  Plan plan_ws = plan_q.nsplit >= plan_t.nsplit ? plan_q : plan_t;
+  Workspace ws{};
+  rc = carve_checked(d_workspace, workspace_bytes, n, plan_ws, &ws, "dm_weights");
+  if (rc) return rc;
+
+  const int D = proposals->D;
+  const int vec_ok = vec_ok_for(d_x, D);
+  const bool fusable = plan_q.nsplit == 1 && plan_t.nsplit == 1 && proposals->cov_kind != AISB_COV_FULL &&
+                       (!target || target->cov_kind == AISB_COV_DIAG);
+  int64_t nblocks;
+  if (fusable) {
+    PassArgs t{};
+    if (target) t = pass_args(target);
+    const PassArgs q = pass_args(proposals);
+    nblocks = plan_q.ntiles;
+    if (proposals->cov_kind == AISB_COV_DIAG)
+      rc = launch_dm_dp<AISB_COV_DIAG, true>(plan_q.DP, d_x, n, D, vec_ok, t, d_logp_in, q, d_out_logw, d_out_logp,
+                                             d_out_logq, ws.block_partials, nblocks, st);
+    else if (proposals->d_offsets)
+      rc = launch_dm_dp<AISB_COV_ISO_SHARED, true>(plan_q.DP, d_x, n, D, vec_ok, t, d_logp_in, q, d_out_logw,
+                                                   d_out_logp, d_out_logq, ws.block_partials, nblocks, st);
+    else
+      rc = launch_dm_dp<AISB_COV_ISO_SHARED, false>(plan_q.DP, d_x, n, D, vec_ok, t, d_logp_in, q, d_out_logw,
+                                                    d_out_logp, d_out_logq, ws.block_partials, nblocks, st);
+    if (rc) return rc;
+  } else {
+    const float* lp = d_logp_in;
+    if (target) {
+      float* lp_out = d_out_logp ? d_out_logp : ws.tmp_p;
+      rc = run_logpdf(d_x, n, target, lp_out, plan_t, ws, st);
+      if (rc) return rc;
+      lp = lp_out;
+    } else if (d_out_logp) {
+      AISB_CUDA_CHECK(cudaMemcpyAsync(d_out_logp, d_logp_in, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+    }
+    float* lq = d_out_logq ? d_out_logq : ws.tmp_q;
+    rc = run_logpdf(d_x, n, proposals, lq, plan_q, ws, st);
+    if (rc) return rc;
+    nblocks = reduce_blocks(n);
+    logw_combine_kernel<<<static_cast<unsigned>(nblocks), 256, 0, st>>>(lp, lq, n, d_out_logw, ws.block_partials);
+    AISB_LAUNCH_CHECK("logw_combine_kernel");
+  }
+  weight_partials_merge_kernel<<<1, 256, 0, st>>>(ws.block_partials, nblocks, d_out_partials);
+  AISB_LAUNCH_CHECK("weight_partials_merge_kernel");
+  return AISB_OK;
+}
+
+extern "C" int aisb_kde_pack_f32(const float* d_samples, int64_t n, int32_t D, const int64_t* d_idx, int64_t n_c,
+                                 double bw, float* d_rows, void* stream) {
+  const int DP = aisb_padded_dims(D);
+  if (!d_samples || !d_rows || n < 1 || n_c < 1 || DP == 0 || !(bw > 0.0) || (!d_idx && n_c > n)) {
+    set_error("kde_pack: invalid argument (n=%lld n_c=%lld D=%d bw=%g)", static_cast<long long>(n),
+              static_cast<long long>(n_c), D, bw);
+    return AISB_ERR_INVALID;
+  }
+  const int64_t KP = aisb_padded_components(n_c);
+  const float a = static_cast<float>(sqrt(kLog2e / (2.0 * bw)));
+  const int64_t total = KP * DP;
+  kde_pack_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_samples, n, D, DP, d_idx, n_c, KP, a, d_rows);
+  AISB_LAUNCH_CHECK("kde_pack_kernel");
+  return AISB_OK;
+}

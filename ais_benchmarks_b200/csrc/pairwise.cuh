@@ -1,0 +1,292 @@
+// Pairwise (points x Gaussian components) online log-sum-exp: the arithmetic core of
+// CMixtureModel.log_prob (reference distributions/mixture/CMixtureModel.py:43-57), the
+// KDE evaluation (sampling_methods/base.py:156-179) and the DM weights (dm_ais.py:72-76).
+//
+// Work decomposition
+//   * a CTA of 128 threads owns a tile of 128*E points; every thread keeps its E points in
+//     registers for the whole kernel (E*DP floats),
+//   * component parameters stream through shared memory in chunks of J components, staged by
+//     1-D TMA bulk copies (cp.async.bulk -> UBLKCP) into a 2-deep mbarrier ring,
+//   * all lanes of a warp read the SAME component (LDS broadcast) and evaluate it against
+//     their own points; JJ components are evaluated per online-LSE step so that the running
+//     max / rescale costs one extra MUFU per JJ pairs,
+//   * everything is carried in the log2 domain: t = c_k - ||A_k x + b_k||^2, accumulated as an
+//     FFMA chain seeded with c_k, then S += ex2(t - m).
+//
+// Instruction budget per (point, component) pair, ISO/DIAG kinds: 2*DP FFMA + (1 FMNMX + 1 FADD
+// + 1 MUFU.EX2 + 1 FADD) + (2 MUFU-related)/JJ.
+#pragma once
+#include "common.cuh"
+
+namespace aisb {
+
+// ---------------------------------------------------------------------------------------------
+// Compile-time tiling traits
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int points_per_thread(int DP) { return DP <= 16 ? 4 : (DP == 32 ? 2 : 1); }
+
+__host__ __device__ constexpr int comps_per_step(int kind, int DP) {
+  return kind == AISB_COV_FULL ? (DP <= 8 ? 4 : (DP == 16 ? 2 : 1)) : (DP <= 8 ? 8 : (DP <= 32 ? 4 : 8));
+}
+
+__host__ __device__ constexpr int pow2_floor(int v) {
+  int p = 1;
+  while (2 * p <= v) p *= 2;
+  return p;
+}
+
+// components per shared-memory chunk: ~16 KB of rows, a power of two in [max(JJ,4), 256]
+__host__ __device__ constexpr int chunk_comps(int kind, int DP) {
+  const int jj = comps_per_step(kind, DP) < 4 ? 4 : comps_per_step(kind, DP);
+  const int fit = pow2_floor(16384 / (row_floats(kind, DP) * 4) > 0 ? 16384 / (row_floats(kind, DP) * 4) : 1);
+  return fit < jj ? jj : (fit > 256 ? 256 : fit);
+}
+
+__host__ __device__ constexpr int stage_floats(int kind, int DP, bool has_c) {
+  return chunk_comps(kind, DP) * row_floats(kind, DP) + (has_c ? chunk_comps(kind, DP) : 0);
+}
+
+constexpr int kStages = 2;
+
+__host__ __device__ constexpr size_t pass_smem_bytes(int kind, int DP, bool has_c) {
+  return size_t(kStages) * stage_floats(kind, DP, has_c) * sizeof(float);
+}
+
+#ifdef __CUDACC__
+
+// ---------------------------------------------------------------------------------------------
+// Shared-memory vector loads (all lanes read the same address -> broadcast)
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void lds_vec(const float* __restrict__ p, float (&v)[N]) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+      const float4 f = reinterpret_cast<const float4*>(p)[q];
+      v[4 * q + 0] = f.x;
+      v[4 * q + 1] = f.y;
+      v[4 * q + 2] = f.z;
+      v[4 * q + 3] = f.w;
+    }
+  } else if constexpr (N == 2) {
+    const float2 f = *reinterpret_cast<const float2*>(p);
+    v[0] = f.x;
+    v[1] = f.y;
+  } else {
+#pragma unroll
+    for (int q = 0; q < N; ++q) v[q] = p[q];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One component against E register-resident points: t[e] = c - ||A x_e + b||^2   (log2 domain)
+// ---------------------------------------------------------------------------------------------
+template <int KIND, int DP, int E>
+__device__ __forceinline__ void comp_eval(const float* __restrict__ row, float c, float a_iso,
+                                          const float (&x)[E][DP], float (&t)[E]) {
+  if constexpr (KIND == AISB_COV_ISO_SHARED) {
+    float b[DP];
+    lds_vec<DP>(row, b);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      float acc = c;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) {
+        const float dl = fmaf(x[e][d], a_iso, b[d]);
+        acc = fmaf(-dl, dl, acc);
+      }
+      t[e] = acc;
+    }
+  } else if constexpr (KIND == AISB_COV_DIAG) {
+    float a[DP], b[DP];
+    lds_vec<DP>(row, a);
+    lds_vec<DP>(row + DP, b);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      float acc = c;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) {
+        const float dl = fmaf(x[e][d], a[d], b[d]);
+        acc = fmaf(-dl, dl, acc);
+      }
+      t[e] = acc;
+    }
+  } else {  // FULL: z = A x + b with A lower triangular (row-major packed), t = c - ||z||^2
+    constexpr int TRI = DP * (DP + 1) / 2;
+    float acc[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = c;
+    int idx = 0;
+#pragma unroll
+    for (int r = 0; r < DP; ++r) {
+      float z[E];
+      const float br = row[TRI + r];
+#pragma unroll
+      for (int e = 0; e < E; ++e) z[e] = br;
+#pragma unroll
+      for (int cc = 0; cc <= r; ++cc) {
+        const float a = row[idx++];
+#pragma unroll
+        for (int e = 0; e < E; ++e) z[e] = fmaf(a, x[e][cc], z[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[e] = fmaf(-z[e], z[e], acc[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) t[e] = acc[e];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Online LSE over `cnt` staged components (cnt is a multiple of JJ)
+// ---------------------------------------------------------------------------------------------
+template <int KIND, int DP, int E, int JJ, bool HAS_C>
+__device__ __forceinline__ void accumulate_chunk(const float* __restrict__ srows, const float* __restrict__ soffs,
+                                                 int cnt, float a_iso, const float (&x)[E][DP], float (&m)[E],
+                                                 float (&S)[E]) {
+  constexpr int ROW = row_floats(KIND, DP);
+#pragma unroll 1
+  for (int j0 = 0; j0 < cnt; j0 += JJ) {
+    float t[JJ][E];
+    float c[JJ];
+    if constexpr (HAS_C) {
+      lds_vec<JJ>(soffs + j0, c);
+    } else {
+#pragma unroll
+      for (int jj = 0; jj < JJ; ++jj) c[jj] = 0.f;
+    }
+#pragma unroll
+    for (int jj = 0; jj < JJ; ++jj) comp_eval<KIND, DP, E>(srows + (j0 + jj) * ROW, c[jj], a_iso, x, t[jj]);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      float gm = t[0][e];
+#pragma unroll
+      for (int jj = 1; jj < JJ; ++jj) gm = fmaxf(gm, t[jj][e]);
+      const float mn = fmaxf(m[e], gm);
+      float s = S[e] * ex2(m[e] - mn);
+#pragma unroll
+      for (int jj = 0; jj < JJ; ++jj) s += ex2(t[jj][e] - mn);
+      S[e] = s;
+      m[e] = mn;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stream components [k_begin, k_end) of a packed mixture through the smem ring, calling
+// fn(srows, soffs, cnt, k0) on every staged chunk (cnt components starting at global index k0).
+// `it` counts chunks consumed so far by this CTA (carries the mbarrier phase across passes).
+// k_begin/k_end are multiples of AISB_COMP_ALIGN. All threads of the CTA must call this.
+// ---------------------------------------------------------------------------------------------
+template <int KIND, int DP, bool HAS_C, typename Fn>
+__device__ __forceinline__ void stream_components(const float* __restrict__ g_rows, const float* __restrict__ g_offs,
+                                                  int64_t k_begin, int64_t k_end, float* smem, uint64_t* bars,
+                                                  uint32_t& it, Fn&& fn) {
+  constexpr int ROW = row_floats(KIND, DP);
+  constexpr int J = chunk_comps(KIND, DP);
+  constexpr int STAGE = stage_floats(KIND, DP, HAS_C);
+  const int nchunks = static_cast<int>((k_end - k_begin + J - 1) / J);
+  const uint32_t it0 = it;
+
+  auto issue = [&](int c) {
+    const int64_t k0 = k_begin + static_cast<int64_t>(c) * J;
+    const int64_t rem = k_end - k0;
+    const int cnt = rem < J ? static_cast<int>(rem) : J;
+    const uint32_t stage = (it0 + c) % kStages;
+    float* dst = smem + stage * STAGE;
+    const uint32_t bytes_rows = static_cast<uint32_t>(cnt) * ROW * 4u;
+    const uint32_t bytes_offs = HAS_C ? static_cast<uint32_t>(cnt) * 4u : 0u;
+    mbar_arrive_expect_tx(&bars[stage], bytes_rows + bytes_offs);
+    bulk_g2s(dst, g_rows + k0 * ROW, bytes_rows, &bars[stage]);
+    if constexpr (HAS_C) bulk_g2s(dst + J * ROW, g_offs + k0, bytes_offs, &bars[stage]);
+  };
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s)
+      if (s < nchunks) issue(s);
+  }
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    const uint32_t stage = (it0 + c) % kStages;
+    const uint32_t parity = ((it0 + c) / kStages) & 1u;
+    mbar_wait(&bars[stage], parity);
+    const int64_t k0 = k_begin + static_cast<int64_t>(c) * J;
+    const int64_t rem = k_end - k0;
+    const int cnt = rem < J ? static_cast<int>(rem) : J;
+    const float* s = smem + stage * STAGE;
+    fn(s, s + J * ROW, cnt, k0);
+    __syncthreads();  // every thread is done reading this stage
+    if (threadIdx.x == 0 && c + kStages < nchunks) issue(c + kStages);
+  }
+  it = it0 + nchunks;
+}
+
+// Fold components [k_begin, k_end) into the running (m, S) of the E register-resident points.
+template <int KIND, int DP, int E, bool HAS_C>
+__device__ __forceinline__ void mixture_pass(const float* __restrict__ g_rows, const float* __restrict__ g_offs,
+                                             int64_t k_begin, int64_t k_end, float a_iso, float* smem, uint64_t* bars,
+                                             uint32_t& it, const float (&x)[E][DP], float (&m)[E], float (&S)[E]) {
+  constexpr int JJ = comps_per_step(KIND, DP);
+  stream_components<KIND, DP, HAS_C>(g_rows, g_offs, k_begin, k_end, smem, bars, it,
+                                     [&](const float* srows, const float* soffs, int cnt, int64_t) {
+                                       accumulate_chunk<KIND, DP, E, JJ, HAS_C>(srows, soffs, cnt, a_iso, x, m, S);
+                                     });
+}
+
+// ---------------------------------------------------------------------------------------------
+// Point tile load: thread t owns points tile_base + e*128 + t (coalesced across the warp).
+// Out-of-range points are clamped to n-1 (computed, never stored).
+// ---------------------------------------------------------------------------------------------
+template <int DP, int E>
+__device__ __forceinline__ void load_points(const float* __restrict__ x, int64_t n, int D, int vec_ok,
+                                            int64_t tile_base, float (&xr)[E][DP], int64_t (&pidx)[E]) {
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int64_t p = tile_base + e * kThreads + threadIdx.x;
+    pidx[e] = p;
+    const int64_t pc = p < n ? p : n - 1;
+    bool done = false;
+    if constexpr (DP >= 4) {
+      if (D == DP && vec_ok) {
+        const float4* r = reinterpret_cast<const float4*>(x + pc * DP);
+#pragma unroll
+        for (int q = 0; q < DP / 4; ++q) {
+          const float4 f = __ldg(r + q);
+          xr[e][4 * q + 0] = f.x;
+          xr[e][4 * q + 1] = f.y;
+          xr[e][4 * q + 2] = f.z;
+          xr[e][4 * q + 3] = f.w;
+        }
+        done = true;
+      }
+    } else if constexpr (DP == 2) {
+      if (D == 2 && vec_ok) {
+        const float2 f = __ldg(reinterpret_cast<const float2*>(x + pc * 2));
+        xr[e][0] = f.x;
+        xr[e][1] = f.y;
+        done = true;
+      }
+    }
+    if (!done) {
+      const float* r = x + pc * D;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) xr[e][d] = d < D ? __ldg(r + d) : 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void ring_init(uint64_t* bars) {
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+}
+
+// natural-log result from a log2-domain (m, S) pair; S == 0 -> -inf
+__device__ __forceinline__ float lse_finish(float m, float S) { return (m + log2f(S)) * 0.69314718055994530942f; }
+
+#endif  // __CUDACC__
+}  // namespace aisb

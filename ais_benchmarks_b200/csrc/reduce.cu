@@ -1,0 +1,293 @@
+// Device-side weight-normaliser / ESS and KLD reductions + their C-ABI entry points.
+#include "reduce.cuh"
+
+namespace aisb {
+
+__global__ void weight_partials_merge_kernel(const double* __restrict__ bp, int64_t nblocks,
+                                             double* __restrict__ out4) {
+  __shared__ double sh[3][8];
+  __shared__ double shM;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double M = kNegBig;
+  for (int64_t b = threadIdx.x; b < nblocks; b += blockDim.x) M = fmax(M, bp[4 * b]);
+  M = warp_max(M);
+  if (lane == 0) sh[0][warp] = M;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = sh[0][0];
+    for (int w = 1; w < 8; ++w) v = fmax(v, sh[0][w]);
+    shM = v;
+  }
+  __syncthreads();
+  M = shM;
+  double s1 = 0.0, s2 = 0.0, cnt = 0.0;
+  for (int64_t b = threadIdx.x; b < nblocks; b += blockDim.x) {
+    const double f = exp(bp[4 * b] - M);
+    s1 += bp[4 * b + 1] * f;
+    s2 += bp[4 * b + 2] * f * f;
+    cnt += bp[4 * b + 3];
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  cnt = warp_sum(cnt);
+  __syncthreads();
+  if (lane == 0) {
+    sh[0][warp] = s1;
+    sh[1][warp] = s2;
+    sh[2][warp] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b2 = 0.0, c = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      a += sh[0][w];
+      b2 += sh[1][w];
+      c += sh[2][w];
+    }
+    out4[0] = M;
+    out4[1] = a;
+    out4[2] = b2;
+    out4[3] = c;
+  }
+}
+
+__global__ void __launch_bounds__(256) logw_partials_kernel(const float* __restrict__ logw, int64_t n,
+                                                            double* __restrict__ block_partials) {
+  __shared__ float red[256 / 32 * 4];
+  constexpr int E = 8;
+  float lw[E];
+  bool ok[E];
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * (256 * E);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int64_t p = base + e * 256 + threadIdx.x;
+    const bool in = p < n;
+    lw[e] = in ? logw[p] : 0.f;
+    ok[e] = in && (lw[e] == lw[e]) && (lw[e] != INFINITY);
+  }
+  block_weight_partials<E, 256>(lw, ok, red, block_partials + 4 * static_cast<int64_t>(blockIdx.x));
+}
+
+__global__ void normalize_weights_kernel(const float* __restrict__ logw, int64_t n, float M, float logS,
+                                         float* __restrict__ out) {
+  const int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (p >= n) return;
+  // (lw - M) is exact-ish near the maximum where the weights are largest; logS is O(log n)
+  out[p] = expf((logw[p] - M) - logS);
+}
+
+// KLD block record (8 doubles): { m_p, S_p, A, m_q, S_q, n_inlier, n_posinf_q, n_total }
+__global__ void __launch_bounds__(256) kld_partials_kernel(const float* __restrict__ lp, const float* __restrict__ lq,
+                                                           int64_t n, double* __restrict__ block_partials) {
+  constexpr int E = 8, NW = 8;
+  __shared__ float redf[2 * NW];
+  __shared__ double redd[6 * NW];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float p[E], q[E];
+  bool in[E];
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * (256 * E);
+  float mp = kNegBig, mq = kNegBig;
+  float ntot = 0.f;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int64_t i = base + e * 256 + threadIdx.x;
+    const bool valid = i < n;
+    p[e] = valid ? lp[i] : -INFINITY;
+    q[e] = valid ? lq[i] : -INFINITY;
+    // reference: inliers = (lp > -inf) & (lq > -inf)  (NaN compares false)  divergences.py:138-139
+    in[e] = valid && (p[e] > -INFINITY) && (q[e] > -INFINITY);
+    if (valid) ntot += 1.f;
+    if (in[e]) {
+      if (p[e] < INFINITY) mp = fmaxf(mp, p[e]);
+      if (q[e] < INFINITY) mq = fmaxf(mq, q[e]);
+    }
+  }
+  mp = warp_max(mp);
+  mq = warp_max(mq);
+  if (lane == 0) {
+    redf[warp] = mp;
+    redf[NW + warp] = mq;
+  }
+  __syncthreads();
+  mp = redf[0];
+  mq = redf[NW];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) {
+    mp = fmaxf(mp, redf[w]);
+    mq = fmaxf(mq, redf[NW + w]);
+  }
+  double sp = 0.0, a = 0.0, sq = 0.0, nin = 0.0, ninf = 0.0;
+#pragma unroll
+  for (int e = 0; e < E; ++e)
+    if (in[e]) {
+      nin += 1.0;
+      if (q[e] == INFINITY) {
+        ninf += 1.0;
+      } else {
+        const float up = expf(p[e] - mp);  // +inf lp -> inf -> NaN downstream, as in the reference
+        sp += up;
+        a += static_cast<double>(up) * (static_cast<double>(p[e]) - static_cast<double>(q[e]));
+        sq += expf(q[e] - mq);
+      }
+    }
+  sp = warp_sum(sp);
+  a = warp_sum(a);
+  sq = warp_sum(sq);
+  nin = warp_sum(nin);
+  ninf = warp_sum(ninf);
+  double nt = warp_sum(static_cast<double>(ntot));
+  if (lane == 0) {
+    redd[warp] = sp;
+    redd[NW + warp] = a;
+    redd[2 * NW + warp] = sq;
+    redd[3 * NW + warp] = nin;
+    redd[4 * NW + warp] = ninf;
+    redd[5 * NW + warp] = nt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < 6; ++k)
+      for (int w = 0; w < NW; ++w) r[k] += redd[k * NW + w];
+    double* o = block_partials + 8 * static_cast<int64_t>(blockIdx.x);
+    o[0] = mp;
+    o[1] = r[0];
+    o[2] = r[1];
+    o[3] = mq;
+    o[4] = r[2];
+    o[5] = r[3];
+    o[6] = r[4];
+    o[7] = r[5];
+  }
+}
+
+__global__ void kld_partials_merge_kernel(const double* __restrict__ bp, int64_t nblocks, double* __restrict__ out8) {
+  __shared__ double sh[6][8];
+  __shared__ double shM[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double mp = kNegBig, mq = kNegBig;
+  for (int64_t b = threadIdx.x; b < nblocks; b += blockDim.x) {
+    mp = fmax(mp, bp[8 * b]);
+    mq = fmax(mq, bp[8 * b + 3]);
+  }
+  mp = warp_max(mp);
+  mq = warp_max(mq);
+  if (lane == 0) {
+    sh[0][warp] = mp;
+    sh[1][warp] = mq;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = sh[0][0], b = sh[1][0];
+    for (int w = 1; w < 8; ++w) {
+      a = fmax(a, sh[0][w]);
+      b = fmax(b, sh[1][w]);
+    }
+    shM[0] = a;
+    shM[1] = b;
+  }
+  __syncthreads();
+  mp = shM[0];
+  mq = shM[1];
+  double r[6] = {0, 0, 0, 0, 0, 0};
+  for (int64_t b = threadIdx.x; b < nblocks; b += blockDim.x) {
+    const double fp = exp(bp[8 * b] - mp), fq = exp(bp[8 * b + 3] - mq);
+    r[0] += bp[8 * b + 1] * fp;
+    r[1] += bp[8 * b + 2] * fp;
+    r[2] += bp[8 * b + 4] * fq;
+    r[3] += bp[8 * b + 5];
+    r[4] += bp[8 * b + 6];
+    r[5] += bp[8 * b + 7];
+  }
+  __syncthreads();
+  for (int k = 0; k < 6; ++k) {
+    r[k] = warp_sum(r[k]);
+    if (lane == 0) sh[k][warp] = r[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < 6; ++k)
+      for (int w = 0; w < 8; ++w) t[k] += sh[k][w];
+    out8[0] = mp;
+    out8[1] = t[0];
+    out8[2] = t[1];
+    out8[3] = mq;
+    out8[4] = t[2];
+    out8[5] = t[3];
+    out8[6] = t[4];
+    out8[7] = t[5];
+  }
+}
+
+static int64_t reduce_blocks(int64_t n) { return (n + 2047) / 2048; }
+
+static int check_ws(void* d_ws, size_t ws_bytes, size_t need, double** out, const char* who) {
+  char* base = static_cast<char*>(d_ws);
+  const size_t mis = base ? (256 - reinterpret_cast<uintptr_t>(base) % 256) % 256 : 0;
+  if (!base || need + mis > ws_bytes) {
+    set_error("%s: workspace too small (%zu < %zu bytes)", who, ws_bytes, need + mis);
+    return AISB_ERR_WORKSPACE;
+  }
+  *out = reinterpret_cast<double*>(base + mis);
+  return AISB_OK;
+}
+
+}  // namespace aisb
+
+using namespace aisb;
+
+extern "C" int aisb_logw_partials_f32(const float* d_logw, int64_t n, double* d_out_partials, void* d_workspace,
+                                      size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!d_out_partials || n < 0 || (n > 0 && !d_logw)) {
+    set_error("logw_partials: null pointer or negative n");
+    return AISB_ERR_INVALID;
+  }
+  const int64_t nblocks = reduce_blocks(n);
+  double* bp = nullptr;
+  int rc = check_ws(d_workspace, workspace_bytes, sizeof(double) * 4 * (nblocks + 1), &bp, "logw_partials");
+  if (rc) return rc;
+  if (nblocks > 0) {
+    logw_partials_kernel<<<static_cast<unsigned>(nblocks), 256, 0, st>>>(d_logw, n, bp);
+    AISB_LAUNCH_CHECK("logw_partials_kernel");
+  }
+  weight_partials_merge_kernel<<<1, 256, 0, st>>>(bp, nblocks, d_out_partials);
+  AISB_LAUNCH_CHECK("weight_partials_merge_kernel");
+  return AISB_OK;
+}
+
+extern "C" int aisb_normalize_weights_f32(const float* d_logw, int64_t n, const double* h_partials, float* d_out_w,
+                                          void* stream) {
+  if (n < 0 || !h_partials || (n > 0 && (!d_logw || !d_out_w))) {
+    set_error("normalize_weights: null pointer or negative n");
+    return AISB_ERR_INVALID;
+  }
+  if (n == 0) return AISB_OK;
+  const float M = static_cast<float>(h_partials[0]);
+  const float logS = static_cast<float>(log(h_partials[1]) + (h_partials[0] - static_cast<double>(M)));
+  normalize_weights_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_logw, n, M, logS, d_out_w);
+  AISB_LAUNCH_CHECK("normalize_weights_kernel");
+  return AISB_OK;
+}
+
+extern "C" int aisb_kld_partials_f32(const float* d_lp, const float* d_lq, int64_t n, double* d_out_partials,
+                                     void* d_workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!d_out_partials || n < 0 || (n > 0 && (!d_lp || !d_lq))) {
+    set_error("kld_partials: null pointer or negative n");
+    return AISB_ERR_INVALID;
+  }
+  const int64_t nblocks = reduce_blocks(n);
+  double* bp = nullptr;
+  int rc = check_ws(d_workspace, workspace_bytes, sizeof(double) * 8 * (nblocks + 1), &bp, "kld_partials");
+  if (rc) return rc;
+  if (nblocks > 0) {
+    kld_partials_kernel<<<static_cast<unsigned>(nblocks), 256, 0, st>>>(d_lp, d_lq, n, bp);
+    AISB_LAUNCH_CHECK("kld_partials_kernel");
+  }
+  kld_partials_merge_kernel<<<1, 256, 0, st>>>(bp, nblocks, d_out_partials);
+  AISB_LAUNCH_CHECK("kld_partials_merge_kernel");
+  return AISB_OK;
+}

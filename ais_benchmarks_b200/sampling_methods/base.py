@@ -1,0 +1,348 @@
+"""Sampling-method base classes with the reference's interface
+(reference ais_benchmarks/sampling_methods/base.py:11-246).
+
+State lives on the GPU: accumulated samples as a float32 [n, D] tensor and accumulated
+*log* weights as a float32 [n] tensor. ``self.samples`` / ``self.weights`` are numpy views of
+that state (float64, weights in the linear domain like the reference) materialised on demand, so
+unmodified callers (CBenchmark.evaluate_method, write_results) keep working.
+"""
+import math
+from abc import ABCMeta, abstractmethod
+
+import numpy as np
+import torch
+
+from .. import _device
+from ..distributions.distributions import CDistribution
+
+
+class CSamplingMethod(metaclass=ABCMeta):
+    def __init__(self, params):
+        self.space_min = np.asarray(params["space_min"], dtype=np.float64)
+        self.space_max = np.asarray(params["space_max"], dtype=np.float64)
+        self.ndims = params["dims"]
+        self._name = params["name"] if "name" in params.keys() else "GenericSamplingMethod"
+        # True: importance_sample()/sample() return CUDA tensors instead of numpy arrays
+        self.device_outputs = bool(params.get("device_outputs", False))
+
+        assert self.space_max.shape == self.space_min.shape
+        assert self.ndims == len(self.space_max)
+
+        self._debug = False
+        self._reset_state()
+
+    def _reset_state(self):
+        self._num_pi_evals = 0
+        self._num_q_evals = 0
+        self._num_q_samples = 0
+        self._samples_dev = None   # float32 [n, D] CUDA
+        self._logw_dev = None      # float32 [n] CUDA, log of the reference's self.weights
+        self._samples_np = None
+        self._weights_np = None
+        self._partials = None      # host float64[4] record of the accumulated log-weights
+        self.variogram = np.array([])
+
+    def reset(self):
+        self._reset_state()
+
+    # -- numpy views of the device state -----------------------------------------------------------
+    @property
+    def samples(self):
+        if self._samples_np is None:
+            self._samples_np = (np.array([]) if self._samples_dev is None
+                                else self._samples_dev.cpu().numpy().astype(np.float64))
+        return self._samples_np
+
+    @samples.setter
+    def samples(self, val):
+        val = np.asarray(val, dtype=np.float64)
+        self._samples_np = val
+        if val.size:
+            _device.require_cuda()
+            self._samples_dev = torch.from_numpy(val.reshape(-1, self.ndims)).to(_device.device(), torch.float32)
+        else:
+            self._samples_dev = None
+
+    @property
+    def weights(self):
+        if self._weights_np is None:
+            self._weights_np = (np.array([]) if self._logw_dev is None
+                                else torch.exp(self._logw_dev.double()).cpu().numpy())
+        return self._weights_np
+
+    @weights.setter
+    def weights(self, val):
+        val = np.asarray(val, dtype=np.float64)
+        self._weights_np = val
+        self._partials = None
+        if val.size:
+            _device.require_cuda()
+            with np.errstate(divide="ignore"):
+                self._logw_dev = torch.from_numpy(np.log(val)).to(_device.device(), torch.float32)
+        else:
+            self._logw_dev = None
+
+    def _append(self, new_samples, new_logw):
+        self._samples_dev = new_samples if self._samples_dev is None else torch.cat((self._samples_dev, new_samples))
+        self._logw_dev = new_logw if self._logw_dev is None else torch.cat((self._logw_dev, new_logw))
+        self._samples_np = self._weights_np = self._partials = None
+
+    def _n(self):
+        return 0 if self._samples_dev is None else int(self._samples_dev.shape[0])
+
+    def _weight_partials(self):
+        if self._partials is None:
+            self._partials = _device.logw_partials(self._logw_dev).cpu().numpy()
+        return self._partials
+
+    def _out(self, t, exp=False):
+        if self.device_outputs:
+            return torch.exp(t) if exp else t
+        return _device.exp_from_device(t, True) if exp else t.cpu().numpy().astype(np.float64)
+
+    # -- statistics --------------------------------------------------------------------------------
+    def get_acceptance_rate(self):
+        assert self._n(), "Invalid number of samples to compute acceptance rate"
+        return self._n() / self._num_q_samples
+
+    def get_NESS(self):
+        """Autocorrelation-based ESS of base.py:41-70 (host statistic over the sample chain; not on the hot path)."""
+        x = self.samples
+        n = len(x)
+        variogram = lambda t: np.array([((x[t:] - x[:(n - t)]) ** 2).sum() / (n - t)])
+        mean = x.mean()
+        dist = x - mean
+        W = (dist ** 2).sum() / (n - 1)
+        t = 1
+        rho = np.ones(n)
+        negative_autocorr = False
+        while not negative_autocorr and (t < n):
+            rho[t] = (1. - variogram(t) / (2. * W))[0]
+            if not t % 2:
+                negative_autocorr = sum(rho[t - 1:t + 1]) < 0
+            t += 1
+        ess = n / (1 + 2 * rho[1:t].sum())
+        return ess / len(self.samples)
+
+    def get_approx_NESS(self):
+        """ESS / n with ESS = 1 / sum w~^2 (base.py:72-75), from the device-side partial sums
+        (C ABI aisb_logw_partials_f32 + aisb_weight_partials_ess)."""
+        return _device.weight_ess(self._weight_partials()) / self._n()
+
+    def get_stats(self):
+        return {"proposal_samples": self._num_q_samples,
+                "proposal_evals": self._num_q_evals,
+                "target_evals": self._num_pi_evals,
+                "n_samples": self._n()}
+
+    @property
+    def name(self):
+        return self._name
+
+    @name.setter
+    def name(self, val):
+        self._name = val
+
+    @property
+    def num_proposal_samples(self):
+        return self._num_q_samples
+
+    @property
+    def num_target_evals(self):
+        return self._num_pi_evals
+
+    @property
+    def num_proposal_evals(self):
+        return self._num_q_evals
+
+    @property
+    def debug(self):
+        return self._debug
+
+    @debug.setter
+    def debug(self, val):
+        self._debug = val
+
+    @abstractmethod
+    def sample(self, n_samples):
+        raise NotImplementedError
+
+    @abstractmethod
+    def importance_sample(self, target_d, n_samples, timeout):
+        raise NotImplementedError
+
+    @abstractmethod
+    def prob(self, samples):
+        raise NotImplementedError
+
+    @abstractmethod
+    def log_prob(self, samples):
+        raise NotImplementedError
+
+    def draw(self, ax):
+        return []
+
+    def get_viz_frames(self):
+        return None
+
+
+class CDeviceKDE(CDistribution):
+    """The KDE that CMixtureSamplingMethod._update_model builds (base.py:162-179), kept as ONE packed
+    HBM buffer of n_kde centres instead of n_kde CMultivariateNormal objects: equal weights, kernel
+    covariance bw*I (bw is a variance, quirk Q1)."""
+
+    def __init__(self, samples_dev, idx_dev, n_kde, bw, dims, support):
+        params = {"type": "KDE", "family": "mixture", "dims": dims, "support": support,
+                  "likelihood_f": self.prob, "loglikelihood_f": self.log_prob}
+        super().__init__(params)
+        self.bw = float(bw)
+        self.n_kde = int(n_kde)
+        self._idx = idx_dev
+        self._src = samples_dev
+        self.mixture = _device.DeviceMixture.kde(samples_dev, idx_dev, n_kde, bw)
+        self.weights = np.full(shape=(self.n_kde,), fill_value=1 / self.n_kde)
+
+    def centres(self):
+        return self._src if self._idx is None else self._src[self._idx]
+
+    def log_prob(self, data):
+        x, as_numpy = _device.to_device_points(data, self.dims)
+        return _device.from_device(_device.mixture_logpdf(x, self.mixture), as_numpy)
+
+    def prob(self, data):
+        x, as_numpy = _device.to_device_points(data, self.dims)
+        return _device.exp_from_device(_device.mixture_logpdf(x, self.mixture), as_numpy)
+
+    def sample(self, n_samples=1, as_tensor=False):
+        c = self.centres()
+        pick = torch.randint(0, c.shape[0], (int(n_samples),), device=c.device)
+        x = _device.sample_iso(c[pick].contiguous(), 1, self.bw)
+        return x if as_tensor else x.cpu().numpy().astype(np.float64)
+
+    def condition(self, dist):
+        raise NotImplementedError
+
+    def marginal(self, dim):
+        raise NotImplementedError
+
+
+class CMixtureSamplingMethod(CSamplingMethod):
+    def __init__(self, params):
+        super(CMixtureSamplingMethod, self).__init__(params)
+        self.model = None
+        self.n_samples_kde = params["n_samples_kde"]
+
+    def reset(self):
+        super(CMixtureSamplingMethod, self).reset()
+        self.model = None
+
+    def sample(self, n_samples):
+        if self.model is None:
+            self._update_model()
+        self._num_q_samples += n_samples
+        return self.model.sample(n_samples, as_tensor=True) if self.device_outputs else self.model.sample(n_samples)
+
+    def prob(self, s):
+        if self.model is None:
+            self._update_model()
+        return self.model.prob(s)
+
+    def log_prob(self, s):
+        if self.model is None:
+            self._update_model()
+        return self.model.log_prob(s)
+
+    def _update_model(self):
+        """KDE over n_samples_kde samples drawn with replacement (base.py:162-179)."""
+        _device.require_cuda()
+        n = self._n()
+        assert n > 0, "no samples to build the KDE from"
+        seed = int(np.random.randint(0, 2 ** 31 - 1))  # follows np.random.seed like the reference's index draw
+        gen = torch.Generator(device=_device.device())
+        gen.manual_seed(seed)
+        idx = torch.randint(0, n, (int(self.n_samples_kde),), device=_device.device(), generator=gen)
+        self.model = CDeviceKDE(self._samples_dev, idx, self.n_samples_kde, self.bw, self.ndims,
+                                [self.space_min, self.space_max])
+
+
+class CMixtureISSamplingMethod(CMixtureSamplingMethod):
+    def __init__(self, params):
+        params["n_samples_kde"] = None
+        super(CMixtureISSamplingMethod, self).__init__(params)
+
+    def get_NESS(self):
+        return self.get_approx_NESS()
+
+    def _update_model(self):
+        # reference base.py:234-246 is broken as shipped (wrong CMixtureModel call) and is overridden with `pass`
+        # by every importance sampler on the path; keep the override contract.
+        raise NotImplementedError("CMixtureISSamplingMethod subclasses own their proposal mixture")
+
+
+# ---------------------------------------------------------------------------------------------------
+# helpers shared by the importance samplers
+# ---------------------------------------------------------------------------------------------------
+def target_device_mixture(target_d):
+    """Packed HBM parameters of a target built from this package's Gaussian classes, else None."""
+    if hasattr(target_d, "device_mixture"):
+        return target_d.device_mixture()
+    if hasattr(target_d, "_packed") and callable(getattr(target_d, "_packed")):
+        kind, packed = target_d._packed()
+        return packed if kind == "gauss" else None
+    if hasattr(target_d, "_device_mixture"):
+        return target_d._device_mixture()
+    return None
+
+
+def foreign_target_logp(target_d, x_dev):
+    """log pi(x) of a target that is not one of this package's Gaussian classes: the caller's own log_prob/prob
+    runs wherever it runs (typically numpy on the host); the result is uploaded for the weight kernel."""
+    x_np = x_dev.cpu().numpy().astype(np.float64)
+    if hasattr(target_d, "log_prob"):
+        lp = np.asarray(target_d.log_prob(x_np), dtype=np.float64).reshape(-1)
+    else:
+        with np.errstate(divide="ignore"):
+            lp = np.log(np.asarray(target_d.prob(x_np), dtype=np.float64).reshape(-1))
+    return torch.from_numpy(lp).to(x_dev.device, torch.float32)
+
+
+def multinomial_resample(logw, n_draws):
+    """n_draws indices ~ Categorical(w / sum w), w = exp(logw) (dm_ais.py:47-54). Invalid (NaN / +inf) weights
+    count as zero. Inverse-CDF on the device: cumsum + searchsorted, float64."""
+    lw = logw.double()
+    lw = torch.where(torch.isfinite(lw) | (lw == -math.inf), lw, torch.full_like(lw, -math.inf))
+    m = torch.max(lw)
+    if not torch.isfinite(m):
+        return torch.randint(0, logw.shape[0], (n_draws,), device=logw.device)
+    cdf = torch.cumsum(torch.exp(lw - m), 0)
+    u = torch.rand(n_draws, dtype=torch.float64, device=logw.device) * cdf[-1]
+    return torch.clamp(torch.searchsorted(cdf, u, right=True), max=logw.shape[0] - 1)
+
+
+def make_grid(space_min, space_max, resolution):
+    """base.py:249-264."""
+    dim_range = space_max - space_min
+    num_samples = (dim_range / resolution).tolist()
+    for i in range(len(num_samples)):
+        num_samples[i] = int(num_samples[i])
+        if num_samples[i] < 1:
+            num_samples[i] = 1
+    dimensions = []
+    shape = np.array([0] * len(num_samples))
+    for i in range(len(num_samples)):
+        dimensions.append(np.linspace(space_min[i], space_max[i], num_samples[i]))
+        shape[i] = len(dimensions[i])
+    samples = np.array(np.meshgrid(*dimensions)).T.reshape(-1, len(space_min))
+    return samples, dimensions, shape
+
+
+def grid_sample_distribution(dist, space_min, space_max, resolution):
+    grid, dims, shape = make_grid(space_min, space_max, resolution)
+    log_prob = dist.log_prob(np.array(grid))
+    return grid, log_prob, dims, shape
+
+
+def uniform_sample_distribution(dist, space_min, space_max, nsamples):
+    samples = np.random.uniform(space_min, space_max, size=(nsamples, len(space_max)))
+    log_prob = dist.log_prob(samples.reshape(nsamples, len(space_max)))
+    return samples.reshape(nsamples, len(space_max)), log_prob

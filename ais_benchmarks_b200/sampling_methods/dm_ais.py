@@ -1,0 +1,143 @@
+"""DM-AIS / DM-PMC with the reference's interface
+(reference ais_benchmarks/sampling_methods/dm_ais.py:10-89).
+
+One iteration = N*K proposal draws (Philox kernel), ONE fused weight kernel launch
+(log pi, log q over all N proposals, log w and the normaliser / ESS partials; C ABI
+aisb_dm_weights_f32) and an N-draw multinomial resampling of the proposal means. The proposal
+means never leave HBM; ``self.proposals`` / ``self.model`` are rebuilt as reference-style objects
+only when someone reads them.
+"""
+import time
+
+import numpy as np
+import torch
+
+from .. import _device
+from ..distributions import CMixtureModel, CMultivariateNormal
+from .base import (CMixtureISSamplingMethod, foreign_target_logp, multinomial_resample, target_device_mixture)
+
+
+class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
+    def __init__(self, params):
+        """
+        :param params:
+            - space_min / space_max: space boundaries; dims: number of dimensions
+            - K: samples per proposal; N: number of proposals; J: iteration cap (unused, like the reference)
+            - sigma: proposal VARIANCE (covariance = sigma * I, dm_ais.py:38-39)
+        """
+        super(CDeterministicMixtureAIS, self).__init__(params)
+        self.K = params["K"]
+        self.N = params["N"]
+        self.J = params["J"]
+        self.sigma = params["sigma"]
+        self._means = None
+        self._mixture = None
+        self._objects = None
+        self.reset()
+
+    # -- proposal state ----------------------------------------------------------------------------
+    def reset(self):
+        super(CDeterministicMixtureAIS, self).reset()
+        # proposal centres ~ U(space_min, space_max) from the host RNG, as dm_ais.py:36-37
+        centres = np.random.uniform(self.space_min, self.space_max, size=(self.N, self.ndims))
+        self._set_means_host(centres)
+
+    def _set_means_host(self, centres):
+        self._means_host = np.asarray(centres, dtype=np.float64)
+        self._means = None
+        self._mixture = None
+        self._objects = None
+
+    def _set_means_dev(self, means):
+        self._means = means.contiguous()
+        self._means_host = None
+        self._mixture = None
+        self._objects = None
+
+    def proposal_means(self):
+        """float32 CUDA [N, D]."""
+        if self._means is None:
+            _device.require_cuda()
+            self._means = torch.from_numpy(self._means_host).to(_device.device(), torch.float32).contiguous()
+        return self._means
+
+    def proposal_mixture(self):
+        """Packed equal-weight isotropic mixture q = (1/N) sum_n N(mu_n, sigma I) in HBM."""
+        if self._mixture is None:
+            self._mixture = _device.DeviceMixture.kde(self.proposal_means(), None, self.N, float(self.sigma))
+        return self._mixture
+
+    def _build_objects(self):
+        if self._objects is None:
+            means = self._means_host if self._means_host is not None else self._means.cpu().numpy().astype(np.float64)
+            cov = np.diag(np.array([self.sigma] * self.ndims, dtype=np.float64))
+            props = [CMultivariateNormal({"mean": m, "sigma": cov.copy()}) for m in means]
+            model = CMixtureModel({"models": props, "weights": np.array([1 / len(props)] * len(props)),
+                                   "dims": self.ndims, "support": [self.space_min, self.space_max]})
+            self._objects = (props, model)
+        return self._objects
+
+    @property
+    def proposals(self):
+        return self._build_objects()[0]
+
+    @proposals.setter
+    def proposals(self, val):
+        if val:
+            self._set_means_host(np.array([np.asarray(p.loc, dtype=np.float64).reshape(-1) for p in val]))
+
+    @property
+    def model(self):
+        return self._build_objects()[1]
+
+    @model.setter
+    def model(self, val):
+        pass  # the mixture is derived from the proposal means
+
+    # -- density / sampling of the proposal mixture ------------------------------------------------
+    def log_prob(self, s):
+        x, as_numpy = _device.to_device_points(s, self.ndims)
+        return _device.from_device(_device.mixture_logpdf(x, self.proposal_mixture()), as_numpy)
+
+    def prob(self, s):
+        x, as_numpy = _device.to_device_points(s, self.ndims)
+        return _device.exp_from_device(_device.mixture_logpdf(x, self.proposal_mixture()), as_numpy)
+
+    def sample(self, n_samples):
+        self._num_q_samples += n_samples
+        means = self.proposal_means()
+        pick = torch.randint(0, self.N, (int(n_samples),), device=means.device)
+        x = _device.sample_iso(means[pick].contiguous(), 1, float(self.sigma))
+        return x if self.device_outputs else x.cpu().numpy().astype(np.float64)
+
+    # -- the adapt loop ----------------------------------------------------------------------------
+    def weigh(self, new_samples, target_d):
+        """log w = log pi(x) - log q(x) for a batch + its normaliser/ESS partials (dm_ais.py:72-76)."""
+        target = target_device_mixture(target_d)
+        logp_in = None if target is not None else foreign_target_logp(target_d, new_samples)
+        logw, _, _, partials = _device.dm_weights(new_samples, target, logp_in, self.proposal_mixture())
+        return logw, partials
+
+    def resample(self, samples, logw):
+        """DM-PMC update (dm_ais.py:47-56): each proposal mean <- a sample drawn ~ batch-normalised weights."""
+        idx = multinomial_resample(logw, self.N)
+        self._set_means_dev(samples[idx])
+
+    def importance_sample(self, target_d, n_samples, timeout=60):
+        elapsed_time = 0
+        t_ini = time.time()
+        while n_samples > self._n() and elapsed_time < timeout:
+            # K samples from each proposal, proposal-major like dm_ais.py:64-69
+            new_samples = _device.sample_iso(self.proposal_means(), int(self.K), float(self.sigma))
+            self._num_q_samples += self.N * self.K
+            new_logw, _ = self.weigh(new_samples, target_d)
+            self._num_pi_evals += self.N * self.K
+            self.resample(new_samples, new_logw)
+            self._append(new_samples, new_logw)
+            elapsed_time = time.time() - t_ini
+        # weights / weights.sum() over ALL iterations (dm_ais.py:86)
+        norm_w = _device.normalize_weights(self._logw_dev, self._weight_partials())
+        return self._out(self._samples_dev), (norm_w if self.device_outputs else norm_w.double().cpu().numpy())
+
+    def _update_model(self):
+        pass

@@ -1,0 +1,163 @@
+"""Mixture PMC with the reference's interface
+(reference ais_benchmarks/sampling_methods/m_pmc.py:10-121).
+
+Per iteration: K draws from the proposal mixture, one fused weight kernel (log pi, log q, log w,
+normaliser), one Rao-Blackwellised moment kernel (alpha_d and mu_d numerators over all K x N
+(sample, proposal) pairs; C ABI aisb_mpmc_moments_f32) and one raw-moment kernel for the scatter.
+The O(N D^2) parameter update runs on the host in float64, as in the reference.
+
+Reference quirks kept on purpose: Q3 - the covariance update multiplies the UNWEIGHTED scatter
+(X - mu_d)^T (X - mu_d) by sum_i w_i rho_di / alpha_d = 1, and falls back to 10*I when any entry is NaN or > 10
+(m_pmc.py:64-72); Q4 - returned weights are normalised per batch, not globally (m_pmc.py:108,118).
+``paper_covariance=True`` in params switches to the weighted covariance of eq. 14.3 instead (not parity mode).
+"""
+import time
+
+import numpy as np
+import torch
+
+from .. import _device
+from .._lib import COV_FULL
+from ..distributions import CMixtureModel, CMultivariateNormal
+from ..distributions.mixture.CMixtureModel import sanitize_weights
+from .base import CMixtureISSamplingMethod, foreign_target_logp, target_device_mixture
+
+
+class CMixturePMC(CMixtureISSamplingMethod):
+    def __init__(self, params):
+        super(CMixturePMC, self).__init__(params)
+        self.K = params["K"]            # samples per iteration (paper: N)
+        self.N = params["N"]            # mixture components (paper: D)
+        self.J = params["J"]
+        self.sigma = params["sigma"]
+        self.paper_covariance = bool(params.get("paper_covariance", False))
+        self.reset()
+
+    def reset(self):
+        super(CMixturePMC, self).reset()
+        self._means = np.random.uniform(self.space_min, self.space_max, size=(self.N, self.ndims))
+        self._covs = np.tile(np.diag(np.array([self.sigma] * self.ndims, dtype=np.float64)), (self.N, 1, 1))
+        self.wproposals = np.array([1 / self.N] * self.N)
+        self._mix_weights = sanitize_weights(self.wproposals.copy())
+        self._mixture = None
+        self._objects = None
+
+    # -- proposal mixture --------------------------------------------------------------------------
+    def proposal_mixture(self):
+        if self._mixture is None:
+            diag = np.diagonal(self._covs, axis1=1, axis2=2)
+            if np.count_nonzero(self._covs - diag[:, :, None] * np.eye(self.ndims)[None]) == 0:
+                from .._lib import COV_DIAG
+                self._mixture = _device.DeviceMixture.from_params(self._means, np.ascontiguousarray(diag),
+                                                                  self._mix_weights, COV_DIAG)
+            else:
+                self._mixture = _device.DeviceMixture.from_params(self._means, self._covs, self._mix_weights, COV_FULL)
+        return self._mixture
+
+    def _build_objects(self):
+        if self._objects is None:
+            props = [CMultivariateNormal({"mean": m.copy(), "sigma": c.copy()}) for m, c in zip(self._means, self._covs)]
+            model = CMixtureModel({"models": props, "weights": self.wproposals.copy(),
+                                   "dims": self.ndims, "support": [self.space_min, self.space_max]})
+            self._objects = (props, model)
+        return self._objects
+
+    @property
+    def proposals(self):
+        return self._build_objects()[0]
+
+    @proposals.setter
+    def proposals(self, val):
+        pass
+
+    @property
+    def model(self):
+        return self._build_objects()[1]
+
+    @model.setter
+    def model(self, val):
+        pass
+
+    def log_prob(self, s):
+        x, as_numpy = _device.to_device_points(s, self.ndims)
+        return _device.from_device(_device.mixture_logpdf(x, self.proposal_mixture()), as_numpy)
+
+    def prob(self, s):
+        x, as_numpy = _device.to_device_points(s, self.ndims)
+        return _device.exp_from_device(_device.mixture_logpdf(x, self.proposal_mixture()), as_numpy)
+
+    def _sample_device(self, n):
+        """Ancestral sampling from the proposal mixture on the device (m_pmc.py:86 -> CMixtureModel.sample)."""
+        dev = _device.device()
+        w = torch.from_numpy(self._mix_weights).to(dev)
+        idx = torch.multinomial(w, int(n), replacement=True)
+        z = _device.sample_iso(torch.zeros((1, self.ndims), dtype=torch.float32, device=dev), int(n), 1.0)
+        L = np.linalg.cholesky(0.5 * (self._covs + np.transpose(self._covs, (0, 2, 1))))
+        Ld = torch.from_numpy(L).to(dev, torch.float32)[idx]
+        mu = torch.from_numpy(self._means).to(dev, torch.float32)[idx]
+        return (mu + torch.bmm(Ld, z.unsqueeze(-1)).squeeze(-1)).contiguous()
+
+    def sample(self, n_samples):
+        self._num_q_samples += n_samples
+        x = self._sample_device(n_samples)
+        return x if self.device_outputs else x.cpu().numpy().astype(np.float64)
+
+    # -- one M-PMC iteration on a given batch (also the parity-test entry point) -------------------
+    def weigh(self, new_samples, target_d):
+        """-> (log w [K], log q [K], partials) for a batch (m_pmc.py:93-96)."""
+        target = target_device_mixture(target_d)
+        logp_in = None if target is not None else foreign_target_logp(target_d, new_samples)
+        logw, _, logq, partials = _device.dm_weights(new_samples, target, logp_in, self.proposal_mixture(),
+                                                    want_logq=True)
+        return logw, logq, partials
+
+    def adapt(self, samples, logw, logq, partials_host):
+        """alpha, mu, Sigma update (m_pmc.py:53-78) from device-side sufficient statistics."""
+        log_norm = _device.weight_logsum(partials_host)  # log sum_i w_i: weights are batch-normalised (m_pmc.py:108)
+        mom = _device.mpmc_moments(samples, self.proposal_mixture(), logq, logw, log_norm).cpu().numpy()
+        alpha = mom[:, 0].copy()                           # eq. 14.1 (Rao-Blackwellised)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            mu = mom[:, 1:] / alpha[:, None]               # eq. 14.2
+        n = samples.shape[0]
+        s1_t, s2_t = _device.raw_moments(samples)
+        s1, s2 = s1_t.cpu().numpy(), s2_t.cpu().numpy()
+        covs = np.empty_like(self._covs)
+        for d in range(self.N):
+            with np.errstate(invalid="ignore", over="ignore"):
+                if self.paper_covariance:
+                    raise NotImplementedError("paper_covariance needs the weighted second-moment kernel (next round)")
+                # quirk Q3: raw scatter about mu_d, (X - mu)^T (X - mu) = S2 - mu s1^T - s1 mu^T + n mu mu^T
+                cov = s2 - np.outer(mu[d], s1) - np.outer(s1, mu[d]) + n * np.outer(mu[d], mu[d])
+            if np.any(np.isnan(cov)) or np.any(cov > 10):
+                cov = np.diag(np.ones(self.ndims) * 10)
+            # CMultivariateNormal.set_moments asserts det > 0 (CMultivariateNormal.py:55-56)
+            assert np.linalg.det(cov) > 0
+            covs[d] = cov
+        self._means, self._covs = mu, covs
+        self.wproposals = alpha
+        self.wproposals = self.wproposals / self.wproposals.sum()
+        self._mix_weights = sanitize_weights(self.wproposals.copy())
+        self._mixture = None
+        self._objects = None
+
+    def importance_sample(self, target_d, n_samples, timeout=60):
+        elapsed_time = 0
+        t_ini = time.time()
+        while n_samples > self._n() and elapsed_time < timeout:
+            new_samples = self.sample_batch()
+            logw, logq, partials = self.weigh(new_samples, target_d)
+            self._num_pi_evals += self.K
+            self._num_q_evals += self.K * (self.N + 1)
+            ph = partials.cpu().numpy()
+            self.adapt(new_samples, logw, logq, ph)
+            # accumulated weights are the batch-normalised ones (quirk Q4)
+            self._append(new_samples, logw - float(_device.weight_logsum(ph)))
+            elapsed_time = time.time() - t_ini
+        return self._out(self._samples_dev), self._out(self._logw_dev, exp=True)
+
+    def sample_batch(self):
+        self._num_q_samples += self.K
+        return self._sample_device(self.K)
+
+    def _update_model(self):
+        pass

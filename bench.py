@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""Benchmark of the ais-benchmarks hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+  python bench.py --impl reference [...]                        # the reference algorithm (oracle port) on host cores
+
+Headline workload (BASELINE.json configs[3], "KDE-KLD metric sweep"): D = 8, 1e6 KDE centres x 1e6
+evaluation points, 16-mode GMM target, bw = 0.02 -> metric "KDE-KLD kernel-evals/s". The second half of
+BASELINE.json's metric (configs[4], DM-AIS weighting of 1e7 samples x 1024 proposals, D = 32, 64-mode GMM target)
+is measured in the same run and reported under "dm_ais" in the same JSON line.
+
+A "step" is one full evaluation of the metric on one batch: KDE build (pack) + q log-density (pairwise kernel)
++ target log-density + KLD reduction (+ the 8-double all-gather for N > 1). Evaluation points are sharded over
+the ranks (total work fixed -> "scaling": "strong").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "KDE-KLD kernel-evals/sec"
+UNIT = "kernel-evals/s"
+KDE_CFG = dict(D=8, modes=16, n_centres=1_000_000, n_eval=1_000_000, bw=0.02)
+DM_CFG = dict(D=32, modes=64, n_samples=10_000_000, n_proposals=1024, sigma=0.05)
+
+
+# ----------------------------------------------------------------------------------------------------
+# synthetic workloads (host numpy, seeded; same construction as the reference's generateRandomGMM,
+# utils/misc.py:40-60: "sigma" are variances, means keep a 5*sigma margin, support = hull of mean +- 5*sigma)
+# ----------------------------------------------------------------------------------------------------
+def random_gmm(seed, dims, k):
+    rs = np.random.RandomState(seed)
+    lo, hi = np.full(dims, -1.0), np.full(dims, 1.0)
+    sig = rs.uniform(0.04, 0.05, size=(k, dims))
+    mu = rs.uniform(lo + 5 * sig, hi - 5 * sig)
+    w = rs.rand(k)
+    w /= w.sum()
+    support = np.array([np.min(mu - 5 * sig, axis=0), np.max(mu + 5 * sig, axis=0)])
+    return mu, sig, w, support
+
+
+def gmm_samples(rs, mu, sig, w, n):
+    comp = rs.choice(len(w), size=n, p=w)
+    return (mu[comp] + rs.standard_normal((n, mu.shape[1])) * np.sqrt(sig[comp])).astype(np.float32)
+
+
+def kde_workload(seed=0, scale=1.0):
+    c = KDE_CFG
+    mu, sig, w, sup = random_gmm(seed, c["D"], c["modes"])
+    rs = np.random.RandomState(seed + 1)
+    n_c, n_e = int(c["n_centres"] * scale), int(c["n_eval"] * scale)
+    centres = gmm_samples(rs, mu, sig, w, n_c)
+    x = rs.uniform(sup[0], sup[1], size=(n_e, c["D"])).astype(np.float32)
+    return mu, sig, w, sup, centres, x
+
+
+def dm_workload(seed=10, scale=1.0):
+    c = DM_CFG
+    mu, sig, w, sup = random_gmm(seed, c["D"], c["modes"])
+    rs = np.random.RandomState(seed + 1)
+    N = c["n_proposals"]
+    pmeans = rs.uniform(sup[0], sup[1], size=(N, c["D"]))
+    per = max(1, int(c["n_samples"] * scale) // N)
+    return mu, sig, w, sup, pmeans, per
+
+
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from ais_benchmarks_b200 import _device, _lib, parallel
+    from ais_benchmarks_b200.distributions import CGaussianMixtureModel
+    from ais_benchmarks_b200.metrics import CKLDivergence
+    from ais_benchmarks_b200.sampling_methods.base import CDeviceKDE
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    dev = torch.device("cuda", local)
+    scale = args.scale
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # ---- live FP32-FMA / MUFU.EX2 peaks on this GPU (roofline denominators for the compute-bound kernels) -------
+    sink = torch.zeros(4, dtype=torch.float32, device=dev)
+    peaks = {}
+    for name, fn in (("fma", lib.aisb_peak_fma_f32), ("ex2", lib.aisb_peak_ex2_f32)):
+        import ctypes as C
+        ops = C.c_double(0)
+        best = 0.0
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(fn(4096, C.c_void_p(sink.data_ptr()), C.byref(ops), _device.stream_ptr()), "peak")
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, ops.value / (e0.elapsed_time(e1) * 1e-3))
+        peaks[name] = best
+    fp32_peak_tflops = 2.0 * peaks["fma"] / 1e12
+    ex2_peak = peaks["ex2"]
+
+    # ================================ KDE-KLD (headline) =====================================================
+    c = KDE_CFG
+    mu, sig, w, sup, centres_h, x_h = kde_workload(scale=scale)
+    n_c, n_e, D = len(centres_h), len(x_h), c["D"]
+    start, stop = parallel.shard_rows(n_e, rank, world)
+    target = CGaussianMixtureModel({"means": mu, "sigmas": sig, "weights": w, "support": sup})
+    centres_pin = torch.from_numpy(centres_h).pin_memory()
+    x_pin = torch.from_numpy(x_h[start:stop].copy()).pin_memory()
+    centres_d = centres_pin.to(dev)
+    x_d = x_pin.to(dev)
+    metric = CKLDivergence()
+    kernel_ms = []
+
+    def kde_step(resident=True):
+        """One metric evaluation. resident=False: inputs start in pinned host memory (e2e)."""
+        cd = centres_d if resident else centres_pin.to(dev, non_blocking=True)
+        xd = x_d if resident else x_pin.to(dev, non_blocking=True)
+        kde = CDeviceKDE(cd, None, n_c, c["bw"], D, sup)                 # pack kernel
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lq = kde.log_prob(xd)                                            # pairwise kernel (+ merge)
+        e1.record()
+        lp = target.log_prob(xd)
+        rec = _device.kld_partials(lp, lq)                               # device reduction
+        kld = parallel.global_kld(rec)                                   # 8 doubles D2H (+ all-gather)
+        kernel_ms.append((e0, e1))
+        return kld
+
+    for _ in range(args.warmup):
+        kld_val = kde_step()
+    kernel_ms.clear()
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        kld_val = kde_step()
+    t1.record()
+    barrier()
+    kde_ms = max_over_ranks(t0.elapsed_time(t1)) / args.steps
+    pair_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_ms]))
+    kernel_ms.clear()
+
+    # e2e: inputs in pinned host memory every step, result read back; wall clock around the public API
+    for _ in range(max(1, args.warmup // 2)):
+        kde_step(resident=False)
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        kde_step(resident=False)
+    barrier()
+    kde_e2e_ms = max_over_ranks((time.perf_counter() - w0) * 1e3) / args.steps
+    clock_info = clocks.stop() if rank == 0 else None
+    kernel_ms.clear()
+
+    total_pairs = float(n_c) * float(n_e)
+    local_pairs = float(n_c) * float(stop - start)
+    flop_per_pair = 3 * D + 6            # isotropic pair, direct form
+    achieved_tflops = local_pairs * flop_per_pair / (pair_kernel_ms * 1e-3) / 1e12
+
+    # ================================ DM-AIS weighting ========================================================
+    dc = DM_CFG
+    mu2, sig2, w2, sup2, pmeans, per = dm_workload(scale=scale)
+    N, D2 = dc["n_proposals"], dc["D"]
+    per_local = parallel.shard_rows(per, rank, world)
+    per_r = per_local[1] - per_local[0]
+    target2 = CGaussianMixtureModel({"means": mu2, "sigmas": sig2, "weights": w2, "support": sup2})
+    tmix = target2.device_mixture()
+    pm_d = torch.from_numpy(pmeans).to(dev, torch.float32).contiguous()
+    qmix = _device.DeviceMixture.kde(pm_d, None, N, dc["sigma"])
+    _device.seed(1234 + rank)
+    xs = _device.sample_iso(pm_d, per_r, dc["sigma"])     # proposal-major samples, resident in HBM
+    n_local = xs.shape[0]
+    n_total = N * per
+    xs_pin = torch.empty(xs.shape, dtype=torch.float32).pin_memory()
+    xs_pin.copy_(xs)
+    dm_kernel = []
+
+    def dm_step(resident=True):
+        xd = xs if resident else xs_pin.to(dev, non_blocking=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        logw, _, _, part = _device.dm_weights(xd, tmix, None, qmix)      # fused kernel + partial merge
+        e1.record()
+        g = parallel.global_weight_partials(part)                        # 4 doubles D2H (+ all-gather)
+        wn = _device.normalize_weights(logw, g)                          # normalised weights stay in HBM
+        dm_kernel.append((e0, e1))
+        return _device.weight_ess(g) / n_total, wn
+
+    for _ in range(args.warmup):
+        ness, _ = dm_step()
+    dm_kernel.clear()
+    barrier()
+    t0.record()
+    for _ in range(args.steps):
+        ness, _ = dm_step()
+    t1.record()
+    barrier()
+    dm_ms = max_over_ranks(t0.elapsed_time(t1)) / args.steps
+    dm_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in dm_kernel]))
+    dm_kernel.clear()
+    dm_step(resident=False)
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        ness_e, wn = dm_step(resident=False)
+        _ = wn[:1].cpu()
+    barrier()
+    dm_e2e_ms = max_over_ranks((time.perf_counter() - w0) * 1e3) / args.steps
+    dm_flops = float(n_local) * (N * (3 * D2 + 6) + dc["modes"] * (4 * D2 + 6))
+    dm_tflops = dm_flops / (dm_kernel_ms * 1e-3) / 1e12
+
+    # ================================ CPU baseline (rank 0, N = 1 only) ======================================
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_kde(cores=1, budget_s=12.0)
+
+    if rank == 0:
+        pk, pk_src = measured_peaks()
+        out = {
+            "metric": METRIC, "value": total_pairs / (kde_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": kde_ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[3]: KDE-KLD, D=8, %d KDE centres x %d eval points, 16-mode GMM "
+                                   "target, bw=0.02; eval points sharded over %d GPU(s)" % (n_c, n_e, world),
+                       "l2": "inputs (%.0f MB centres + %.0f MB points) exceed nothing; the pairwise kernel is "
+                             "compute-bound and re-reads the centres from L2 by design; no flush" %
+                             (n_c * D * 4 / 1e6, n_e * D * 4 / 1e6),
+                       "kld": kld_val, "scale": scale},
+            "e2e": {"value": total_pairs / (kde_e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(centres_pin.numel() * 4 + x_pin.numel() * 4), "d2h_bytes_per_step": 64,
+                    "ms_per_step": kde_e2e_ms},
+            "gpu_launches": 6 * args.steps,
+            "clocks": clock_info,
+            "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+                         "frac": achieved_tflops / fp32_peak_tflops, "traffic": None,
+                         "kernel": "logpdf_kernel<ISO_SHARED, 8, no offsets>", "kernel_ms": pair_kernel_ms,
+                         "flop_per_pair": flop_per_pair,
+                         "peak_source": "live FFMA micro-benchmark in this run (aisb_peak_fma_f32); nominal 74.5",
+                         "mufu": {"achieved_gops": local_pairs / (pair_kernel_ms * 1e-3) / 1e9,
+                                  "peak_gops": ex2_peak / 1e9},
+                         "hbm_peak_gbs": pk.get("hbm_gbs"), "hbm_peak_source": pk_src},
+            "cpu_baseline": cpu,
+            "dm_ais": {"metric": "DM-AIS weighted samples/sec", "value": n_total / (dm_ms * 1e-3), "unit": "samples/s",
+                       "ms_per_step": dm_ms,
+                       "config": {"workload": "BASELINE configs[4]: D=32, 64-mode GMM target, %d samples x %d "
+                                              "proposals, sigma=0.05; samples sharded over %d GPU(s)" %
+                                              (n_total, N, world), "ness": ness},
+                       "e2e": {"value": n_total / (dm_e2e_ms * 1e-3), "unit": "samples/s",
+                               "h2d_bytes_per_step": int(xs_pin.numel() * 4), "d2h_bytes_per_step": 36,
+                               "ms_per_step": dm_e2e_ms},
+                       "roofline": {"bound": "fp32", "achieved": dm_tflops, "peak": fp32_peak_tflops,
+                                    "unit": "TFLOP/s", "frac": dm_tflops / fp32_peak_tflops,
+                                    "kernel": "dm_weights_kernel<32, ISO_SHARED>", "kernel_ms": dm_kernel_ms},
+                       "gpu_launches": 3 * args.steps},
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arms: the reference algorithm as restated by the oracle (per-component loop + logsumexp, float64)
+# ----------------------------------------------------------------------------------------------------
+def _cpu_kde_chunk(task):
+    from oracle import ais_oracle as O
+    x, centres, bw, mu, sig, w = task
+    covs = np.stack([np.eye(centres.shape[1]) * bw] * len(centres))
+    lq = O.mixture_log_prob(x, centres, covs, np.full(len(centres), 1.0 / len(centres)))   # reference hot loop #3
+    lp = O.gmm_log_prob(x, mu, sig, w)
+    return lp, lq
+
+
+def cpu_kde_once(n_eval, n_centres, cores, seed=0):
+    from oracle import ais_oracle as O
+    c = KDE_CFG
+    mu, sig, w, sup = random_gmm(seed, c["D"], c["modes"])
+    rs = np.random.RandomState(seed + 1)
+    centres = gmm_samples(rs, mu, sig, w, n_centres).astype(np.float64)
+    x = rs.uniform(sup[0], sup[1], size=(n_eval, c["D"]))
+    chunks = np.array_split(x, cores)
+    tasks = [(ch, centres, c["bw"], mu, sig, w) for ch in chunks]
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [_cpu_kde_chunk(tasks[0])]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(cores) as pool:
+            res = pool.map(_cpu_kde_chunk, tasks)
+    lp = np.concatenate([r[0] for r in res])
+    lq = np.concatenate([r[1] for r in res])
+    kld = O.kld_from_log_probs(lp, lq)
+    return time.perf_counter() - t0, kld
+
+
+def cpu_baseline_kde(cores, budget_s):
+    n_eval, n_centres = 2048 * cores, 2000
+    dt, _ = cpu_kde_once(n_eval, n_centres, cores)
+    rate = n_eval * n_centres / dt
+    n_centres = int(max(2000, min(40000, rate * budget_s / n_eval)))
+    dt, kld = cpu_kde_once(n_eval, n_centres, cores)
+    return {"value": n_eval * n_centres / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "oracle port of the reference algorithm (per-component float64 loop + logsumexp, "
+                      "CMixtureModel.py:43-57 + divergences.py:136-153) on %d eval points x %d centres, D=8, %.1f s"
+                      % (n_eval, n_centres, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = []
+    n_eval, n_centres = 1024 * cores, 4000
+    for _ in range(args.warmup):
+        cpu_kde_once(256 * cores, 500, cores)
+    for _ in range(args.steps):
+        dt, kld = cpu_kde_once(n_eval, n_centres, cores)
+        per_step.append(dt)
+    ms = float(np.mean(per_step)) * 1e3
+    val = n_eval * n_centres / (ms * 1e-3)
+    sample = ("oracle port of the reference CPU algorithm, %d processes, each step = %d eval points x %d centres "
+              "(bounded sample of the 1e6 x 1e6 workload; the rate is size-independent)" % (cores, n_eval, n_centres))
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "BASELINE configs[3]: KDE-KLD, D=8, 16-mode GMM target, bw=0.02 (bounded sample)"},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink both workloads (smoke / ncu captures)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

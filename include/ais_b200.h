@@ -1,0 +1,249 @@
+/*
+ * ais_b200.h -- C ABI of libais_b200.so: the B200 (sm_100a) implementation of the
+ * ais-benchmarks density / importance-weight / KLD hot path.
+ *
+ * The reference (IntelLabs/ais-benchmarks) is pure Python/numpy and has no FFI of
+ * its own; the binding a maintainer adds is a ctypes stub.
+ * Each entry point below names the reference code it replaces
+ * (paths relative to the reference root).
+ *
+ * Conventions
+ *  - Pointers named d_* are DEVICE pointers owned by the caller. Pointers named
+ *    h_* are HOST pointers. The library never allocates or frees caller memory;
+ *    scratch space is passed in explicitly (see the *_bytes queries).
+ *  - Every device call is asynchronous on `stream` (a cudaStream_t passed as
+ *    void*; NULL = legacy default stream).
+ *  - Return value: 0 (AISB_OK) or a negative aisb_status. No exception crosses
+ *    the ABI. aisb_last_error() returns a thread-local message for the last failure.
+ *  - All point sets are batch-first row-major float32 [n, D] (the reference's
+ *    (N, D) float64 layout, distributions/distributions.py:35-37, cast to fp32).
+ *  - Component parameters are passed PACKED (see "Packed mixture layout");
+ *    packing is done once per parameter update in float64 on the host
+ *    (aisb_pack_mixture_f64) or on device for KDE centres (aisb_kde_pack_f32).
+ */
+#ifndef AIS_B200_H
+#define AIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AISB_ABI_VERSION 1
+
+typedef enum aisb_status {
+  AISB_OK = 0,
+  AISB_ERR_INVALID = -1,     /* bad argument (null pointer, D out of range, ...) */
+  AISB_ERR_UNSUPPORTED = -2, /* shape/kind combination not built */
+  AISB_ERR_CUDA = -3,        /* a CUDA runtime call failed (message has the cudaError string) */
+  AISB_ERR_WORKSPACE = -4    /* workspace too small */
+} aisb_status;
+
+/* Covariance kinds of a packed Gaussian mixture. */
+typedef enum aisb_cov_kind {
+  AISB_COV_ISO_SHARED = 0, /* every component has covariance v*I with the SAME v (KDE, DM-AIS/LAIS proposals) */
+  AISB_COV_DIAG = 1,       /* per-component diagonal covariance (CGaussianMixtureModel) */
+  AISB_COV_FULL = 2        /* per-component full covariance (CMultivariateNormal, M-PMC after adapt) */
+} aisb_cov_kind;
+
+#define AISB_MAX_DIMS 64
+
+/*
+ * Packed mixture layout (all float32, log2 domain; LOG2E = 1/ln 2).
+ *
+ * For a component k with mean mu_k, covariance Sigma_k and normalised weight w_k
+ * (CMixtureModel.set_weights, distributions/mixture/CMixtureModel.py:25-41):
+ *     log2 (w_k N(x; mu_k, Sigma_k)) = c_k - || A_k x + b_k ||^2
+ *   c_k = LOG2E * ( log w_k - 0.5 * (D log 2pi + log det Sigma_k) )      (-inf if w_k == 0)
+ *   A_k = sqrt(LOG2E / 2) * L_k^{-1},  Sigma_k = L_k L_k^T (Cholesky),  b_k = -A_k mu_k
+ * (CMultivariateNormal.log_prob, distributions/parametric/CMultivariateNormal.py:67-71).
+ *
+ * DP = aisb_padded_dims(D) is D rounded up to {1,2,4,8,16,32,64}; KP = K rounded up
+ * to a multiple of AISB_COMP_ALIGN. Padding dims hold 0; padding components hold
+ * c = -inf (offsets present) or coordinate 1e18 (no offsets).
+ *
+ *  ISO_SHARED: rows[KP][DP]           = b_k = -a * mu_k,  a = sqrt(LOG2E / (2 v));  `a` is passed as `iso_scale`
+ *  DIAG:       rows[KP][2*DP]         = a_k[0..DP) then b_k[0..DP),  a_kd = sqrt(LOG2E / (2 v_kd)), b_kd = -a_kd mu_kd
+ *  FULL:       rows[KP][RF], RF = DP*(DP+1)/2 + DP rounded up to a multiple of 4
+ *              = lower triangle of A_k row-major (A00, A10, A11, A20, ...), then b_k, then zero padding (D <= 32 only)
+ *  offsets[KP] = c_k  (may be NULL for ISO_SHARED: all components share `uniform_offset`)
+ */
+#define AISB_COMP_ALIGN 32
+
+typedef struct aisb_packed_mixture {
+  const float* d_rows;    /* device, layout above, 16-byte aligned */
+  const float* d_offsets; /* device [KP] or NULL (ISO_SHARED only) */
+  int64_t K;              /* real number of components */
+  int32_t D;              /* real dimensionality, 1..AISB_MAX_DIMS */
+  int32_t cov_kind;       /* aisb_cov_kind */
+  float iso_scale;        /* ISO_SHARED: a = sqrt(LOG2E / (2 v)); ignored otherwise */
+  float uniform_offset;   /* natural-log constant added to every result when d_offsets == NULL:
+                             log w - 0.5 * D * log(2 pi v); ignored otherwise */
+} aisb_packed_mixture;
+
+int aisb_abi_version(void);
+const char* aisb_last_error(void);
+
+/* Rounded-up dimensionality used by the packed layouts; 0 if D is unsupported. */
+int32_t aisb_padded_dims(int32_t D);
+/* Floats per packed row for (kind, D); 0 if unsupported. */
+int64_t aisb_packed_row_floats(int32_t cov_kind, int32_t D);
+/* K rounded up to AISB_COMP_ALIGN. */
+int64_t aisb_padded_components(int64_t K);
+/* a = (float) sqrt(LOG2E / (2 v)): the ISO_SHARED scale for kernel variance v (same rounding everywhere). */
+float aisb_iso_scale(double variance);
+
+/*
+ * HOST-side float64 -> packed float32 conversion (no CUDA). Replaces the per-object
+ * precompute of CMultivariateNormal.__init__/set_moments (CMultivariateNormal.py:26-62:
+ * det, inv, log_det, term1, term2) and CMixtureModel.set_weights (CMixtureModel.py:25-41,
+ * NaN/<=0 -> 0, then / sum if sum > 0).
+ *   h_means [K, D]; h_cov: ISO_SHARED -> [1] variance; DIAG -> [K, D] variances;
+ *   FULL -> [K, D, D] covariance matrices; h_weights [K] raw weights or NULL (= equal, 1/K).
+ *   h_rows [KP * row_floats], h_offsets [KP] out.
+ * Returns AISB_ERR_INVALID if a covariance is not positive definite (reference: assert det > 0).
+ */
+int aisb_pack_mixture_f64(const double* h_means, const double* h_cov, const double* h_weights, int64_t K, int32_t D,
+                          int32_t cov_kind, float* h_rows, float* h_offsets, float* iso_scale);
+
+/*
+ * KDE model build on device. Replaces CMixtureSamplingMethod._update_model
+ * (sampling_methods/base.py:162-179): n_c isotropic kernels N(x_idx[j], bw*I) with equal weights.
+ *   d_samples [n, D]; d_idx [n_c] int64 row indices into d_samples, or NULL (identity, n_c <= n);
+ *   bw = kernel VARIANCE (reference quirk: "bw" goes on the covariance diagonal);
+ *   d_rows out [aisb_padded_components(n_c) * DP].
+ * The matching aisb_packed_mixture is {d_rows, NULL, n_c, D, ISO_SHARED, sqrt(LOG2E/(2 bw)),
+ *   -log(n_c) - 0.5 * D * log(2 pi bw)}.
+ */
+int aisb_kde_pack_f32(const float* d_samples, int64_t n, int32_t D, const int64_t* d_idx, int64_t n_c, double bw,
+                      float* d_rows, void* stream);
+
+/*
+ * Workspace (bytes) needed by aisb_mixture_logpdf_f32 / aisb_dm_weights_f32 for n points
+ * against K components (split-component partials + block partials).
+ */
+int aisb_workspace_bytes(int64_t n, int64_t K, int32_t D, size_t* bytes);
+
+/*
+ * Mixture log-density:  out_logp[i] = log sum_k w_k N(x_i; mu_k, Sigma_k)   (natural log).
+ * Replaces CMixtureModel.log_prob (CMixtureModel.py:43-57: loop over components +
+ * scipy logsumexp(b=weights)), CGaussianMixtureModel.log_prob (CGaussianMixtureModel.py:40-41),
+ * CMultivariateNormal.log_prob (K == 1) and the KDE evaluation reached through
+ * CMixtureSamplingMethod.log_prob (sampling_methods/base.py:156-159).
+ */
+int aisb_mixture_logpdf_f32(const float* d_x, int64_t n, const aisb_packed_mixture* mix, float* d_out_logp,
+                            void* d_workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Deterministic-mixture importance weights in one pass over the samples:
+ *   logp_i = log pi(x_i) (target mixture, or read from d_logp_in when target == NULL),
+ *   logq_i = log q(x_i)  (proposal mixture),  logw_i = logp_i - logq_i.
+ * Replaces the per-sample loop `w = target_d.prob(s) / self.prob(s)` of
+ * CDeterministicMixtureAIS.importance_sample (sampling_methods/dm_ais.py:72-76),
+ * CLayeredAIS.importance_sample (layered_ais.py:90-94) and the pi_x/q_x part of
+ * CMixturePMC.importance_sample (m_pmc.py:93-96).
+ *   d_out_logw [n]; d_out_logp, d_out_logq [n] or NULL;
+ *   d_out_partials [4] doubles: {M = max_i logw_i, sum_i exp(logw_i - M), sum_i exp(2 (logw_i - M)), n_finite}
+ *   computed over finite logw_i only (reference weights that are inf/nan are excluded).
+ */
+int aisb_dm_weights_f32(const float* d_x, int64_t n, const aisb_packed_mixture* target, const float* d_logp_in,
+                        const aisb_packed_mixture* proposals, float* d_out_logw, float* d_out_logp, float* d_out_logq,
+                        double* d_out_partials, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Partials of an existing log-weight vector (same 4 doubles as above). Used when samples
+ * accumulate over iterations (dm_ais.py:81-86 normalises over ALL iterations).
+ */
+int aisb_logw_partials_f32(const float* d_logw, int64_t n, double* d_out_partials, void* d_workspace,
+                           size_t workspace_bytes, void* stream);
+
+/*
+ * Normalised weights  w_i = exp(logw_i - (M + log S))  from (possibly all-reduced) partials.
+ * Replaces `self.weights / self.weights.sum()` (dm_ais.py:86, m_pmc.py:108).
+ * h_partials: the 4 doubles on the HOST (after any cross-rank merge).
+ */
+int aisb_normalize_weights_f32(const float* d_logw, int64_t n, const double* h_partials, float* d_out_w, void* stream);
+
+/*
+ * Host-side helpers on partials (no CUDA): merge two partial records with the
+ * log-sum-exp rescale rule; ESS = 1 / sum w~^2 (sampling_methods/base.py:72-75).
+ */
+void aisb_weight_partials_merge(const double* a, const double* b, double* out);
+double aisb_weight_partials_ess(const double* partials);
+double aisb_weight_partials_logsum(const double* partials);
+
+/*
+ * KLD one-pass partials over (lp, lq) pairs:
+ *   inliers I = { i : lp_i > -inf and lq_i > -inf }  (metrics/divergences.py:138-139)
+ *   d_out_partials [8] doubles: { m_p, S_p = sum_I exp(lp - m_p), A = sum_I exp(lp - m_p) (lp - lq),
+ *                                  m_q, S_q = sum_I exp(lq - m_q), n_inlier, n_nan_q, n_total }
+ * Replaces CKLDivergence.compute_from_log_probs (divergences.py:136-153).
+ */
+int aisb_kld_partials_f32(const float* d_lp, const float* d_lq, int64_t n, double* d_out_partials, void* d_workspace,
+                          size_t workspace_bytes, void* stream);
+/* Host: merge two KLD partial records / finish:  KLD = A/S_p - (m_p + log S_p) + (m_q + log S_q);
+ * +inf if any lq in I is NaN; 0.0 if I is empty (divergences.py:147-153, 105). */
+void aisb_kld_partials_merge(const double* a, const double* b, double* out);
+double aisb_kld_finalize(const double* partials);
+
+/*
+ * M-PMC Rao-Blackwellised moment accumulation (sampling_methods/m_pmc.py:57-61, 102-105):
+ *   rho_{d,i} = exp(log alpha_d + log q_d(x_i) - log q(x_i)),
+ *   out[d][0]      = sum_i w~_i rho_{d,i}            (alpha_d numerator)
+ *   out[d][1..D]   = sum_i w~_i rho_{d,i} x_i        (mean numerator)
+ * w~_i = exp(logw_i - log_norm).  `proposals` offsets must hold log2 (alpha_d N-normaliser).
+ *   d_out [K, D+1] doubles, ZEROED by the caller (the kernel accumulates with atomics so
+ *   that ranks / batches can be chained).
+ */
+int aisb_mpmc_moments_f32(const float* d_x, int64_t n, const aisb_packed_mixture* proposals, const float* d_logq,
+                          const float* d_logw, double log_norm, double* d_out, void* stream);
+
+/*
+ * First and second raw moments of a point set, in float64:  out = { sum_i x_i [D], sum_i x_i x_i^T [D*D] }.
+ * Used for the (unweighted, quirk Q3) scatter of m_pmc.py:64-68. d_out [D + D*D] doubles, zeroed by the caller.
+ */
+int aisb_raw_moments_f32(const float* d_x, int64_t n, int32_t D, double* d_out, void* stream);
+
+/*
+ * LAIS upper layer: N independent Metropolis-Hastings chains, L steps each, all on device
+ * (sampling_methods/layered_ais.py:54-74). Noise is supplied by the caller so that the
+ * result is a pure function of its inputs (RNG streams are not part of the contract):
+ *   d_means [N, D] in/out (chain states = proposal means); d_delta [L, N, D] ~ N(0, mh_sigma I);
+ *   d_u [L, N] ~ U(0,1); proposals are clipped to [d_lo, d_hi] ([D] each); accept when
+ *   pi(x_hat) / pi(x) > u  (linear-domain ratio, layered_ais.py:63-66).
+ */
+int aisb_lais_mh_f32(float* d_means, int64_t N, const aisb_packed_mixture* target, const float* d_delta,
+                     const float* d_u, int32_t L, const float* d_lo, const float* d_hi, void* stream);
+
+/*
+ * Mixture of axis-aligned boxes ("haar" leaves of TP-AIS and CMultivariateUniform):
+ *   out_logp[i] = log sum_k w_k [lo_k < x_i (<|<=) hi_k] / vol_k
+ * open_upper != 0: lo < x <  hi  (tree_pyramid.py:595-596);  0: lo < x <= hi (CMultivariateUniform.py:44).
+ *   d_lo, d_hi [K, D]; d_logw_over_vol [K] = log(w_k / vol_k).  D <= 32.
+ */
+int aisb_box_mixture_logpdf_f32(const float* d_x, int64_t n, int32_t D, const float* d_lo, const float* d_hi,
+                                const float* d_logw_over_vol, int64_t K, int32_t open_upper, float* d_out_logp,
+                                void* stream);
+
+/*
+ * Device-side sampling (Philox4x32-10 + Box-Muller). RNG streams are NOT comparable with numpy's.
+ *  aisb_sample_iso_f32: out[(k*per + j), :] = means[k] + sqrt(var) * z  for k < K, j < per
+ *      (DM-AIS / LAIS: K samples from each of N proposals, dm_ais.py:64-69).
+ *  aisb_uniform_box_f32: out[i, d] ~ U(lo_d, hi_d)  (CDivergence.compute eval points, divergences.py:84-85).
+ */
+int aisb_sample_iso_f32(const float* d_means, int64_t K, int32_t D, int64_t per, double var, uint64_t seed,
+                        uint64_t offset, float* d_out, void* stream);
+int aisb_uniform_box_f32(const float* d_lo, const float* d_hi, int32_t D, int64_t n, uint64_t seed, uint64_t offset,
+                         float* d_out, void* stream);
+
+/* Micro-benchmarks used to measure the FP32-FMA and MUFU.EX2 peaks on the box (bench.py roofline denominators).
+ * Each runs `iters` dependent-chain iterations in every thread of a full-chip grid; returns ops executed via *ops. */
+int aisb_peak_fma_f32(int64_t iters, float* d_sink, double* ops, void* stream);
+int aisb_peak_ex2_f32(int64_t iters, float* d_sink, double* ops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIS_B200_H */

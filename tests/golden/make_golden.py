@@ -1,0 +1,312 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on seeded inputs.
+
+Run here (the build container), not on the GPU box:  python tests/golden/make_golden.py
+Every fixture stores the float64 inputs next to the reference's float64 outputs, so the tests
+can feed the same numbers to the oracle (CPU) and to the CUDA path (GPU) without the reference.
+RNG streams are never part of a fixture's contract: wherever the reference draws random numbers
+inside the code under test (MH noise, KDE resampling), the draws are captured and stored.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_harness  # noqa: E402
+
+ref_harness.load()
+from ais_benchmarks.distributions import (CGaussianMixtureModel, CMixtureModel, CMultivariateNormal,  # noqa: E402
+                                          CMultivariateUniform)
+from ais_benchmarks.metrics.divergences import CKLDivergence  # noqa: E402
+from ais_benchmarks.sampling_methods import CDeterministicMixtureAIS, CLayeredAIS, CMixturePMC  # noqa: E402
+from ais_benchmarks.sampling_methods.base import CMixtureSamplingMethod  # noqa: E402
+from ais_benchmarks.utils.misc import generateRandomGMM  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("%-28s %7.1f KB" % (name + ".npz", os.path.getsize(path) / 1024.0))
+
+
+def random_gmm(seed, dims, k):
+    """BASELINE.json configs 2-5 targets: generateRandomGMM (utils/misc.py:40-60), 'sigma' = variances."""
+    np.random.seed(seed)
+    return generateRandomGMM(np.full(dims, -1.0), np.full(dims, 1.0), k,
+                             sigma_min=np.full(dims, 0.04), sigma_max=np.full(dims, 0.05))
+
+
+def gmm_arrays(g):
+    return np.array(g.means, dtype=np.float64), np.array(g.sigmas, dtype=np.float64), np.array(g.weights, dtype=np.float64)
+
+
+# ----------------------------------------------------------------------------------------------
+def make_mvn():
+    rs = np.random.RandomState(1)
+    out = {}
+    cases = []
+    # the reference's own test inputs (tests/distributions/test_multivariate_normal_unittest.py:17-48)
+    cases.append((np.array([0.0]), np.diag([1.5]), np.array([[0], [0.2], [-2], [-.2]], dtype=np.float64)))
+    cases.append((np.zeros(3), np.diag([1.5, 1.5, 1.5]),
+                  np.array([[0, 0, 0], [0, .2, 0], [-2, 0, .3], [-.2, .1, .3]], dtype=np.float64)))
+    # full covariance, random SPD, D = 4 and D = 8
+    for d in (4, 8):
+        a = rs.normal(size=(d, d))
+        cases.append((rs.normal(size=d), a @ a.T / d + 0.1 * np.eye(d), rs.normal(size=(64, d)) * 1.5))
+    # the non-symmetric "covariance" of CMultivariateNormal.py's __main__ demo (:97-99)
+    cases.append((np.zeros(2), np.array([[0.1, .2], [.0, .2]]), rs.uniform(-1, 1, size=(64, 2))))
+    # default-config Normal target (benchmark/def_benchmark.yaml:26-28)
+    cases.append((np.array([0.0]), np.array([[0.2]]), rs.uniform(-5, 5, size=(256, 1))))
+    for i, (mean, cov, x) in enumerate(cases):
+        dist = CMultivariateNormal({"mean": mean.copy(), "sigma": cov.copy()})
+        out["mean%d" % i], out["cov%d" % i], out["x%d" % i] = mean, cov, x
+        out["logp%d" % i] = dist.log_prob(x)
+        out["prob%d" % i] = dist.prob(x)
+        out["support%d" % i] = dist.support()
+    out["n"] = np.array(len(cases))
+    save("mvn", **out)
+
+
+def make_gmm():
+    rs = np.random.RandomState(2)
+    out = {}
+    targets = []
+    # benchmark/def_benchmark.yaml:4-24 verbatim
+    targets.append(CGaussianMixtureModel({"means": [[1.5], [-4.2], [0.01], [7.5]],
+                                          "sigmas": [[0.4], [0.05], [0.003], [0.003]],
+                                          "weights": [0.4, 0.4, 0.1, 0.1], "support": [[-10], [10]]}))
+    targets.append(CGaussianMixtureModel({"means": [[0.0, 0.0], [-0.3, 0.5]], "sigmas": [[0.01, 0.1], [0.01, 0.03]],
+                                          "weights": [0.5, 0.5], "support": [[-1, -1], [1, 1]]}))
+    targets.append(random_gmm(10, 2, 4))    # config 2 target
+    targets.append(random_gmm(11, 8, 16))   # config 3/4 target
+    targets.append(random_gmm(12, 32, 64))  # config 5 target
+    targets.append(random_gmm(13, 3, 5))    # non power-of-two D
+    for i, g in enumerate(targets):
+        means, sigmas, weights = gmm_arrays(g)
+        sup = g.support()
+        n = 2000 if g.dims <= 2 else 384
+        x = rs.uniform(sup[0], sup[1], size=(n, g.dims))
+        # half of the points near the modes so that |log p| = O(1) cases are covered too
+        idx = rs.randint(0, len(means), size=n // 2)
+        x[: n // 2] = means[idx] + rs.normal(size=(n // 2, g.dims)) * np.sqrt(sigmas[idx])
+        out["means%d" % i], out["sigmas%d" % i], out["weights%d" % i] = means, sigmas, weights
+        out["support%d" % i], out["x%d" % i] = sup, x
+        out["logp%d" % i] = g.log_prob(x)
+        out["prob%d" % i] = g.prob(x)
+    out["n"] = np.array(len(targets))
+    save("gmm", **out)
+
+
+def make_mixture():
+    """CMixtureModel over full-covariance components with zero / NaN / negative weights (CMixtureModel.py:25-41)."""
+    rs = np.random.RandomState(3)
+    d, k = 3, 6
+    means = rs.uniform(-1, 1, size=(k, d))
+    covs = np.empty((k, d, d))
+    for j in range(k):
+        a = rs.normal(size=(d, d))
+        covs[j] = a @ a.T / d * 0.2 + 0.05 * np.eye(d)
+    weights = np.array([0.3, 0.0, np.nan, 0.5, -1.0, 0.2])
+    models = [CMultivariateNormal({"mean": means[j].copy(), "sigma": covs[j].copy()}) for j in range(k)]
+    mix = CMixtureModel({"models": models, "weights": weights.copy(), "dims": d, "support": [[-2] * d, [2] * d]})
+    x = rs.uniform(-2, 2, size=(500, d))
+    save("mixture", means=means, covs=covs, weights=weights, norm_weights=np.array(mix.weights), x=x,
+         logp=mix.log_prob(x), prob=mix.prob(x), logp_single=mix.log_prob(x[0]))
+
+
+def make_dm_weights():
+    """DM-AIS weights exactly as shipped: per-sample loop w = pi(s) / q(s) (sampling_methods/dm_ais.py:58-86)."""
+    out = {}
+    cfgs = [(2, 4, 64, 4, 0.05, 20), (8, 16, 64, 2, 0.05, 21), (1, None, 5, 10, 0.5, 22)]
+    for i, (dims, k, N, K, sigma, seed) in enumerate(cfgs):
+        if k is None:  # default config: 1-D Normal target + def_methods.yaml:61-68 DM-AIS
+            target = CMultivariateNormal({"mean": np.array([0.0]), "sigma": np.array([[0.2]]),
+                                          "support": np.array([[-5.0], [5.0]])})
+            out["tmeans%d" % i], out["tsigmas%d" % i], out["tweights%d" % i] = \
+                np.array([[0.0]]), np.array([[0.2]]), np.array([1.0])
+        else:
+            target = random_gmm(seed, dims, k)
+            out["tmeans%d" % i], out["tsigmas%d" % i], out["tweights%d" % i] = gmm_arrays(target)
+        np.random.seed(seed + 100)
+        sup = target.support()
+        s = CDeterministicMixtureAIS({"space_min": sup[0], "space_max": sup[1], "dims": dims,
+                                      "K": K, "N": N, "J": 1000, "sigma": sigma})
+        out["pmeans%d" % i] = np.array([p.loc for p in s.proposals])
+        samples, norm_w = s.importance_sample(target, N * K, timeout=600)  # exactly one iteration
+        out["x%d" % i] = np.array(samples)
+        out["w%d" % i] = np.array(s.weights)
+        out["norm_w%d" % i] = np.array(norm_w)
+        out["ness%d" % i] = np.array(s.get_NESS())
+        out["sigma%d" % i] = np.array(sigma)
+        # proposal mixture density at the samples with the PRE-adaptation proposals
+        pre = CMixtureModel({"models": [CMultivariateNormal({"mean": m, "sigma": np.eye(dims) * sigma})
+                                        for m in out["pmeans%d" % i]],
+                             "weights": np.full(N, 1.0 / N), "dims": dims, "support": [sup[0], sup[1]]})
+        out["logq%d" % i] = pre.log_prob(np.array(samples))
+        out["logp%d" % i] = target.log_prob(np.array(samples))
+    out["n"] = np.array(len(cfgs))
+    save("dm_weights", **out)
+
+
+class _KdeHolder(CMixtureSamplingMethod):
+    """Smallest concrete user of the reference's KDE builder (sampling_methods/base.py:135-179)."""
+
+    def __init__(self, params):
+        super().__init__(params)
+        self.bw = params["kde_bw"]
+
+    def importance_sample(self, target_d, n_samples, timeout):
+        raise NotImplementedError
+
+
+def make_kde_kld():
+    out = {}
+    cfgs = [(2, 4, 400, 100, 0.02, 2000, 30), (8, 16, 3000, 1000, 0.02, 1024, 31), (1, 3, 200, 100, 0.01, 2000, 32)]
+    for i, (dims, k, n_samples, n_kde, bw, n_eval, seed) in enumerate(cfgs):
+        target = random_gmm(seed, dims, k)
+        sup = target.support()
+        np.random.seed(seed + 100)
+        holder = _KdeHolder({"space_min": sup[0], "space_max": sup[1], "dims": dims, "n_samples_kde": n_kde,
+                             "kde_bw": bw})
+        means, sigmas, weights = gmm_arrays(target)
+        comp = np.random.randint(0, k, size=n_samples)
+        holder.samples = means[comp] + np.random.normal(size=(n_samples, dims)) * np.sqrt(sigmas[comp])
+        holder._update_model()
+        centres = np.array([m.loc for m in holder.model.models])
+        x = np.random.uniform(sup[0], sup[1], size=(n_eval, dims))
+        lq = holder.log_prob(x)
+        lp = target.log_prob(x)
+        metric = CKLDivergence()
+        kld = metric.compute_from_samples(target, holder, x)
+        out["tmeans%d" % i], out["tsigmas%d" % i], out["tweights%d" % i] = means, sigmas, weights
+        out["centres%d" % i], out["bw%d" % i], out["x%d" % i] = centres, np.array(bw), x
+        out["lp%d" % i], out["lq%d" % i], out["kld%d" % i] = lp, lq, np.array(kld)
+        out["terms%d" % i] = CKLDivergence.compute_from_log_probs(lp.copy(), lq.copy())
+    out["n"] = np.array(len(cfgs))
+    # closed-form Gaussian cases of tests/metrics/test_metric_kldivergence.py:77-135 on seeded uniform points
+    kat = [([0.], [0.01], [[1.]], [[1.]]), ([0.], [2.], [[1.]], [[1.]]), ([0.], [5.], [[1.]], [[.1]]),
+           ([0.], [2.], [[2.]], [[2.]]), ([0., 0., 0.], [5., 5., 5.], np.eye(3).tolist(), (np.eye(3) * .5).tolist())]
+    for j, (m0, m1, s0, s1) in enumerate(kat):
+        p = CMultivariateNormal({"mean": np.array(m0), "sigma": np.array(s0)})
+        q = CMultivariateNormal({"mean": np.array(m1), "sigma": np.array(s1)})
+        np.random.seed(40 + j)
+        out["kat_m0_%d" % j], out["kat_m1_%d" % j] = np.array(m0), np.array(m1)
+        out["kat_s0_%d" % j], out["kat_s1_%d" % j] = np.array(s0), np.array(s1)
+        out["kat_seed_%d" % j] = np.array(40 + j)
+        out["kat_kld_%d" % j] = np.array(CKLDivergence().compute(p=p, q=q, nsamples=100000))
+    out["n_kat"] = np.array(len(kat))
+    # edge cases of compute_from_log_probs: -inf entries on either side, empty inlier set
+    lp = np.array([-1.0, -np.inf, -2.0, -0.5, -3.0])
+    lq = np.array([-1.5, -1.0, -np.inf, -0.7, -2.0])
+    out["edge_lp"], out["edge_lq"] = lp, lq
+    out["edge_kld"] = np.array(np.sum(CKLDivergence.compute_from_log_probs(lp.copy(), lq.copy())))
+    out["empty_kld"] = np.array(np.sum(CKLDivergence.compute_from_log_probs(np.full(4, -np.inf), np.zeros(4))))
+    save("kde_kld", **out)
+
+
+def make_mpmc():
+    """Two M-PMC iterations (sampling_methods/m_pmc.py:80-118): the first from isotropic proposals, the second from the
+    adapted ones (full covariance when the 10*I failsafe does not fire)."""
+    out = {}
+    cfgs = [(2, 0.3, 6, 40, 0.001, 50), (3, 1.0, 8, 60, 0.01, 51)]
+    for i, (dims, half, N, K, sigma, seed) in enumerate(cfgs):
+        np.random.seed(seed)
+        target = generateRandomGMM(np.full(dims, -half), np.full(dims, half), 3,
+                                   sigma_min=np.full(dims, 0.002), sigma_max=np.full(dims, 0.004))
+        out["tmeans%d" % i], out["tsigmas%d" % i], out["tweights%d" % i] = gmm_arrays(target)
+        np.random.seed(seed + 100)
+        s = CMixturePMC({"space_min": np.full(dims, -half), "space_max": np.full(dims, half), "dims": dims,
+                         "K": K, "N": N, "J": 1000, "sigma": sigma})
+        for it in range(2):
+            tag = "%d_%d" % (i, it)
+            out["means" + tag] = np.array([p.loc for p in s.proposals])
+            out["covs" + tag] = np.array([p.scale for p in s.proposals])
+            out["alpha" + tag] = np.array(s.wproposals)
+            out["mixw" + tag] = np.array(s.model.weights)
+            n_before = len(s.samples)
+            s.importance_sample(target, n_before + K, timeout=600)
+            out["x" + tag] = np.array(s.samples[n_before:])
+            out["w" + tag] = np.array(s.weights[n_before:])
+            out["new_means" + tag] = np.array([p.loc for p in s.proposals])
+            out["new_covs" + tag] = np.array([p.scale for p in s.proposals])
+            out["new_alpha" + tag] = np.array(s.wproposals)
+        out["sigma%d" % i] = np.array(sigma)
+    out["n"] = np.array(len(cfgs))
+    save("mpmc", **out)
+
+
+def make_lais():
+    """LAIS upper layer (sampling_methods/layered_ais.py:54-74) with the random draws captured."""
+    out = {}
+    cfgs = [(2, 4, 8, 10, 0.05, 0.5, 60), (8, 16, 16, 5, 0.05, 0.05, 61)]
+    for i, (dims, k, N, L, sigma, mh_sigma, seed) in enumerate(cfgs):
+        target = random_gmm(seed, dims, k)
+        sup = target.support()
+        np.random.seed(seed + 100)
+        s = CLayeredAIS({"space_min": sup[0], "space_max": sup[1], "dims": dims, "K": 2, "N": N, "J": 1000, "L": L,
+                         "sigma": sigma, "mh_sigma": mh_sigma})
+        before = np.array([p.loc for p in s.proposals])
+        rs = np.random.RandomState(seed + 200)
+        delta = rs.normal(size=(L, N, dims)) * np.sqrt(mh_sigma)
+        u = rs.uniform(size=(L, N))
+        # reference order: for each proposal n, L steps; each step draws delta then u (layered_ais.py:55-62)
+        d_iter = iter([delta[l, n] for n in range(N) for l in range(L)])
+        u_iter = iter([u[l, n] for n in range(N) for l in range(L)])
+        s.mhproposal.sample = lambda n_samples=1: np.array([next(d_iter)])
+        real_rand = np.random.rand
+        np.random.rand = lambda *a: next(u_iter)
+        try:
+            s.resample(target)
+        finally:
+            np.random.rand = real_rand
+        out["tmeans%d" % i], out["tsigmas%d" % i], out["tweights%d" % i] = gmm_arrays(target)
+        out["before%d" % i], out["after%d" % i] = before, np.array([p.loc for p in s.proposals])
+        out["delta%d" % i], out["u%d" % i] = delta, u
+        out["lo%d" % i], out["hi%d" % i] = sup[0], sup[1]
+        out["pi_evals%d" % i] = np.array(s.num_target_evals)
+    out["n"] = np.array(len(cfgs))
+    save("lais", **out)
+
+
+def make_uniform():
+    """CMultivariateUniform known answers (tests/distributions/test_multivariate_uniform_unittest.py:16-60) and a
+    mixture of uniforms as TP-AIS builds it (sampling_methods/tree_pyramid.py:710-736)."""
+    rs = np.random.RandomState(7)
+    out = {}
+    cases = [(np.array([0.0]), np.array([0.5])), (np.array([0.0, 0.1]), np.array([0.5, 0.2])),
+             (np.array([0.0, 0.0, 0.0]), np.array([0.5]))]
+    for i, (c, r) in enumerate(cases):
+        d = CMultivariateUniform({"center": c.copy(), "radius": r.copy()})
+        x = rs.uniform(-1, 1, size=(200, len(c)))
+        x[0] = c + np.broadcast_to(r, c.shape)   # upper edge is inside (x <= max)
+        x[1] = c - np.broadcast_to(r, c.shape)   # lower edge is outside (min < x)
+        out["c%d" % i], out["r%d" % i], out["x%d" % i] = c, r, x
+        out["logp%d" % i], out["prob%d" % i] = d.log_prob(x), d.prob(x)
+    out["n"] = np.array(len(cases))
+    k, dims = 9, 2
+    centers = rs.uniform(-1, 1, size=(k, dims))
+    radii = rs.uniform(0.1, 0.6, size=(k, 1))
+    w = rs.uniform(size=k)
+    w[3] = 0.0
+    models = [CMultivariateUniform({"center": centers[j].copy(), "radius": radii[j].copy()}) for j in range(k)]
+    mix = CMixtureModel({"models": models, "weights": w.copy(), "dims": dims, "support": [[-2, -2], [2, 2]]})
+    x = rs.uniform(-1.5, 1.5, size=(600, dims))
+    out["mix_centers"], out["mix_radii"], out["mix_w"], out["mix_x"] = centers, radii, w, x
+    out["mix_norm_w"] = np.array(mix.weights)
+    out["mix_logp"] = mix.log_prob(x)
+    save("uniform", **out)
+
+
+if __name__ == "__main__":
+    np.seterr(all="ignore")
+    make_mvn()
+    make_gmm()
+    make_mixture()
+    make_dm_weights()
+    make_kde_kld()
+    make_mpmc()
+    make_lais()
+    make_uniform()

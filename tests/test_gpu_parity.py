@@ -1,0 +1,478 @@
+"""Parity of the CUDA path (through the Python API -> C ABI -> sm_100a kernels) against the committed
+reference fixtures and the oracle. Tolerances (BASELINE.json north_star): log densities 1e-5,
+KLD and normalised weights 1e-4, both as |got - ref| / max(1, |ref|)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import ais_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOGP_TOL = 1e-5
+W_TOL = 1e-4
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from ais_benchmarks_b200 import _lib
+    _lib.load()
+
+
+def gmm(means, sigmas, weights, support=None):
+    from ais_benchmarks_b200.distributions import CGaussianMixtureModel
+    d = means.shape[1]
+    sup = support if support is not None else [np.full(d, -10.0), np.full(d, 10.0)]
+    return CGaussianMixtureModel({"means": means, "sigmas": sigmas, "weights": weights, "support": sup})
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_mvn_golden_and_shapes():
+    from ais_benchmarks_b200.distributions import CMultivariateNormal
+    g = load_golden("mvn")
+    for i in range(int(g["n"])):
+        dist = CMultivariateNormal({"mean": g["mean%d" % i].copy(), "sigma": g["cov%d" % i].copy()})
+        x = g["x%d" % i]
+        lp = dist.log_prob(x)
+        assert lp.shape == (len(x),) and lp.dtype == np.float64
+        assert rel_err(lp, g["logp%d" % i]) < LOGP_TOL
+        assert np.allclose(dist.prob(x), g["prob%d" % i], rtol=1e-4, atol=0)
+        assert np.allclose(dist.support(), g["support%d" % i])
+        # unbatched point -> (1,) result (distributions.py:137-138)
+        one = dist.log_prob(x[0])
+        assert one.shape == (1,) and abs(one[0] - g["logp%d" % i][0]) < LOGP_TOL * max(1, abs(g["logp%d" % i][0]))
+        # torch in -> torch out, stays on the device
+        lt = dist.log_prob(torch.from_numpy(x).cuda())
+        assert isinstance(lt, torch.Tensor) and lt.is_cuda
+        assert rel_err(lt.cpu().numpy(), g["logp%d" % i]) < LOGP_TOL
+    with pytest.raises(ValueError):
+        dist.log_prob(np.zeros((3, dist.dims + 1)))
+    with pytest.raises(ValueError):
+        dist.log_prob(np.zeros((2, 2, dist.dims)))
+    with pytest.raises(AssertionError):
+        CMultivariateNormal({"mean": np.zeros(2), "sigma": np.array([[1.0, 2.0], [2.0, 1.0]])})
+    with pytest.raises(AssertionError):
+        CMultivariateNormal({"sigma": np.eye(2)})
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_gmm_golden(case):
+    g = load_golden("gmm")
+    dist = gmm(g["means%d" % case], g["sigmas%d" % case], g["weights%d" % case], g["support%d" % case])
+    x = g["x%d" % case]
+    assert rel_err(dist.log_prob(x), g["logp%d" % case]) < LOGP_TOL
+    ref_p = g["prob%d" % case]
+    got_p = dist.prob(x)
+    nz = ref_p > 1e-300
+    assert np.allclose(got_p[nz], ref_p[nz], rtol=2e-4, atol=0)
+    assert np.all(got_p[~nz] < 1e-290)
+
+
+def test_gmm_from_yaml_lists():
+    """def_benchmark.yaml passes plain lists (benchmark/CBenchmark.py:129-131)."""
+    from ais_benchmarks_b200.distributions import CGaussianMixtureModel
+    g = load_golden("gmm")
+    dist = CGaussianMixtureModel({"means": [[1.5], [-4.2], [0.01], [7.5]], "sigmas": [[0.4], [0.05], [0.003], [0.003]],
+                                  "weights": [0.4, 0.4, 0.1, 0.1], "support": [[-10], [10]]})
+    assert dist.dims == 1 and dist.support().shape == (2, 1)
+    assert rel_err(dist.log_prob(g["x0"]), g["logp0"]) < LOGP_TOL
+
+
+def test_mixture_bad_weights_full_cov():
+    from ais_benchmarks_b200.distributions import CMixtureModel, CMultivariateNormal
+    g = load_golden("mixture")
+    models = [CMultivariateNormal({"mean": m.copy(), "sigma": c.copy()}) for m, c in zip(g["means"], g["covs"])]
+    mix = CMixtureModel({"models": models, "weights": g["weights"].copy(), "dims": 3, "support": [[-2] * 3, [2] * 3]})
+    assert np.allclose(mix.weights, g["norm_weights"])
+    assert rel_err(mix.log_prob(g["x"]), g["logp"]) < LOGP_TOL
+    assert np.allclose(mix.prob(g["x"]), g["prob"], rtol=2e-4)
+    assert rel_err(mix.log_prob(g["x"][0]), g["logp_single"]) < LOGP_TOL
+    # parameters changed through a component object are picked up (dm_ais.py:56 style set_moments)
+    models[0].set_moments(g["means"][0] + 0.5, g["covs"][0])
+    means2 = g["means"].copy()
+    means2[0] += 0.5
+    assert rel_err(mix.log_prob(g["x"]), O.mixture_log_prob(g["x"], means2, g["covs"], g["weights"])) < LOGP_TOL
+    # all weights zero -> -inf everywhere (logsumexp with b = 0)
+    mix.set_weights(np.zeros(6))
+    assert np.all(np.isneginf(mix.log_prob(g["x"][:5])))
+
+
+@pytest.mark.parametrize("D", [1, 2, 3, 4, 5, 8, 12, 16, 32, 40, 64])
+@pytest.mark.parametrize("kind", ["iso", "diag", "full"])
+def test_every_kernel_instantiation_vs_oracle(D, kind):
+    """One small case per (covariance kind, padded D) template instantiation, incl. non power-of-two D."""
+    from ais_benchmarks_b200 import _device, _lib
+    if kind == "full" and D > 32:
+        with pytest.raises(_lib.AisbError):
+            _device.DeviceMixture.from_params(np.zeros((1, D)), np.eye(D)[None], None, _lib.COV_FULL)
+        return
+    rs = np.random.RandomState(D * 7 + len(kind))
+    K, n = 37, 700
+    means = rs.uniform(-1, 1, size=(K, D))
+    w = rs.uniform(0.1, 1, size=K)
+    x = rs.uniform(-1.2, 1.2, size=(n, D))
+    x[:K] = means + 0.05 * rs.normal(size=(K, D))
+    if kind == "iso":
+        v = 0.07
+        mix = _device.DeviceMixture.from_params(means, np.array([v]), w, _lib.COV_ISO_SHARED)
+        ref = O.iso_mixture_log_prob(x, means, v, w)
+    elif kind == "diag":
+        var = rs.uniform(0.03, 0.3, size=(K, D))
+        mix = _device.DeviceMixture.from_params(means, var, w, _lib.COV_DIAG)
+        ref = O.gmm_log_prob(x, means, var, w)
+    else:
+        covs = np.empty((K, D, D))
+        for k in range(K):
+            a = rs.normal(size=(D, D))
+            covs[k] = 0.1 * a @ a.T / D + 0.05 * np.eye(D)
+        mix = _device.DeviceMixture.from_params(means, covs, w, _lib.COV_FULL)
+        ref = O.mixture_log_prob(x, means, covs, w)
+    got = _device.mixture_logpdf(torch.from_numpy(x).cuda().float(), mix).cpu().numpy()
+    assert rel_err(got, ref) < LOGP_TOL
+
+
+@pytest.mark.parametrize("n,K,D", [(300, 5000, 8), (1, 4100, 2), (2049, 3000, 3), (513, 2048, 32)])
+def test_split_component_path_vs_oracle(n, K, D):
+    """Few points x many centres takes the split-K + merge kernels (workspace path)."""
+    from ais_benchmarks_b200 import _device
+    rs = np.random.RandomState(n + K)
+    centres = rs.normal(size=(K, D)) * 0.4
+    x = rs.normal(size=(n, D)) * 0.5
+    bw = 0.02
+    mix = _device.DeviceMixture.kde(torch.from_numpy(centres).cuda().float(), None, K, bw)
+    got = _device.mixture_logpdf(torch.from_numpy(x).cuda().float(), mix).cpu().numpy()
+    ref = O.iso_mixture_log_prob(x.astype(np.float32).astype(np.float64), centres.astype(np.float32).astype(np.float64), bw)
+    assert rel_err(got, ref) < LOGP_TOL
+
+
+def test_special_values():
+    from ais_benchmarks_b200 import _device
+    g = load_golden("gmm")
+    dist = gmm(g["means3"], g["sigmas3"], g["weights3"])
+    x = g["x3"][:8].copy()
+    x[1, 2] = np.nan
+    x[2, 0] = np.inf
+    x[3, :] = 1e30
+    lp = dist.log_prob(x)
+    assert np.isnan(lp[1]) and np.isneginf(lp[2]) and np.isneginf(lp[3])
+    assert rel_err(lp[[0, 4, 5, 6, 7]], g["logp3"][[0, 4, 5, 6, 7]]) < LOGP_TOL
+    assert dist.log_prob(np.zeros((0, 8))).shape == (0,)
+    assert _device.mixture_logpdf(torch.zeros((0, 8), device="cuda"), dist.device_mixture()).shape == (0,)
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", range(3))
+def test_dm_weights_golden(case):
+    """Reference's own samples -> fused weight kernel; normalised weights and NESS vs the per-sample loop."""
+    from ais_benchmarks_b200.sampling_methods import CDeterministicMixtureAIS
+    g = load_golden("dm_weights")
+    x, pm, sigma = g["x%d" % case], g["pmeans%d" % case], float(g["sigma%d" % case])
+    target = gmm(g["tmeans%d" % case], g["tsigmas%d" % case], g["tweights%d" % case])
+    D = x.shape[1]
+    s = CDeterministicMixtureAIS({"space_min": np.full(D, -1.0), "space_max": np.full(D, 1.0), "dims": D,
+                                  "K": 1, "N": len(pm), "J": 1, "sigma": sigma})
+    s._set_means_host(pm)
+    xd = torch.from_numpy(x).cuda().float()
+    logw, partials = s.weigh(xd, target)
+    ref_w = g["w%d" % case]
+    fin = np.isfinite(ref_w) & (ref_w > 0)
+    assert rel_err(logw.cpu().numpy()[fin], np.log(ref_w[fin])) < 5e-5  # difference of two 1e-5 log densities
+    s._append(xd, logw)
+    from ais_benchmarks_b200 import _device
+    nw = _device.normalize_weights(logw, s._weight_partials()).cpu().numpy()
+    ref_nw = g["norm_w%d" % case]
+    big = ref_nw > 1e-12
+    assert np.max(np.abs(nw[big] - ref_nw[big]) / ref_nw[big]) < W_TOL
+    assert abs(nw.sum() - 1.0) < 1e-5
+    assert s.get_NESS() == pytest.approx(float(g["ness%d" % case]), rel=W_TOL)
+    # the sampler's own log_prob is the pre-adaptation proposal mixture
+    assert rel_err(s.log_prob(x), g["logq%d" % case]) < LOGP_TOL
+    # target given only as a foreign object with prob/log_prob (numpy on the host) takes the logp_in path
+    class Foreign:
+        def log_prob(self, v):
+            return O.gmm_log_prob(v, g["tmeans%d" % case], g["tsigmas%d" % case], g["tweights%d" % case])
+    logw2, _ = s.weigh(xd, Foreign())
+    assert rel_err(logw2.cpu().numpy()[fin], np.log(ref_w[fin])) < 5e-5
+
+
+def test_dm_weights_unfused_paths():
+    """Full-covariance target and split-K proposals go through the unfused branch of aisb_dm_weights_f32."""
+    from ais_benchmarks_b200 import _device, _lib
+    from ais_benchmarks_b200.distributions import CMultivariateNormal
+    rs = np.random.RandomState(5)
+    D = 4
+    a = rs.normal(size=(D, D))
+    cov = a @ a.T / D + 0.2 * np.eye(D)
+    tgt = CMultivariateNormal({"mean": np.zeros(D), "sigma": cov})
+    for N, n in [(16, 1000), (4096, 600)]:
+        pm = rs.normal(size=(N, D))
+        x = rs.normal(size=(n, D))
+        q = _device.DeviceMixture.from_params(pm, np.array([0.3]), None, _lib.COV_ISO_SHARED)
+        logw, logp, logq, part = _device.dm_weights(torch.from_numpy(x).cuda().float(), tgt._device_mixture(), None, q,
+                                                    want_logp=True, want_logq=True)
+        ref_p = O.mvn_log_prob(x, np.zeros(D), cov)
+        ref_q = O.iso_mixture_log_prob(x, pm, 0.3)
+        assert rel_err(logp.cpu().numpy(), ref_p) < LOGP_TOL
+        assert rel_err(logq.cpu().numpy(), ref_q) < LOGP_TOL
+        p = part.cpu().numpy()
+        ref_lw = ref_p - ref_q
+        assert p[3] == n
+        assert p[0] + np.log(p[1]) == pytest.approx(np.log(np.exp(ref_lw - ref_lw.max()).sum()) + ref_lw.max(), abs=1e-4)
+
+
+@pytest.mark.parametrize("case", range(3))
+def test_kde_kld_golden(case):
+    from ais_benchmarks_b200 import _device
+    from ais_benchmarks_b200.metrics import CKLDivergence
+    from ais_benchmarks_b200.sampling_methods.base import CDeviceKDE
+    g = load_golden("kde_kld")
+    target = gmm(g["tmeans%d" % case], g["tsigmas%d" % case], g["tweights%d" % case])
+    centres, bw, x = g["centres%d" % case], float(g["bw%d" % case]), g["x%d" % case]
+    D = x.shape[1]
+    kde = CDeviceKDE(torch.from_numpy(centres).cuda().float(), None, len(centres), bw, D, [x.min(0), x.max(0)])
+    assert rel_err(kde.log_prob(x), g["lq%d" % case]) < LOGP_TOL
+    assert rel_err(target.log_prob(x), g["lp%d" % case]) < LOGP_TOL
+    metric = CKLDivergence()
+    val = metric.compute_from_samples(target, kde, x)
+    ref = float(g["kld%d" % case])
+    assert abs(val - ref) <= W_TOL * max(1.0, abs(ref))
+    assert metric.value == val
+    # per-inlier terms + in-place normalisation of the inputs (quirk Q7)
+    lp, lq = g["lp%d" % case].copy(), g["lq%d" % case].copy()
+    terms = CKLDivergence.compute_from_log_probs(lp, lq)
+    assert abs(terms.sum() - ref) <= W_TOL * max(1.0, abs(ref))
+    inl = np.isfinite(g["lp%d" % case]) & np.isfinite(g["lq%d" % case])
+    assert abs(np.logaddexp.reduce(lp[inl])) < 1e-4
+    # foreign q (numpy-only object) still works
+    class ForeignQ:
+        def log_prob(self, v):
+            return O.iso_mixture_log_prob(v, centres, bw)
+    val2 = CKLDivergence().compute_from_samples(target, ForeignQ(), x)
+    assert abs(val2 - ref) <= W_TOL * max(1.0, abs(ref))
+
+
+def test_kld_edge_cases_and_known_answers():
+    from ais_benchmarks_b200.distributions import CMultivariateNormal, CMultivariateUniform
+    from ais_benchmarks_b200.metrics import CKLDivergence
+    g = load_golden("kde_kld")
+    terms = CKLDivergence.compute_from_log_probs(g["edge_lp"].copy(), g["edge_lq"].copy())
+    assert terms.sum() == pytest.approx(float(g["edge_kld"]), rel=1e-5)
+    assert np.sum(CKLDivergence.compute_from_log_probs(np.full(4, -np.inf), np.zeros(4))) == 0.0
+    # reference tests/metrics/test_metric_kldivergence.py:77-135 (closed-form Gaussian KL within 1 %)
+    for j in range(int(g["n_kat"])):
+        m0, m1, s0, s1 = g["kat_m0_%d" % j], g["kat_m1_%d" % j], g["kat_s0_%d" % j], g["kat_s1_%d" % j]
+        p = CMultivariateNormal({"mean": m0, "sigma": s0})
+        q = CMultivariateNormal({"mean": m1, "sigma": s1})
+        np.random.seed(int(g["kat_seed_%d" % j]))
+        val = CKLDivergence().compute(p=p, q=q, nsamples=100000)
+        ref = float(g["kat_kld_%d" % j])
+        assert abs(val - ref) <= W_TOL * max(1.0, abs(ref))
+        assert abs(val - O.mvn_kld_closed_form(m0, s0, m1, s1)) <= 0.01 * O.mvn_kld_closed_form(m0, s0, m1, s1)
+    # test_equal: identical distributions -> 0; test_disjoint: disjoint uniforms -> empty inlier set -> 0.0
+    p = CMultivariateNormal({"mean": np.array([0.0]), "sigma": np.diag([1.0])})
+    assert abs(CKLDivergence().compute(p=p, q=p, nsamples=10000)) < 1e-6
+    pu = CMultivariateUniform({"center": np.array([0.0]), "radius": np.array([.1])})
+    qu = CMultivariateUniform({"center": np.array([1.0]), "radius": np.diag([.1])})
+    assert CKLDivergence().compute(p=pu, q=qu, nsamples=1000) == 0.0
+    # device-generated evaluation points: same statistic within Monte-Carlo noise
+    m = CKLDivergence()
+    m.device_points = True
+    q2 = CMultivariateNormal({"mean": np.array([2.0]), "sigma": np.diag([1.0])})
+    assert m.compute(p=p, q=q2, nsamples=200000) == pytest.approx(2.0, rel=0.02)
+
+
+def test_mpmc_iteration_golden():
+    from ais_benchmarks_b200.sampling_methods import CMixturePMC
+    g = load_golden("mpmc")
+    for i in range(int(g["n"])):
+        target = gmm(g["tmeans%d" % i], g["tsigmas%d" % i], g["tweights%d" % i])
+        for it in range(2):
+            t = "%d_%d" % (i, it)
+            x = g["x" + t]
+            K, D = x.shape
+            N = len(g["means" + t])
+            np.random.seed(0)
+            s = CMixturePMC({"space_min": np.full(D, -1.0), "space_max": np.full(D, 1.0), "dims": D, "K": K, "N": N,
+                             "J": 1000, "sigma": float(g["sigma%d" % i])})
+            s._means, s._covs = g["means" + t].copy(), g["covs" + t].copy()
+            s.wproposals = g["alpha" + t].copy()
+            s._mix_weights = g["mixw" + t].copy()
+            s._mixture = None
+            xd = torch.from_numpy(x).cuda().float()
+            logw, logq, part = s.weigh(xd, target)
+            ph = part.cpu().numpy()
+            from ais_benchmarks_b200 import _device
+            w = torch.exp(logw.double() - _device.weight_logsum(ph)).cpu().numpy()
+            ref_w = g["w" + t]
+            big = ref_w > 1e-9
+            assert np.max(np.abs(w[big] - ref_w[big]) / ref_w[big]) < W_TOL
+            s.adapt(xd, logw, logq, ph)
+            assert np.allclose(s.wproposals, g["new_alpha" + t], rtol=W_TOL, atol=1e-9)
+            live = g["new_alpha" + t] > 1e-9
+            assert np.allclose(s._means[live], g["new_means" + t][live], rtol=W_TOL, atol=1e-5)
+            assert np.allclose(s._covs[live], g["new_covs" + t][live], rtol=1e-3, atol=1e-5)
+
+
+def test_lais_chains_golden():
+    from ais_benchmarks_b200.sampling_methods import CLayeredAIS
+    g = load_golden("lais")
+    for i in range(int(g["n"])):
+        target = gmm(g["tmeans%d" % i], g["tsigmas%d" % i], g["tweights%d" % i])
+        before, delta, u = g["before%d" % i], g["delta%d" % i], g["u%d" % i]
+        N, D = before.shape
+        np.random.seed(1)
+        s = CLayeredAIS({"space_min": g["lo%d" % i], "space_max": g["hi%d" % i], "dims": D, "K": 2, "N": N, "J": 1,
+                         "L": delta.shape[0], "sigma": 0.05, "mh_sigma": 0.5})
+        s._set_means_host(before)
+        s.mcmc_step(target, torch.from_numpy(delta).cuda().float(), torch.from_numpy(u).cuda().float())
+        after = s.proposal_means().cpu().numpy()
+        assert np.allclose(after, g["after%d" % i], rtol=0, atol=2e-6)
+        assert s.num_target_evals == int(g["pi_evals%d" % i])
+
+
+def test_uniform_and_box_mixture_golden():
+    from ais_benchmarks_b200.distributions import CMixtureModel, CMultivariateUniform
+    g = load_golden("uniform")
+    for i in range(int(g["n"])):
+        d = CMultivariateUniform({"center": g["c%d" % i].copy(), "radius": g["r%d" % i].copy()})
+        x = g["x%d" % i]
+        assert rel_err(d.log_prob(x), g["logp%d" % i]) < LOGP_TOL
+        assert np.allclose(d.prob(x), g["prob%d" % i], rtol=1e-5)
+    c, r = g["mix_centers"], g["mix_radii"]
+    models = [CMultivariateUniform({"center": c[j].copy(), "radius": r[j].copy()}) for j in range(len(c))]
+    mix = CMixtureModel({"models": models, "weights": g["mix_w"].copy(), "dims": 2, "support": [[-2, -2], [2, 2]]})
+    assert rel_err(mix.log_prob(g["mix_x"]), g["mix_logp"]) < LOGP_TOL
+    s = mix.sample(500)
+    assert s.shape == (500, 2) and np.isfinite(mix.log_prob(s)).all()
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_samplers_end_to_end():
+    """importance_sample / adapt loops of DM-AIS, LAIS and M-PMC on the default 2-D GMM target
+    (benchmark/def_benchmark.yaml:15-20): interface, counters and weight normalisation contracts."""
+    from ais_benchmarks_b200 import _device
+    from ais_benchmarks_b200.metrics import CKLDivergence
+    from ais_benchmarks_b200.sampling_methods import CDeterministicMixtureAIS, CLayeredAIS, CMixturePMC
+    np.random.seed(0)
+    _device.seed(0)
+    target = gmm(np.array([[0.0, 0.0], [-0.3, 0.5]]), np.array([[0.01, 0.1], [0.01, 0.03]]), np.array([0.5, 0.5]),
+                 [[-1, -1], [1, 1]])
+    base = {"space_min": target.support()[0], "space_max": target.support()[1], "dims": 2}
+    dm = CDeterministicMixtureAIS(dict(base, K=10, N=5, J=1000, sigma=0.5))
+    x, w = dm.importance_sample(target, 120, timeout=60)
+    assert x.shape == (150, 2) and w.shape == (150,) and abs(w.sum() - 1) < 1e-5
+    assert dm.num_proposal_samples == 150 and dm.num_target_evals == 150
+    assert 0 < dm.get_NESS() <= 1 and dm.get_acceptance_rate() == 1.0
+    x2, w2 = dm.importance_sample(target, 160, timeout=60)  # cumulative, like CBenchmark.py:489-493
+    assert len(x2) == 200 and np.array_equal(x2[:150], x)
+    assert len(dm.proposals) == 5 and dm.model.log_prob(x2[:3]).shape == (3,)
+    assert rel_err(dm.log_prob(x2[:50]), dm.model.log_prob(x2[:50])) < LOGP_TOL
+    kld = CKLDivergence().compute(p=target, q=dm, nsamples=2000)
+    assert np.isfinite(kld) and kld > 0
+    dm.reset()
+    assert dm.num_proposal_samples == 0 and len(dm.samples) == 0
+
+    lais = CLayeredAIS(dict(base, K=3, N=5, J=1000, L=10, sigma=0.5, mh_sigma=0.5))
+    x, w = lais.importance_sample(target, 40, timeout=60)
+    assert x.shape == (45, 2) and abs(w.sum() - 1) < 1e-5
+    assert lais.num_target_evals == 45 + 3 * 2 * 10 * 5 and lais.num_proposal_samples == 45 + 3 * 10 * 5
+    m = lais.proposal_means().cpu().numpy()
+    assert np.all(m >= -1) and np.all(m <= 1)
+
+    pmc = CMixturePMC(dict(base, K=50, N=10, J=1000, sigma=0.01))
+    x, w = pmc.importance_sample(target, 200, timeout=60)
+    assert x.shape == (200, 2) and w.sum() == pytest.approx(4.0, rel=1e-4)  # quirk Q4: one unit of weight per batch
+    assert pmc.num_target_evals == 200 and pmc.num_proposal_evals == 200 * 11
+    assert len(pmc.proposals) == 10 and abs(pmc.wproposals.sum() - 1) < 1e-9
+    assert np.isfinite(CKLDivergence().compute(p=target, q=pmc, nsamples=2000))
+    # tensors out on request
+    dmt = CDeterministicMixtureAIS(dict(base, K=10, N=5, J=1000, sigma=0.5, device_outputs=True))
+    xt, wt = dmt.importance_sample(target, 50)
+    assert xt.is_cuda and wt.is_cuda and abs(float(wt.sum()) - 1) < 1e-5
+
+
+def test_kde_base_class_builder():
+    """CMixtureSamplingMethod._update_model (sampling_methods/base.py:162-179) for any sampler that accumulates samples."""
+    from ais_benchmarks_b200.sampling_methods import CMixtureSamplingMethod
+
+    class Holder(CMixtureSamplingMethod):
+        def __init__(self, params):
+            super().__init__(params)
+            self.bw = params["kde_bw"]
+
+        def importance_sample(self, target_d, n_samples, timeout):
+            raise NotImplementedError
+
+    rs = np.random.RandomState(3)
+    pts = rs.normal(size=(50, 2)) * 0.3
+    h = Holder({"space_min": np.array([-1.0, -1]), "space_max": np.array([1.0, 1]), "dims": 2, "n_samples_kde": 50,
+                "kde_bw": 0.02})
+    h.samples = pts
+    np.random.seed(0)
+    x = rs.uniform(-1, 1, size=(300, 2))
+    lq = h.log_prob(x)
+    idx = h.model._idx.cpu().numpy()
+    assert idx.shape == (50,) and idx.min() >= 0 and idx.max() < 50
+    ref = O.iso_mixture_log_prob(x, pts[idx].astype(np.float32).astype(np.float64), 0.02)
+    assert rel_err(lq, ref) < LOGP_TOL
+    assert h.sample(7).shape == (7, 2) and h.num_proposal_samples == 7
+
+
+def test_device_sampling_statistics():
+    from ais_benchmarks_b200 import _device
+    _device.seed(123)
+    means = torch.tensor([[0.0, 10.0, -5.0], [1.0, 2.0, 3.0]], device="cuda")
+    x = _device.sample_iso(means, 200000, 0.25)
+    assert x.shape == (400000, 3)
+    a, b = x[:200000], x[200000:]
+    assert torch.allclose(a.mean(0), means[0], atol=0.01) and torch.allclose(b.mean(0), means[1], atol=0.01)
+    assert torch.allclose(a.var(0), torch.full((3,), 0.25, device="cuda"), rtol=0.02)
+    z = (a - means[0]) / 0.5
+    assert abs(float((z ** 4).mean()) - 3.0) < 0.06 and abs(float((z[:, 0] * z[:, 1]).mean())) < 0.01
+    u = _device.uniform_box(torch.tensor([-1.0, 2.0], device="cuda"), torch.tensor([1.0, 6.0], device="cuda"), 100000)
+    assert float(u[:, 0].min()) > -1 and float(u[:, 0].max()) < 1 and float(u[:, 1].min()) > 2 and float(u[:, 1].max()) < 6
+    assert abs(float(u[:, 1].mean()) - 4.0) < 0.02 and abs(float(u[:, 0].var()) - 4.0 / 12) < 0.01
+    y = _device.sample_iso(means, 10, 0.25)
+    assert not torch.equal(y, x[:20].reshape(-1, 3)[:20])  # the stream advances between calls
+
+
+def test_raw_moments():
+    from ais_benchmarks_b200 import _device
+    rs = np.random.RandomState(9)
+    for n, D in [(1000, 3), (777, 8), (130, 32)]:
+        x = rs.normal(size=(n, D)).astype(np.float32)
+        s1, s2 = _device.raw_moments(torch.from_numpy(x).cuda())
+        xd = x.astype(np.float64)
+        assert np.allclose(s1.cpu().numpy(), xd.sum(0), rtol=1e-12, atol=1e-9)
+        assert np.allclose(s2.cpu().numpy(), xd.T @ xd, rtol=1e-12, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_large_kde_properties_and_row_subset():
+    """BASELINE config-4-shaped run at a size the GPU finishes in well under a second: 2e5 eval points x 2e5 centres,
+    D = 8. Checked through (i) an oracle evaluation of a random row subset, (ii) the split/merge identity
+    LSE(all centres) = logaddexp(LSE(first half), LSE(second half)) and (iii) invariance to centre permutation."""
+    from ais_benchmarks_b200 import _device
+    rs = np.random.RandomState(4)
+    n, D = 200000, 8
+    g = load_golden("gmm")
+    means, sig, w = g["means3"], g["sigmas3"], g["weights3"]
+    comp = rs.choice(len(w), size=n, p=w / w.sum())
+    centres = (means[comp] + rs.normal(size=(n, D)) * np.sqrt(sig[comp])).astype(np.float32)
+    x = rs.uniform(-1, 1, size=(n, D)).astype(np.float32)
+    cd, xd = torch.from_numpy(centres).cuda(), torch.from_numpy(x).cuda()
+    bw = 0.02
+    full = _device.mixture_logpdf(xd, _device.DeviceMixture.kde(cd, None, n, bw))
+    rows = rs.choice(n, size=48, replace=False)
+    ref = O.iso_mixture_log_prob(x[rows].astype(np.float64), centres.astype(np.float64), bw, chunk=8)
+    assert rel_err(full.cpu().numpy()[rows], ref) < LOGP_TOL
+    h = n // 2
+    a = _device.mixture_logpdf(xd, _device.DeviceMixture.kde(cd[:h].contiguous(), None, h, bw))
+    b = _device.mixture_logpdf(xd, _device.DeviceMixture.kde(cd[h:].contiguous(), None, n - h, bw))
+    merged = torch.logaddexp(a.double(), b.double()) + np.log(0.5)
+    assert rel_err(full.cpu().numpy(), merged.cpu().numpy()) < 2e-6
+    perm = torch.randperm(n, device="cuda")
+    p = _device.mixture_logpdf(xd, _device.DeviceMixture.kde(cd, perm, n, bw))
+    assert rel_err(p.cpu().numpy(), full.cpu().numpy()) < 2e-6
