@@ -11,10 +11,17 @@
 //     their own points; JJ components are evaluated per online-LSE step so that the running
 //     max / rescale costs one extra MUFU per JJ pairs,
 //   * everything is carried in the log2 domain: t = c_k - ||A_k x + b_k||^2, accumulated as an
-//     FFMA chain seeded with c_k, then S += ex2(t - m).
+//     FFMA chain seeded with c_k, then S += ex2(t - m),
+//   * ISO/DIAG kinds use the sm_100 packed FP32 instructions (FFMA2): two POINTS share one 64-bit
+//     register pair per dimension and the component parameters are stored duplicated ((b,b) pairs),
+//     so one FFMA2 advances two (point, component) pairs: half the issue slots for the same FMA-pipe
+//     work, which leaves issue bandwidth for the MUFU / FMNMX / LDS instructions,
+//   * the online-LSE update of group g runs while group g+1 is being evaluated (software pipeline:
+//     the pending group's t values stay in registers), so MUFU.EX2 work interleaves with FFMA2 work
+//     instead of arriving in bursts.
 //
-// Instruction budget per (point, component) pair, ISO/DIAG kinds: 2*DP FFMA + (1 FMNMX + 1 FADD
-// + 1 MUFU.EX2 + 1 FADD) + (2 MUFU-related)/JJ.
+// Per (point, component) pair, ISO/DIAG kinds: DP FFMA2 issue slots (2*DP FMA-pipe lane-cycles)
+// + 1 FMNMX(3) + 1 FADD + 1 MUFU.EX2 + 1 FADD + (2 MUFU-related)/JJ.
 #pragma once
 #include "common.cuh"
 
@@ -23,10 +30,14 @@ namespace aisb {
 // ---------------------------------------------------------------------------------------------
 // Compile-time tiling traits
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int points_per_thread(int DP) { return DP <= 16 ? 4 : (DP == 32 ? 2 : 1); }
+__host__ __device__ constexpr int points_per_thread(int DP) { return DP <= 16 ? 4 : 2; }
+
+#ifndef AISB_JJ_SMALL
+#define AISB_JJ_SMALL 4  // components per online-LSE step for DP <= 8 (ISO/DIAG)
+#endif
 
 __host__ __device__ constexpr int comps_per_step(int kind, int DP) {
-  return kind == AISB_COV_FULL ? (DP <= 8 ? 4 : (DP == 16 ? 2 : 1)) : (DP <= 8 ? 8 : (DP <= 32 ? 4 : 8));
+  return kind == AISB_COV_FULL ? (DP <= 8 ? 4 : (DP == 16 ? 2 : 1)) : (DP <= 8 ? AISB_JJ_SMALL : (DP <= 32 ? 4 : 2));
 }
 
 __host__ __device__ constexpr int pow2_floor(int v) {
@@ -84,9 +95,11 @@ __device__ __forceinline__ void lds_vec(const float* __restrict__ p, float (&v)[
 template <int KIND, int DP, int E>
 __device__ __forceinline__ void comp_eval(const float* __restrict__ row, float c, float a_iso,
                                           const float (&x)[E][DP], float (&t)[E]) {
+  // scalar evaluation (used by the moment kernel); ISO/DIAG rows hold every parameter twice (FFMA2 layout)
   if constexpr (KIND == AISB_COV_ISO_SHARED) {
     float b[DP];
-    lds_vec<DP>(row, b);
+#pragma unroll
+    for (int d = 0; d < DP; ++d) b[d] = row[2 * d];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       float acc = c;
@@ -99,8 +112,11 @@ __device__ __forceinline__ void comp_eval(const float* __restrict__ row, float c
     }
   } else if constexpr (KIND == AISB_COV_DIAG) {
     float a[DP], b[DP];
-    lds_vec<DP>(row, a);
-    lds_vec<DP>(row + DP, b);
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      a[d] = row[2 * d];
+      b[d] = row[2 * DP + 2 * d];
+    }
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       float acc = c;
@@ -173,6 +189,118 @@ __device__ __forceinline__ void accumulate_chunk(const float* __restrict__ srows
 }
 
 // ---------------------------------------------------------------------------------------------
+// Packed (FFMA2) path for ISO / DIAG kinds. Points are held as pairs: x2[pp][d] = (x[2pp][d], x[2pp+1][d]).
+// Row layout (include/ais_b200.h): ISO  (b0,b0,b1,b1,...)            2*DP floats
+//                                  DIAG (a0,a0,a1,a1,...,b0,b0,...)  4*DP floats
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void lds_vec2(const float* __restrict__ p, float2 (&v)[N]) {
+  if constexpr (N % 2 == 0) {
+#pragma unroll
+    for (int q = 0; q < N / 2; ++q) {
+      const float4 f = reinterpret_cast<const float4*>(p)[q];
+      v[2 * q + 0] = make_float2(f.x, f.y);
+      v[2 * q + 1] = make_float2(f.z, f.w);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < N; ++q) v[q] = reinterpret_cast<const float2*>(p)[q];
+  }
+}
+
+__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+
+template <int KIND, int DP, int EP>
+__device__ __forceinline__ void comp_eval2(const float* __restrict__ row, float c, float a_iso,
+                                           const float2 (&x2)[EP][DP], float2 (&t2)[EP]) {
+  float2 b2[DP];
+  if constexpr (KIND == AISB_COV_ISO_SHARED) {
+    lds_vec2<DP>(row, b2);
+    const float2 a2 = make_float2(a_iso, a_iso);
+#pragma unroll
+    for (int pp = 0; pp < EP; ++pp) {
+      float2 acc = make_float2(c, c);
+#pragma unroll
+      for (int d = 0; d < DP; ++d) {
+        const float2 dl = __ffma2_rn(x2[pp][d], a2, b2[d]);
+        acc = __ffma2_rn(neg2(dl), dl, acc);
+      }
+      t2[pp] = acc;
+    }
+  } else {
+    float2 a2[DP];
+    lds_vec2<DP>(row, a2);
+    lds_vec2<DP>(row + 2 * DP, b2);
+#pragma unroll
+    for (int pp = 0; pp < EP; ++pp) {
+      float2 acc = make_float2(c, c);
+#pragma unroll
+      for (int d = 0; d < DP; ++d) {
+        const float2 dl = __ffma2_rn(x2[pp][d], a2[d], b2[d]);
+        acc = __ffma2_rn(neg2(dl), dl, acc);
+      }
+      t2[pp] = acc;
+    }
+  }
+}
+
+template <int KIND, int DP, int EP, int JJ, bool HAS_C>
+__device__ __forceinline__ void eval_group2(const float* __restrict__ srows, const float* __restrict__ soffs, int j0,
+                                            float a_iso, const float2 (&x2)[EP][DP], float2 (&t)[JJ][EP]) {
+  constexpr int ROW = row_floats(KIND, DP);
+  float c[JJ];
+  if constexpr (HAS_C) {
+    lds_vec<JJ>(soffs + j0, c);
+  } else {
+#pragma unroll
+    for (int jj = 0; jj < JJ; ++jj) c[jj] = 0.f;
+  }
+#pragma unroll
+  for (int jj = 0; jj < JJ; ++jj) comp_eval2<KIND, DP, EP>(srows + (j0 + jj) * ROW, c[jj], a_iso, x2, t[jj]);
+}
+
+// fold one evaluated group into the running (m, S) of each point
+template <int EP, int JJ>
+__device__ __forceinline__ void lse_update2(const float2 (&t)[JJ][EP], float (&m)[2 * EP], float (&S)[2 * EP]) {
+#pragma unroll
+  for (int pp = 0; pp < EP; ++pp) {
+    float g0 = t[0][pp].x, g1 = t[0][pp].y;
+#pragma unroll
+    for (int jj = 1; jj < JJ; ++jj) {
+      g0 = fmaxf(g0, t[jj][pp].x);
+      g1 = fmaxf(g1, t[jj][pp].y);
+    }
+    const float m0 = fmaxf(m[2 * pp], g0), m1 = fmaxf(m[2 * pp + 1], g1);
+    float s0 = S[2 * pp] * ex2(m[2 * pp] - m0), s1 = S[2 * pp + 1] * ex2(m[2 * pp + 1] - m1);
+#pragma unroll
+    for (int jj = 0; jj < JJ; ++jj) {
+      s0 += ex2(t[jj][pp].x - m0);
+      s1 += ex2(t[jj][pp].y - m1);
+    }
+    S[2 * pp] = s0;
+    S[2 * pp + 1] = s1;
+    m[2 * pp] = m0;
+    m[2 * pp + 1] = m1;
+  }
+}
+
+// Software-pipelined chunk: on entry tP holds the previously evaluated, not yet folded group (all -inf at the very
+// start: folding it is a no-op); on exit it holds this chunk's last group. cnt / JJ is even (cnt is a multiple of 32).
+template <int KIND, int DP, int EP, int JJ, bool HAS_C>
+__device__ __forceinline__ void accumulate_chunk2(const float* __restrict__ srows, const float* __restrict__ soffs,
+                                                  int cnt, float a_iso, const float2 (&x2)[EP][DP],
+                                                  float2 (&tP)[JJ][EP], float (&m)[2 * EP], float (&S)[2 * EP]) {
+#pragma unroll 1
+  for (int j0 = 0; j0 < cnt; j0 += 2 * JJ) {
+    float2 tQ[JJ][EP];
+    eval_group2<KIND, DP, EP, JJ, HAS_C>(srows, soffs, j0, a_iso, x2, tQ);
+    lse_update2<EP, JJ>(tP, m, S);
+    eval_group2<KIND, DP, EP, JJ, HAS_C>(srows, soffs, j0 + JJ, a_iso, x2, tP);
+    lse_update2<EP, JJ>(tQ, m, S);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stream components [k_begin, k_end) of a packed mixture through the smem ring, calling
 // fn(srows, soffs, cnt, k0) on every staged chunk (cnt components starting at global index k0).
 // `it` counts chunks consumed so far by this CTA (carries the mbarrier phase across passes).
@@ -228,10 +356,30 @@ __device__ __forceinline__ void mixture_pass(const float* __restrict__ g_rows, c
                                              int64_t k_begin, int64_t k_end, float a_iso, float* smem, uint64_t* bars,
                                              uint32_t& it, const float (&x)[E][DP], float (&m)[E], float (&S)[E]) {
   constexpr int JJ = comps_per_step(KIND, DP);
-  stream_components<KIND, DP, HAS_C>(g_rows, g_offs, k_begin, k_end, smem, bars, it,
-                                     [&](const float* srows, const float* soffs, int cnt, int64_t) {
-                                       accumulate_chunk<KIND, DP, E, JJ, HAS_C>(srows, soffs, cnt, a_iso, x, m, S);
-                                     });
+  if constexpr (KIND == AISB_COV_FULL) {
+    stream_components<KIND, DP, HAS_C>(g_rows, g_offs, k_begin, k_end, smem, bars, it,
+                                       [&](const float* srows, const float* soffs, int cnt, int64_t) {
+                                         accumulate_chunk<KIND, DP, E, JJ, HAS_C>(srows, soffs, cnt, a_iso, x, m, S);
+                                       });
+  } else {
+    static_assert(E % 2 == 0, "packed path needs an even number of points per thread");
+    constexpr int EP = E / 2;
+    float2 x2[EP][DP];
+#pragma unroll
+    for (int pp = 0; pp < EP; ++pp)
+#pragma unroll
+      for (int d = 0; d < DP; ++d) x2[pp][d] = make_float2(x[2 * pp][d], x[2 * pp + 1][d]);
+    float2 tP[JJ][EP];
+#pragma unroll
+    for (int jj = 0; jj < JJ; ++jj)
+#pragma unroll
+      for (int pp = 0; pp < EP; ++pp) tP[jj][pp] = make_float2(-INFINITY, -INFINITY);
+    stream_components<KIND, DP, HAS_C>(
+        g_rows, g_offs, k_begin, k_end, smem, bars, it, [&](const float* srows, const float* soffs, int cnt, int64_t) {
+          accumulate_chunk2<KIND, DP, EP, JJ, HAS_C>(srows, soffs, cnt, a_iso, x2, tP, m, S);
+        });
+    lse_update2<EP, JJ>(tP, m, S);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -74,7 +74,8 @@ def dm_workload(seed=10, scale=1.0):
 
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 500 ms during the timed region (polling faster than
+    that measurably delays kernel launches on the sampled GPU)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -85,7 +86,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "500"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -98,7 +99,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.55)
         self.proc.terminate()
         sm, smax, reasons = [], [], set()
         for ln in self.lines:
@@ -301,9 +302,9 @@ def run_cuda(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[3]: KDE-KLD, D=8, %d KDE centres x %d eval points, 16-mode GMM "
                                    "target, bw=0.02; eval points sharded over %d GPU(s)" % (n_c, n_e, world),
-                       "l2": "inputs (%.0f MB centres + %.0f MB points) exceed nothing; the pairwise kernel is "
-                             "compute-bound and re-reads the centres from L2 by design; no flush" %
-                             (n_c * D * 4 / 1e6, n_e * D * 4 / 1e6),
+                       "l2": "no flush between steps: the pairwise kernel is compute-bound (%.0f flop per byte of "
+                             "input); its %.0f MB of packed centres are re-read from L2 by every CTA by design and the "
+                             "%.0f MB of points are read once" % (n_c * 30.0 / 8 / 4, n_c * D * 8 / 1e6, n_e * D * 4 / 1e6),
                        "kld": kld_val, "scale": scale},
             "e2e": {"value": total_pairs / (kde_e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(centres_pin.numel() * 4 + x_pin.numel() * 4), "d2h_bytes_per_step": 64,
