@@ -45,10 +45,10 @@ def all_gather_records(record):
     rec = record if _device.is_tensor(record) else torch.as_tensor(np.asarray(record, dtype=np.float64))
     if ws == 1:
         return rec.detach().cpu().numpy().reshape(1, -1)
-    rec = rec.to(_comm_device(), torch.float64).contiguous()
-    out = torch.empty((ws, rec.numel()), dtype=torch.float64, device=rec.device)
+    rec = rec.to(_comm_device(), torch.float64).contiguous().reshape(-1)
+    out = torch.empty(ws * rec.numel(), dtype=torch.float64, device=rec.device)
     dist.all_gather_into_tensor(out, rec)
-    return out.cpu().numpy()
+    return out.cpu().numpy().reshape(ws, -1)
 
 
 def merge_weight_partials(records):

@@ -1,0 +1,140 @@
+"""Host-side behaviour of the reference-API classes that needs no GPU: constructor contracts, parameter
+sanitising, shape checks, counters / reset, and the loud failure when CUDA is absent."""
+import numpy as np
+import pytest
+import torch
+
+from ais_benchmarks_b200 import AisbError
+from ais_benchmarks_b200._lib import COV_DIAG, COV_FULL, COV_ISO_SHARED
+from ais_benchmarks_b200.distributions import (CGaussianMixtureModel, CMixtureModel, CMultivariateNormal,
+                                               CMultivariateUniform)
+from ais_benchmarks_b200.distributions.mixture.CMixtureModel import gaussian_pack_args, sanitize_weights
+from ais_benchmarks_b200.metrics import CKLDivergence, CMetric
+from ais_benchmarks_b200.sampling_methods import CDeterministicMixtureAIS, CLayeredAIS, CMixturePMC
+
+no_gpu = pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-CUDA failure mode")
+
+
+def test_mvn_constructor_contract():
+    d = CMultivariateNormal({"mean": np.array([0.0, 1.0]), "sigma": np.array([[2.0, 0.3], [0.3, 1.0]])})
+    assert d.dims == 2 and d.type == "normal" and d.family == "exponential"
+    assert np.allclose(d.inv_cov, np.linalg.inv(d.scale)) and d.det == pytest.approx(1.91)
+    assert d.term1 == pytest.approx(-np.log(2 * np.pi)) and d.term2 == pytest.approx(-0.5 * np.log(1.91))
+    assert np.allclose(d.support(), [[-6 * np.sqrt(2), 1 - 6], [6 * np.sqrt(2), 1 + 6]])   # CMultivariateNormal.py:37-40
+    v0 = d._version
+    d.set_moments(np.zeros(2), np.eye(2))
+    assert d._version == v0 + 1 and d.is_diagonal()
+    with pytest.raises(AssertionError):
+        d.set_moments(np.zeros(2), np.zeros((2, 2)))           # det > 0 (CMultivariateNormal.py:55-56)
+    with pytest.raises(AssertionError):
+        d.set_moments(np.zeros(2), np.eye(3))
+    with pytest.raises(AssertionError):
+        CMultivariateNormal({"mean": np.zeros(2)})             # missing "sigma"
+    with pytest.raises(NotImplementedError):
+        d.marginal(0)
+    with pytest.raises(ValueError):
+        d._check_shape(np.zeros((4, 3)))
+    assert d._check_shape(np.zeros(2)).shape == (1, 2)
+
+
+def test_weight_sanitising_matches_reference_rules(capsys):
+    w = np.array([0.3, 0.0, np.nan, 0.5, -1.0, 0.2])
+    out = sanitize_weights(w)
+    assert np.allclose(out, [0.3, 0, 0, 0.5, 0, 0.2])           # sums to 1 already
+    assert np.array_equal(w[[1, 2, 4]], [0, 0, 0])               # the caller's array is modified in place (CMixtureModel.py:33)
+    assert "3 NaN, negative or zero weights out of 6" in capsys.readouterr().err
+    z = sanitize_weights(np.zeros(3))
+    assert np.array_equal(z, np.zeros(3))
+    assert "All weights are set to zero" in capsys.readouterr().err
+    assert np.allclose(sanitize_weights(np.array([2.0, 6.0])), [0.25, 0.75])
+
+
+def test_mixture_and_gmm_constructors():
+    g = CGaussianMixtureModel({"means": [[1.5], [-4.2], [0.01], [7.5]], "sigmas": [[0.4], [0.05], [0.003], [0.003]],
+                               "weights": [0.4, 0.4, 0.1, 0.1], "support": [[-10], [10]]})
+    assert g.dims == 1 and len(g.models) == 4 and g.weights == [0.4, 0.4, 0.1, 0.1]     # raw weights are kept
+    assert np.allclose(g.gmm.weights, [0.4, 0.4, 0.1, 0.1]) and g.support().shape == (2, 1)
+    assert g.models[1].scale.shape == (1, 1) and g.models[1].scale[0, 0] == 0.05        # variances on the diagonal
+    d = g.to_dict(name="t")
+    assert d["type"] == "distributions.CGaussianMixtureModel" and d["params"]["means"][3] == [7.5]
+    g2 = CGaussianMixtureModel({"means": np.zeros((3, 2)), "sigmas": np.ones((3, 2)), "support": [[-1, -1], [1, 1]]})
+    assert np.allclose(g2.weights, 1 / 3)
+    with pytest.raises(AssertionError):
+        CMixtureModel({"models": g.models, "weights": [1.0], "dims": 1, "support": [[-1], [1]]})
+    with pytest.raises(AssertionError):
+        CMixtureModel({"models": g.models, "weights": [1, 1, 1, 1], "support": [[-1], [1]]})   # "dims" is required
+    # layout choice of the packer
+    iso = [CMultivariateNormal({"mean": np.zeros(3) + i, "sigma": np.eye(3) * 0.2}) for i in range(4)]
+    assert gaussian_pack_args(iso)[2] == COV_ISO_SHARED
+    iso[1].set_moments(np.ones(3), np.diag([0.2, 0.3, 0.2]))
+    assert gaussian_pack_args(iso)[2] == COV_DIAG
+    iso[2].set_moments(np.ones(3), np.array([[1, .1, 0], [.1, 1, 0], [0, 0, 1.0]]))
+    assert gaussian_pack_args(iso)[2] == COV_FULL
+    m = CMixtureModel({"models": iso, "weights": np.ones(4), "dims": 3, "support": [[-9] * 3, [9] * 3]})
+    k1 = m._key()
+    iso[0].set_moments(np.zeros(3), np.eye(3))
+    assert m._key() != k1                                          # component edits invalidate the packed cache
+
+
+def test_uniform_constructor():
+    u = CMultivariateUniform({"center": np.array([0.0, 0.1]), "radius": np.array([0.5, 0.2])})
+    assert u.prob_val == pytest.approx(1 / (1.0 * 0.4)) and np.allclose(u.support(), [[-0.5, -0.1], [0.5, 0.3]])
+    u1 = CMultivariateUniform({"center": np.zeros(3), "radius": np.array([0.5])})
+    lo, hi, lpv = u1.box()
+    assert np.allclose(lo, -0.5) and np.allclose(hi, 0.5) and lpv == pytest.approx(0.0)
+    with pytest.raises(ValueError):
+        CMultivariateUniform({"center": np.zeros(3), "radius": np.array([0.5, 0.5])})
+    assert u.integral(np.array([-1.0, -1.0]), np.array([0.0, 1.0])) == pytest.approx(0.5)
+
+
+def test_sampler_state_and_counters():
+    np.random.seed(3)
+    base = {"space_min": np.array([-1.0, -2.0]), "space_max": np.array([1.0, 2.0]), "dims": 2}
+    dm = CDeterministicMixtureAIS(dict(base, K=3, N=4, J=10, sigma=0.1, name="dm"))
+    assert dm.name == "dm" and dm.get_stats() == {"proposal_samples": 0, "proposal_evals": 0, "target_evals": 0,
+                                                   "n_samples": 0}
+    means = np.array([p.loc for p in dm.proposals])
+    assert means.shape == (4, 2) and np.all(means >= base["space_min"]) and np.all(means <= base["space_max"])
+    assert np.allclose(dm.proposals[0].scale, np.eye(2) * 0.1) and np.allclose(dm.model.weights, 0.25)
+    dm.name, dm.debug = "x", True
+    assert dm.name == "x" and dm.debug is True
+    assert len(dm.samples) == 0 and len(dm.weights) == 0
+    with pytest.raises(AssertionError):
+        dm.get_acceptance_rate()
+    dm.reset()
+    assert not np.allclose(np.array([p.loc for p in dm.proposals]), means)      # new proposal centres after reset
+    with pytest.raises(AssertionError):
+        CDeterministicMixtureAIS(dict(base, dims=3, K=3, N=4, J=10, sigma=0.1))
+    pmc = CMixturePMC(dict(base, K=5, N=3, J=10, sigma=0.01))
+    assert np.allclose(pmc.wproposals, 1 / 3) and len(pmc.proposals) == 3 and not pmc.paper_covariance
+    la = CLayeredAIS(dict(base, K=2, N=3, J=10, L=4, sigma=0.1, mh_sigma=0.5))
+    assert la.L == 4 and la.mhsigma == 0.5 and len(la.proposals) == 3
+
+
+def test_metric_contract():
+    m = CKLDivergence()
+    assert (m.name, m.type, m.is_symmetric, m.disjoint_support, m.value) == ("KL", "divergence", False, False, 0)
+    m.pre(); m.post(); m.reset()
+    with pytest.raises(AssertionError):
+        m.compute(p=object(), q=object(), nsamples=10)
+    with pytest.raises(NotImplementedError):
+        CMetric().compute()
+    res = CKLDivergence.compute_from_probs(np.array([0.2, 0.3, 0.5, 0.0]), np.array([0.25, 0.25, 0.5, 0.1]))
+    p, q = np.array([0.2, 0.3, 0.5]), np.array([0.25, 0.25, 0.5])
+    assert res.sum() == pytest.approx(np.sum(p * np.log(p / q)))
+
+
+@no_gpu
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry point raises instead of silently running elsewhere."""
+    g = CGaussianMixtureModel({"means": [[0.0]], "sigmas": [[1.0]], "support": [[-5], [5]]})
+    for call in (lambda: g.log_prob(np.zeros((2, 1))), lambda: g.prob(np.zeros((2, 1))), lambda: g.sample(3),
+                 lambda: CMultivariateUniform({"center": np.zeros(1), "radius": np.ones(1)}).log_prob(np.zeros((1, 1))),
+                 lambda: CKLDivergence().compute(p=g, q=g, nsamples=10)):
+        with pytest.raises(AisbError, match="no CPU fallback"):
+            call()
+    np.random.seed(0)
+    dm = CDeterministicMixtureAIS({"space_min": np.array([-1.0]), "space_max": np.array([1.0]), "dims": 1, "K": 2, "N": 2,
+                                   "J": 1, "sigma": 0.1})
+    with pytest.raises(AisbError):
+        dm.importance_sample(g, 4)
