@@ -128,15 +128,15 @@ __global__ void uniform_box_kernel(const float* __restrict__ lo, const float* __
 // Peak micro-benchmarks: 8 independent dependent-chains per thread, no memory traffic
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) peak_fma_kernel(int64_t iters, float* sink) {
-  // packed FFMA2 chains: 2 FMAs per lane per instruction (the form the pairwise kernels use); 8 chains x 4 rounds
-  // x 2 lanes-worth = 64 FMAs per thread per iteration, counted as 32 "ops" of 2 FMAs by the caller
+  // packed FFMA2 chains (the form the pairwise kernels use): 8 chains x 8 rounds per iteration, multiplier and addend
+  // loaded at run time so that they stay in registers. The caller counts 64 packed instructions = 128 FMAs per lane.
   float2 a[8];
+  const float2 m = make_float2(sink[1] + 0.999999f, sink[1] + 0.999998f), c = make_float2(sink[2] + 1.0e-7f, sink[2] + 2.0e-7f);
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = make_float2(0.001f * (threadIdx.x + i), 0.002f * (threadIdx.x + i));
-  const float2 m = make_float2(0.999999f, 0.999998f), c = make_float2(1.0e-7f, 2.0e-7f);
   for (int64_t it = 0; it < iters; ++it) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < 8; ++r)
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[i] = __ffma2_rn(a[i], m, c);
   }
@@ -239,7 +239,7 @@ static int peak_launch(void (*kern)(int64_t, float*), int64_t iters, float* d_si
 
 extern "C" int aisb_peak_fma_f32(int64_t iters, float* d_sink, double* ops, void* stream) {
   const int rc = peak_launch(peak_fma_kernel, iters, d_sink, ops, stream);
-  if (rc == AISB_OK && ops) *ops *= 2.0;  // every packed instruction is two FMAs per lane
+  if (rc == AISB_OK && ops) *ops *= 4.0;  // 64 packed instructions per iteration, two FMAs per lane each
   return rc;
 }
 extern "C" int aisb_peak_ex2_f32(int64_t iters, float* d_sink, double* ops, void* stream) {

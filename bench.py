@@ -26,6 +26,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+print_json = None
 METRIC = "KDE-KLD kernel-evals/sec"
 UNIT = "kernel-evals/s"
 KDE_CFG = dict(D=8, modes=16, n_centres=1_000_000, n_eval=1_000_000, bw=0.02)
@@ -333,7 +334,7 @@ def run_cuda(args):
                                     "kernel": "dm_weights_kernel<32, ISO_SHARED>", "kernel_ms": dm_kernel_ms},
                        "gpu_launches": 3 * args.steps},
         }
-        print(json.dumps(out))
+        print_json(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -407,10 +408,16 @@ def run_reference(args):
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    print_json(out)
 
 
 def main():
+    # Libraries (NCCL's version banner, torchrun notices) may write to stdout; the contract is ONE JSON line there.
+    # Keep the real stdout aside, point fd 1 at stderr for the duration of the run, print the JSON to the real one.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global print_json
+    print_json = lambda obj: (real_stdout.write(json.dumps(obj) + "\n"), real_stdout.flush())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

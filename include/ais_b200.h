@@ -244,7 +244,7 @@ int aisb_uniform_box_f32(const float* d_lo, const float* d_hi, int32_t D, int64_
 /* Micro-benchmarks used to measure the FP32-FMA and MUFU.EX2 peaks on the box (bench.py roofline denominators).
  * Each runs `iters` dependent-chain iterations in every thread of a full-chip grid; *ops = FMAs (packed FFMA2 chains,
  * 2 flop each) resp. EX2 evaluations executed. */
-int aisb_peak_fma_f32(int64_t iters, float* d_sink, double* ops, void* stream);
+int aisb_peak_fma_f32(int64_t iters, float* d_sink /* >= 4 zeroed floats */, double* ops, void* stream);
 int aisb_peak_ex2_f32(int64_t iters, float* d_sink, double* ops, void* stream);
 
 #ifdef __cplusplus
