@@ -4,6 +4,7 @@ from .base import CSamplingMethod, CMixtureSamplingMethod, CMixtureISSamplingMet
 from .dm_ais import CDeterministicMixtureAIS
 from .layered_ais import CLayeredAIS
 from .m_pmc import CMixturePMC
+from .tree_pyramid import CTreePyramid, CTreePyramidSampling
 
 __all__ = ["CSamplingMethod", "CMixtureSamplingMethod", "CMixtureISSamplingMethod", "CDeviceKDE",
-           "CDeterministicMixtureAIS", "CLayeredAIS", "CMixturePMC"]
+           "CDeterministicMixtureAIS", "CLayeredAIS", "CMixturePMC", "CTreePyramid", "CTreePyramidSampling"]

@@ -19,7 +19,8 @@ ref_harness.load()
 from ais_benchmarks.distributions import (CGaussianMixtureModel, CMixtureModel, CMultivariateNormal,  # noqa: E402
                                           CMultivariateUniform)
 from ais_benchmarks.metrics.divergences import CKLDivergence  # noqa: E402
-from ais_benchmarks.sampling_methods import CDeterministicMixtureAIS, CLayeredAIS, CMixturePMC  # noqa: E402
+from ais_benchmarks.sampling_methods import (CDeterministicMixtureAIS, CLayeredAIS, CMixturePMC,  # noqa: E402
+                                             CTreePyramidSampling)
 from ais_benchmarks.sampling_methods.base import CMixtureSamplingMethod  # noqa: E402
 from ais_benchmarks.utils.misc import generateRandomGMM  # noqa: E402
 
@@ -300,6 +301,54 @@ def make_uniform():
     save("uniform", **out)
 
 
+def make_tpais():
+    """TP-AIS "simple" runs (sampling_methods/tree_pyramid.py:421-457) with every random draw captured in prototype units
+    (uniform: (x - centre) / (2 radius); normal: (x - mean) / sqrt(var)), so that the run can be replayed exactly."""
+    out = {}
+    cfgs = [("haar", 0.9, 5, 32, 120, 70), ("normal", 0.9, 5, 32, 100, 71), ("haar", 2.0, 5, 8, 60, 72)]
+    for i, (kernel, ess_target, n_min, par, n_samples, seed) in enumerate(cfgs):
+        target = CGaussianMixtureModel({"means": [[0.0, 0.0], [-0.3, 0.5]], "sigmas": [[0.01, 0.1], [0.01, 0.03]],
+                                        "weights": [0.5, 0.5], "support": [[-1, -1], [1, 1]]})
+        queue = []
+        real_u, real_n = CMultivariateUniform.sample, CMultivariateNormal.sample
+
+        def rec_u(self, n_samples=1):
+            res = real_u(self, n_samples)
+            queue.append((res - self._loc) / (2 * self._scale))
+            return res
+
+        def rec_n(self, n_samples=1):
+            res = real_n(self, n_samples)
+            queue.append((res - self._loc.reshape(1, -1)) / np.sqrt(np.diag(self._scale)).reshape(1, -1))
+            return res
+
+        CMultivariateUniform.sample, CMultivariateNormal.sample = rec_u, rec_n
+        try:
+            np.random.seed(seed)
+            s = CTreePyramidSampling({"space_min": np.array([-1.0, -1.0]), "space_max": np.array([1.0, 1.0]), "dims": 2,
+                                      "method": "simple", "resampling": "leaf", "kernel": kernel,
+                                      "ess_target": ess_target, "n_min": n_min, "parallel_samples": par})
+            samples, weights = s.importance_sample(target, n_samples, timeout=600)
+        finally:
+            CMultivariateUniform.sample, CMultivariateNormal.sample = real_u, real_n
+        rs = np.random.RandomState(seed + 1)
+        xt = rs.uniform(-1, 1, size=(400, 2))
+        out["kernel%d" % i] = np.array(kernel)
+        out["cfg%d" % i] = np.array([ess_target, n_min, par, n_samples], dtype=np.float64)
+        out["draws%d" % i] = np.concatenate(queue)
+        out["samples%d" % i], out["weights%d" % i] = np.array(samples), np.array(weights)
+        out["centers%d" % i], out["radii%d" % i] = np.array(s.T.centers), np.array(s.T.radii).reshape(-1)
+        out["tweights%d" % i], out["leaves_idx%d" % i] = np.array(s.T.weights), np.array(s.T.leaves_idx)
+        out["ness%d" % i] = np.array(s.get_NESS())
+        out["counters%d" % i] = np.array([s.num_proposal_samples, s.num_proposal_evals, s.num_target_evals])
+        out["xt%d" % i] = xt
+        out["prob%d" % i] = s.prob(xt)
+        out["model_logp%d" % i] = s.model.log_prob(xt)
+        out["acc%d" % i] = np.array(s.get_acceptance_rate())
+    out["n"] = np.array(len(cfgs))
+    save("tpais", **out)
+
+
 if __name__ == "__main__":
     np.seterr(all="ignore")
     make_mvn()
@@ -310,3 +359,4 @@ if __name__ == "__main__":
     make_mpmc()
     make_lais()
     make_uniform()
+    make_tpais()

@@ -478,3 +478,40 @@ def test_large_kde_properties_and_row_subset():
     perm = torch.randperm(n, device="cuda")
     p = _device.mixture_logpdf(xd, _device.DeviceMixture.kde(cd, perm, n, bw))
     assert rel_err(p.cpu().numpy(), full.cpu().numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("case", range(3))
+def test_tpais_replay_on_device(case):
+    """TP-AIS with the reference's captured draws, target densities from the CUDA kernels: same tree and samples,
+    weights / NESS within tolerance; haar `prob` (box-mixture kernel, strict bounds) and the leaf mixture model vs the
+    reference's values at 400 test points."""
+    from test_host_logic import run_tpais_replay
+    target = gmm(np.array([[0.0, 0.0], [-0.3, 0.5]]), np.array([[0.01, 0.1], [0.01, 0.03]]), np.array([0.5, 0.5]),
+                 [[-1, -1], [1, 1]])
+    g, s, samples, weights = run_tpais_replay(case, target)
+    assert np.array_equal(s.T.leaves_idx, g["leaves_idx%d" % case])
+    assert np.allclose(samples, g["samples%d" % case], atol=1e-12)
+    ref_w = g["weights%d" % case]
+    big = ref_w > 1e-9 * ref_w.max()
+    assert np.max(np.abs(weights[big] - ref_w[big]) / ref_w[big]) < W_TOL
+    assert s.get_NESS() == pytest.approx(float(g["ness%d" % case]), rel=W_TOL)
+    xt = g["xt%d" % case]
+    ref_p = g["prob%d" % case]
+    got_p = s.prob(xt)
+    assert np.array_equal(got_p == 0, ref_p == 0)
+    nz = ref_p > 0
+    assert np.max(np.abs(got_p[nz] - ref_p[nz]) / ref_p[nz]) < W_TOL
+    with np.errstate(divide="ignore"):
+        assert rel_err(s.log_prob(xt), np.log(ref_p)) < 2e-5
+    assert rel_err(s.model.log_prob(xt), g["model_logp%d" % case]) < 2e-5
+    # end-to-end with device draws: interface contract only (RNG streams are not comparable)
+    from ais_benchmarks_b200 import _device
+    from ais_benchmarks_b200.sampling_methods import CTreePyramidSampling
+    _device.seed(5)
+    t = CTreePyramidSampling({"space_min": np.array([-1.0, -1.0]), "space_max": np.array([1.0, 1.0]), "dims": 2,
+                              "method": "simple", "resampling": "leaf", "kernel": str(g["kernel%d" % case]),
+                              "ess_target": 0.9, "n_min": 5, "parallel_samples": 32})
+    x, w = t.importance_sample(target, 80)
+    assert len(x) == len(w) >= 80 and np.all(w > 0) and 0 < t.get_NESS() <= 1
+    from ais_benchmarks_b200.metrics import CKLDivergence
+    assert np.isfinite(CKLDivergence().compute(p=target, q=t, nsamples=2000))

@@ -138,3 +138,75 @@ def test_no_cpu_fallback():
                                    "J": 1, "sigma": 0.1})
     with pytest.raises(AisbError):
         dm.importance_sample(g, 4)
+
+
+class ReplayDraws:
+    """Feeds TP-AIS the prototype draws captured from the reference run (tests/golden/make_golden.py:make_tpais)."""
+
+    def __init__(self, rows):
+        self.rows, self.pos = rows, 0
+
+    def _take(self, n, dims):
+        out = self.rows[self.pos:self.pos + n]
+        assert out.shape == (n, dims), "replay exhausted or out of step with the reference"
+        self.pos += n
+        return out
+
+    uniform = _take
+    normal = _take
+
+
+class OracleTarget:
+    """float64 host target: isolates the tree logic from float32 kernel rounding in the CPU test."""
+
+    def __init__(self, means, sigmas, weights):
+        self.args = (np.asarray(means, float), np.asarray(sigmas, float), np.asarray(weights, float))
+
+    def prob(self, x):
+        from oracle import ais_oracle as O
+        return O.gmm_prob(x, *self.args)
+
+
+def run_tpais_replay(case, target):
+    from conftest import load_golden
+    from ais_benchmarks_b200.sampling_methods import CTreePyramidSampling
+    g = load_golden("tpais")
+    ess_target, n_min, par, n_samples = g["cfg%d" % case]
+    s = CTreePyramidSampling({"space_min": np.array([-1.0, -1.0]), "space_max": np.array([1.0, 1.0]), "dims": 2,
+                              "method": "simple", "resampling": "leaf", "kernel": str(g["kernel%d" % case]),
+                              "ess_target": float(ess_target), "n_min": int(n_min), "parallel_samples": int(par)})
+    s.draws = ReplayDraws(g["draws%d" % case])
+    samples, weights = s.importance_sample(target, int(n_samples), timeout=600)
+    return g, s, samples, weights
+
+
+@pytest.mark.parametrize("case", range(3))
+def test_tpais_tree_logic_replays_reference_run(case):
+    """Same draws + same (float64) target -> the same tree, samples, weights, NESS and counters as the reference
+    (sampling_methods/tree_pyramid.py:421-457, 500-533, 646-708), including the `_get_samples` offset quirk."""
+    g, s, samples, weights = run_tpais_replay(case, OracleTarget([[0.0, 0.0], [-0.3, 0.5]], [[0.01, 0.1], [0.01, 0.03]],
+                                                                   [0.5, 0.5]))
+    assert s.draws.pos == len(g["draws%d" % case])                      # consumed exactly the reference's draws
+    assert np.allclose(s.T.centers, g["centers%d" % case], atol=1e-15)
+    assert np.allclose(s.T.radii, g["radii%d" % case], atol=1e-15)
+    assert np.array_equal(s.T.leaves_idx, g["leaves_idx%d" % case])
+    assert np.allclose(s.T.weights, g["tweights%d" % case], rtol=1e-9, atol=1e-300)
+    assert samples.shape == g["samples%d" % case].shape
+    assert np.allclose(samples, g["samples%d" % case], atol=1e-12)
+    assert np.allclose(weights, g["weights%d" % case], rtol=1e-9)
+    assert s.get_NESS() == pytest.approx(float(g["ness%d" % case]), rel=1e-9)
+    assert [s.num_proposal_samples, s.num_proposal_evals, s.num_target_evals] == list(g["counters%d" % case])
+    assert s.get_acceptance_rate() == pytest.approx(float(g["acc%d" % case]))
+    assert np.allclose(s.model.weights, g["tweights%d" % case][g["leaves_idx%d" % case]], rtol=1e-9)
+
+
+def test_tpais_rejects_dead_reference_methods():
+    from ais_benchmarks_b200.sampling_methods import CTreePyramidSampling
+    base = {"space_min": np.array([-1.0]), "space_max": np.array([1.0]), "dims": 1, "resampling": "leaf",
+            "kernel": "haar", "ess_target": 0.9, "n_min": 5, "parallel_samples": 4}
+    with pytest.raises(NotImplementedError):
+        CTreePyramidSampling(dict(base, method="dm"))
+    with pytest.raises(AssertionError):
+        CTreePyramidSampling(dict(base, method="bogus"))
+    with pytest.raises(AssertionError):
+        CTreePyramidSampling(dict(base, method="simple", kernel="triangle"))
