@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libais_b200.so")
+# AISB_LIB selects an alternative build of the same ABI (kernel tuning experiments); the default is the in-tree library
+LIB_PATH = os.environ.get("AISB_LIB") or os.path.join(_HERE, "libais_b200.so")
 
 AISB_OK = 0
 COV_ISO_SHARED, COV_DIAG, COV_FULL = 0, 1, 2

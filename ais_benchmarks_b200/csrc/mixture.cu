@@ -2,6 +2,10 @@
 #include "pairwise.cuh"
 #include "reduce.cuh"
 
+#ifndef AISB_MIN_CTAS_SMALL
+#define AISB_MIN_CTAS_SMALL 4  // resident CTAs per SM asked of the compiler for the DP <= 8 pairwise kernels
+#endif
+
 namespace aisb {
 
 struct PassArgs {
@@ -19,7 +23,7 @@ struct PassArgs {
 // lse_merge_kernel finishes.
 // ---------------------------------------------------------------------------------------------
 template <int KIND, int DP, bool HAS_C>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (KIND != AISB_COV_FULL && DP <= 8) ? AISB_MIN_CTAS_SMALL : 1)
     logpdf_kernel(const float* __restrict__ x, int64_t n, int D, int vec_ok, PassArgs mix, int nsplit,
                   int64_t comps_per_split, int64_t ntiles, float* __restrict__ out, float* __restrict__ ws_m,
                   float* __restrict__ ws_S) {
@@ -188,10 +192,11 @@ static bool make_plan(int64_t n, int64_t K, int D, Plan* p) {
   p->KP = aisb_padded_components(K);
   const int64_t tile_pts = static_cast<int64_t>(kThreads) * p->E;
   p->ntiles = n > 0 ? (n + tile_pts - 1) / tile_pts : 0;
-  // Split the component range when the point tiles alone cannot fill ~32 waves of CTAs
-  // (4 resident CTAs per SM); keep >= 1024 components per split.
-  const int64_t target = static_cast<int64_t>(sm_count()) * 4 * 32;
-  int64_t max_split = p->KP / 1024;
+  // Split the component range when the point tiles alone cannot fill ~16 waves of CTAs
+  // (4 resident CTAs per SM; tail loss <= 1/waves); keep >= 2048 components per split so that the
+  // per-CTA prologue (point load, barrier init) and the partial (m, S) traffic stay negligible.
+  const int64_t target = static_cast<int64_t>(sm_count()) * 4 * 16;
+  int64_t max_split = p->KP / 2048;
   if (max_split < 1) max_split = 1;
   int64_t want = p->ntiles > 0 ? (target + p->ntiles - 1) / p->ntiles : 1;
   if (want > max_split) want = max_split;

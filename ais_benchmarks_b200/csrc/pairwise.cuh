@@ -30,7 +30,10 @@ namespace aisb {
 // ---------------------------------------------------------------------------------------------
 // Compile-time tiling traits
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int points_per_thread(int DP) { return DP <= 16 ? 4 : 2; }
+#ifndef AISB_E_SMALL
+#define AISB_E_SMALL 4  // points per thread for DP <= 8
+#endif
+__host__ __device__ constexpr int points_per_thread(int DP) { return DP <= 8 ? AISB_E_SMALL : (DP <= 16 ? 4 : 2); }
 
 #ifndef AISB_JJ_SMALL
 #define AISB_JJ_SMALL 4  // components per online-LSE step for DP <= 8 (ISO/DIAG)
@@ -211,7 +214,7 @@ __device__ __forceinline__ void lds_vec2(const float* __restrict__ p, float2 (&v
 __device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
 
 template <int KIND, int DP, int EP>
-__device__ __forceinline__ void comp_eval2(const float* __restrict__ row, float c, float a_iso,
+__device__ __forceinline__ void comp_eval2(const float* __restrict__ row, const float2 (&seed)[EP], float a_iso,
                                            const float2 (&x2)[EP][DP], float2 (&t2)[EP]) {
   float2 b2[DP];
   if constexpr (KIND == AISB_COV_ISO_SHARED) {
@@ -219,7 +222,7 @@ __device__ __forceinline__ void comp_eval2(const float* __restrict__ row, float 
     const float2 a2 = make_float2(a_iso, a_iso);
 #pragma unroll
     for (int pp = 0; pp < EP; ++pp) {
-      float2 acc = make_float2(c, c);
+      float2 acc = seed[pp];
 #pragma unroll
       for (int d = 0; d < DP; ++d) {
         const float2 dl = __ffma2_rn(x2[pp][d], a2, b2[d]);
@@ -233,7 +236,7 @@ __device__ __forceinline__ void comp_eval2(const float* __restrict__ row, float 
     lds_vec2<DP>(row + 2 * DP, b2);
 #pragma unroll
     for (int pp = 0; pp < EP; ++pp) {
-      float2 acc = make_float2(c, c);
+      float2 acc = seed[pp];
 #pragma unroll
       for (int d = 0; d < DP; ++d) {
         const float2 dl = __ffma2_rn(x2[pp][d], a2[d], b2[d]);
@@ -246,22 +249,29 @@ __device__ __forceinline__ void comp_eval2(const float* __restrict__ row, float 
 
 template <int KIND, int DP, int EP, int JJ, bool HAS_C>
 __device__ __forceinline__ void eval_group2(const float* __restrict__ srows, const float* __restrict__ soffs, int j0,
-                                            float a_iso, const float2 (&x2)[EP][DP], float2 (&t)[JJ][EP]) {
+                                            float a_iso, const float2 (&x2)[EP][DP], const float2 (&seed0)[EP],
+                                            float2 (&t)[JJ][EP]) {
   constexpr int ROW = row_floats(KIND, DP);
-  float c[JJ];
   if constexpr (HAS_C) {
+    float c[JJ];
     lds_vec<JJ>(soffs + j0, c);
+#pragma unroll
+    for (int jj = 0; jj < JJ; ++jj) {
+      float2 seed[EP];
+#pragma unroll
+      for (int pp = 0; pp < EP; ++pp) seed[pp] = make_float2(c[jj], c[jj]);
+      comp_eval2<KIND, DP, EP>(srows + (j0 + jj) * ROW, seed, a_iso, x2, t[jj]);
+    }
   } else {
 #pragma unroll
-    for (int jj = 0; jj < JJ; ++jj) c[jj] = 0.f;
+    for (int jj = 0; jj < JJ; ++jj) comp_eval2<KIND, DP, EP>(srows + (j0 + jj) * ROW, seed0, a_iso, x2, t[jj]);
   }
-#pragma unroll
-  for (int jj = 0; jj < JJ; ++jj) comp_eval2<KIND, DP, EP>(srows + (j0 + jj) * ROW, c[jj], a_iso, x2, t[jj]);
 }
 
-// fold one evaluated group into the running (m, S) of each point
+// fold one evaluated group into the running (m, S) of each point pair. Every FP32 operation here is PACKED
+// (FADD2 / FMUL2): a scalar FADD between FFMA2s leaves half of the FMA datapath idle for its two cycles.
 template <int EP, int JJ>
-__device__ __forceinline__ void lse_update2(const float2 (&t)[JJ][EP], float (&m)[2 * EP], float (&S)[2 * EP]) {
+__device__ __forceinline__ void lse_update2(const float2 (&t)[JJ][EP], float2 (&m2)[EP], float2 (&S2)[EP]) {
 #pragma unroll
   for (int pp = 0; pp < EP; ++pp) {
     float g0 = t[0][pp].x, g1 = t[0][pp].y;
@@ -270,17 +280,17 @@ __device__ __forceinline__ void lse_update2(const float2 (&t)[JJ][EP], float (&m
       g0 = fmaxf(g0, t[jj][pp].x);
       g1 = fmaxf(g1, t[jj][pp].y);
     }
-    const float m0 = fmaxf(m[2 * pp], g0), m1 = fmaxf(m[2 * pp + 1], g1);
-    float s0 = S[2 * pp] * ex2(m[2 * pp] - m0), s1 = S[2 * pp + 1] * ex2(m[2 * pp + 1] - m1);
+    const float2 mn = make_float2(fmaxf(m2[pp].x, g0), fmaxf(m2[pp].y, g1));
+    const float2 nmn = neg2(mn);
+    const float2 dm = __fadd2_rn(m2[pp], nmn);
+    float2 acc = __fmul2_rn(S2[pp], make_float2(ex2(dm.x), ex2(dm.y)));
 #pragma unroll
     for (int jj = 0; jj < JJ; ++jj) {
-      s0 += ex2(t[jj][pp].x - m0);
-      s1 += ex2(t[jj][pp].y - m1);
+      const float2 a = __fadd2_rn(t[jj][pp], nmn);
+      acc = __fadd2_rn(acc, make_float2(ex2(a.x), ex2(a.y)));
     }
-    S[2 * pp] = s0;
-    S[2 * pp + 1] = s1;
-    m[2 * pp] = m0;
-    m[2 * pp + 1] = m1;
+    S2[pp] = acc;
+    m2[pp] = mn;
   }
 }
 
@@ -289,14 +299,99 @@ __device__ __forceinline__ void lse_update2(const float2 (&t)[JJ][EP], float (&m
 template <int KIND, int DP, int EP, int JJ, bool HAS_C>
 __device__ __forceinline__ void accumulate_chunk2(const float* __restrict__ srows, const float* __restrict__ soffs,
                                                   int cnt, float a_iso, const float2 (&x2)[EP][DP],
-                                                  float2 (&tP)[JJ][EP], float (&m)[2 * EP], float (&S)[2 * EP]) {
+                                                  float2 (&tP)[JJ][EP], float2 (&m)[EP], float2 (&S)[EP]) {
+  float2 zero[EP];
+#pragma unroll
+  for (int pp = 0; pp < EP; ++pp) zero[pp] = make_float2(0.f, 0.f);
 #pragma unroll 1
   for (int j0 = 0; j0 < cnt; j0 += 2 * JJ) {
     float2 tQ[JJ][EP];
-    eval_group2<KIND, DP, EP, JJ, HAS_C>(srows, soffs, j0, a_iso, x2, tQ);
+    eval_group2<KIND, DP, EP, JJ, HAS_C>(srows, soffs, j0, a_iso, x2, zero, tQ);
     lse_update2<EP, JJ>(tP, m, S);
-    eval_group2<KIND, DP, EP, JJ, HAS_C>(srows, soffs, j0 + JJ, a_iso, x2, tP);
+    eval_group2<KIND, DP, EP, JJ, HAS_C>(srows, soffs, j0 + JJ, a_iso, x2, zero, tP);
     lse_update2<EP, JJ>(tQ, m, S);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lazy-reference variant for mixtures WITHOUT per-component offsets (KDE, equal-weight proposals).
+// The FFMA2 chain of every pair is seeded with -mref (the point's current reference exponent), so it ends
+// directly in t' = t - mref and the common case needs no subtraction and no rescale: S += ex2(t').
+// mref is only moved when a group maximum exceeds it by more than kLazyThresh (or at the first group): the
+// rare slow path shifts mref, rescales S and patches the two groups that are in flight. mref trails the true
+// running maximum by at most kLazyThresh, so terms stay below 2^kLazyThresh and nothing that matters underflows.
+// Saves one FADD2 per pair and the per-group MUFU / FMUL2 of the eager scheme.
+// ---------------------------------------------------------------------------------------------
+constexpr float kLazyThresh = 16.f;
+
+template <int EP, int JJ>
+__device__ __forceinline__ void lse_update2_lazy(float2 (&t)[JJ][EP], float2 (&other)[JJ][EP], float2 (&mref)[EP],
+                                                 float2 (&S)[EP], int& phase) {
+  // phase 0: nothing pending yet (pipeline prologue, `t` is not a real group); 1: `t` is the first real group;
+  // 2: steady state. The phase is uniform across the CTA.
+  if (phase == 0) {
+    phase = 1;
+    return;
+  }
+  const bool fresh = phase == 1;
+  float2 g[EP];
+  bool trig = fresh;
+#pragma unroll
+  for (int pp = 0; pp < EP; ++pp) {
+    float g0 = t[0][pp].x, g1 = t[0][pp].y;
+#pragma unroll
+    for (int jj = 1; jj < JJ; ++jj) {
+      g0 = fmaxf(g0, t[jj][pp].x);
+      g1 = fmaxf(g1, t[jj][pp].y);
+    }
+    g[pp] = make_float2(g0, g1);
+    trig = trig || (g0 > kLazyThresh) || (g1 > kLazyThresh);
+  }
+  if (trig) {
+#pragma unroll
+    for (int pp = 0; pp < EP; ++pp) {
+      // first group: reference exactly on its maximum (may move down); later: only move up. Non-finite maxima
+      // (NaN input, -inf from overflowed coordinates) leave the reference where it is.
+      float d0 = (fresh || g[pp].x > kLazyThresh) ? g[pp].x : 0.f;
+      float d1 = (fresh || g[pp].y > kLazyThresh) ? g[pp].y : 0.f;
+      d0 = (d0 > -1.0e30f && d0 < 1.0e30f) ? d0 : 0.f;
+      d1 = (d1 > -1.0e30f && d1 < 1.0e30f) ? d1 : 0.f;
+      const float2 nd = make_float2(-d0, -d1);
+      mref[pp] = make_float2(mref[pp].x + d0, mref[pp].y + d1);
+      // d < 0 only happens at the first group, where S is still 0: clamp so that 0 * 2^(+big) cannot make a NaN
+      S[pp] = __fmul2_rn(S[pp], make_float2(ex2(fminf(-d0, 0.f)), ex2(fminf(-d1, 0.f))));
+#pragma unroll
+      for (int jj = 0; jj < JJ; ++jj) {
+        t[jj][pp] = __fadd2_rn(t[jj][pp], nd);
+        other[jj][pp] = __fadd2_rn(other[jj][pp], nd);
+      }
+    }
+    phase = 2;
+  }
+#pragma unroll
+  for (int pp = 0; pp < EP; ++pp) {
+    float2 acc = S[pp];
+#pragma unroll
+    for (int jj = 0; jj < JJ; ++jj) acc = __fadd2_rn(acc, make_float2(ex2(t[jj][pp].x), ex2(t[jj][pp].y)));
+    S[pp] = acc;
+  }
+}
+
+template <int KIND, int DP, int EP, int JJ>
+__device__ __forceinline__ void accumulate_chunk2_lazy(const float* __restrict__ srows, int cnt, float a_iso,
+                                                       const float2 (&x2)[EP][DP], float2 (&tP)[JJ][EP],
+                                                       float2 (&mref)[EP], float2 (&S)[EP], int& phase) {
+#pragma unroll 1
+  for (int j0 = 0; j0 < cnt; j0 += 2 * JJ) {
+    float2 tQ[JJ][EP], seed[EP];
+#pragma unroll
+    for (int pp = 0; pp < EP; ++pp) seed[pp] = neg2(mref[pp]);
+    eval_group2<KIND, DP, EP, JJ, false>(srows, nullptr, j0, a_iso, x2, seed, tQ);
+    lse_update2_lazy<EP, JJ>(tP, tQ, mref, S, phase);
+#pragma unroll
+    for (int pp = 0; pp < EP; ++pp) seed[pp] = neg2(mref[pp]);
+    eval_group2<KIND, DP, EP, JJ, false>(srows, nullptr, j0 + JJ, a_iso, x2, seed, tP);
+    lse_update2_lazy<EP, JJ>(tQ, tP, mref, S, phase);
   }
 }
 
@@ -369,16 +464,48 @@ __device__ __forceinline__ void mixture_pass(const float* __restrict__ g_rows, c
     for (int pp = 0; pp < EP; ++pp)
 #pragma unroll
       for (int d = 0; d < DP; ++d) x2[pp][d] = make_float2(x[2 * pp][d], x[2 * pp + 1][d]);
-    float2 tP[JJ][EP];
+    float2 tP[JJ][EP], m2[EP], S2[EP];
 #pragma unroll
     for (int jj = 0; jj < JJ; ++jj)
 #pragma unroll
       for (int pp = 0; pp < EP; ++pp) tP[jj][pp] = make_float2(-INFINITY, -INFINITY);
-    stream_components<KIND, DP, HAS_C>(
-        g_rows, g_offs, k_begin, k_end, smem, bars, it, [&](const float* srows, const float* soffs, int cnt, int64_t) {
-          accumulate_chunk2<KIND, DP, EP, JJ, HAS_C>(srows, soffs, cnt, a_iso, x2, tP, m, S);
-        });
-    lse_update2<EP, JJ>(tP, m, S);
+    if constexpr (HAS_C) {
+#pragma unroll
+      for (int pp = 0; pp < EP; ++pp) {
+        m2[pp] = make_float2(m[2 * pp], m[2 * pp + 1]);
+        S2[pp] = make_float2(S[2 * pp], S[2 * pp + 1]);
+      }
+      stream_components<KIND, DP, HAS_C>(
+          g_rows, g_offs, k_begin, k_end, smem, bars, it, [&](const float* srows, const float* soffs, int cnt, int64_t) {
+            accumulate_chunk2<KIND, DP, EP, JJ, HAS_C>(srows, soffs, cnt, a_iso, x2, tP, m2, S2);
+          });
+      lse_update2<EP, JJ>(tP, m2, S2);
+    } else {
+      // lazy-reference scheme; the pass starts from scratch (callers enter with m = kNegBig, S = 0)
+      int phase = 0;
+      float2 tDummy[JJ][EP];
+#pragma unroll
+      for (int pp = 0; pp < EP; ++pp) {
+        m2[pp] = make_float2(0.f, 0.f);
+        S2[pp] = make_float2(0.f, 0.f);
+      }
+      stream_components<KIND, DP, HAS_C>(
+          g_rows, g_offs, k_begin, k_end, smem, bars, it, [&](const float* srows, const float*, int cnt, int64_t) {
+            accumulate_chunk2_lazy<KIND, DP, EP, JJ>(srows, cnt, a_iso, x2, tP, m2, S2, phase);
+          });
+#pragma unroll
+      for (int jj = 0; jj < JJ; ++jj)
+#pragma unroll
+        for (int pp = 0; pp < EP; ++pp) tDummy[jj][pp] = make_float2(-INFINITY, -INFINITY);
+      if (phase != 0) lse_update2_lazy<EP, JJ>(tP, tDummy, m2, S2, phase);
+    }
+#pragma unroll
+    for (int pp = 0; pp < EP; ++pp) {
+      m[2 * pp] = m2[pp].x;
+      m[2 * pp + 1] = m2[pp].y;
+      S[2 * pp] = S2[pp].x;
+      S[2 * pp + 1] = S2[pp].y;
+    }
   }
 }
 

@@ -97,13 +97,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Start of the timed region: samples taken before this call are dropped. (nvidia-smi is started during
+        warm-up because its start-up stalls kernel launches for tens of milliseconds.)"""
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.55)
         self.proc.terminate()
         sm, smax, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "first", 0):]:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -165,7 +170,7 @@ def run_cuda(args):
         import ctypes as C
         ops = C.c_double(0)
         best = 0.0
-        for _ in range(4):
+        for _ in range(12):  # the first launches run before the clocks have ramped up; keep the best
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             _lib.check(fn(4096, C.c_void_p(sink.data_ptr()), C.byref(ops), _device.stream_ptr()), "peak")
@@ -204,13 +209,14 @@ def run_cuda(args):
         kernel_ms.append((e0, e1))
         return kld
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         kld_val = kde_step()
     kernel_ms.clear()
-    clocks = ClockSampler(local)
     barrier()
-    if rank == 0:
-        clocks.start()
+    clocks.mark()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
