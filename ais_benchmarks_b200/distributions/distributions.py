@@ -26,11 +26,36 @@ class CDistribution(metaclass=ABCMeta):
         self.type = params["type"]
         self.family = params["family"]
         self.dims = params["dims"]
-        self.likelihood_f = params["likelihood_f"]
-        self.loglikelihood_f = params["loglikelihood_f"]
+        # The reference stores the bound methods self.prob / self.log_prob on the instance and in `params`
+        # (distributions.py:98-99), which makes every distribution a reference cycle that only the cyclic GC can
+        # free. Here a distribution can own a 64 MB packed KDE in HBM, so the default callables are resolved lazily
+        # (same attribute names, same values) and the object dies with its last reference.
+        lik, loglik = params["likelihood_f"], params["loglikelihood_f"]
+        self._likelihood_f = None if getattr(lik, "__self__", None) is self else lik
+        self._loglikelihood_f = None if getattr(loglik, "__self__", None) is self else loglik
+        if self._likelihood_f is None:
+            params["likelihood_f"] = "self.prob"
+        if self._loglikelihood_f is None:
+            params["loglikelihood_f"] = "self.log_prob"
         self.support_vals = params["support"]
         self._loc = None
         self._scale = None
+
+    @property
+    def likelihood_f(self):
+        return self.prob if self._likelihood_f is None else self._likelihood_f
+
+    @likelihood_f.setter
+    def likelihood_f(self, f):
+        self._likelihood_f = f
+
+    @property
+    def loglikelihood_f(self):
+        return self.log_prob if self._loglikelihood_f is None else self._loglikelihood_f
+
+    @loglikelihood_f.setter
+    def loglikelihood_f(self, f):
+        self._loglikelihood_f = f
 
     @property
     def loc(self):

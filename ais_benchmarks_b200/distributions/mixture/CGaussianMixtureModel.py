@@ -35,8 +35,10 @@ class CGaussianMixtureModel(CDistribution):
         else:
             self.weights = (1.0 / len(self.means)) * np.array([1] * len(self.means))
 
+        # the reference hands the inner mixture the bound method self.support (CGaussianMixtureModel.py:38, never read);
+        # the support values are passed instead so that the object is not a reference cycle
         self.gmm = CMixtureModel({"models": self.models, "weights": self.weights,
-                                  "dims": self.dims, "support": self.support})
+                                  "dims": self.dims, "support": self.support_vals})
 
     def log_prob(self, samples):
         return self.gmm.log_prob(samples)

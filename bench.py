@@ -14,6 +14,7 @@ A "step" is one full evaluation of the metric on one batch: KDE build (pack) + q
 the ranks (total work fixed -> "scaling": "strong").
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -150,6 +151,10 @@ def run_cuda(args):
     lib = _lib.load()
     dev = torch.device("cuda", local)
     scale = args.scale
+    # nvidia-smi's start-up stalls CUDA API calls for tens of milliseconds: start it long before anything is timed
+    clocks = ClockSampler(local)
+    if rank == 0 and os.environ.get("AISB_NO_CLOCKS", "0") != "1":
+        clocks.start()
 
     def barrier():
         if world > 1:
@@ -162,24 +167,6 @@ def run_cuda(args):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
-
-    # ---- live FP32-FMA / MUFU.EX2 peaks on this GPU (roofline denominators for the compute-bound kernels) -------
-    sink = torch.zeros(4, dtype=torch.float32, device=dev)
-    peaks = {}
-    for name, fn in (("fma", lib.aisb_peak_fma_f32), ("ex2", lib.aisb_peak_ex2_f32)):
-        import ctypes as C
-        ops = C.c_double(0)
-        best = 0.0
-        for _ in range(12):  # the first launches run before the clocks have ramped up; keep the best
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            _lib.check(fn(4096, C.c_void_p(sink.data_ptr()), C.byref(ops), _device.stream_ptr()), "peak")
-            e1.record()
-            torch.cuda.synchronize()
-            best = max(best, ops.value / (e0.elapsed_time(e1) * 1e-3))
-        peaks[name] = best
-    fp32_peak_tflops = 2.0 * peaks["fma"] / 1e12
-    ex2_peak = peaks["ex2"]
 
     # ================================ KDE-KLD (headline) =====================================================
     c = KDE_CFG
@@ -209,12 +196,13 @@ def run_cuda(args):
         kernel_ms.append((e0, e1))
         return kld
 
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     for _ in range(args.warmup):
         kld_val = kde_step()
     kernel_ms.clear()
+    # a generation-2 garbage collection of the Python heap stalls the launching thread for 50-100 ms: collect now,
+    # keep the collector off inside the timed regions (what timeit does); nothing in a step creates reference cycles
+    gc.collect()
+    gc.disable()
     barrier()
     clocks.mark()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -232,10 +220,16 @@ def run_cuda(args):
         kde_step(resident=False)
     barrier()
     w0 = time.perf_counter()
+    e2e_marks = [w0]
     for _ in range(args.steps):
         kde_step(resident=False)
+        e2e_marks.append(time.perf_counter())
     barrier()
     kde_e2e_ms = max_over_ranks((time.perf_counter() - w0) * 1e3) / args.steps
+    if rank == 0:
+        print("[bench] e2e step walls (ms): %s; pairwise kernel inside e2e (ms): %s" % (
+            ["%.1f" % ((b - a) * 1e3) for a, b in zip(e2e_marks, e2e_marks[1:])],
+            ["%.1f" % a.elapsed_time(b) for a, b in kernel_ms[-args.steps:]]), file=sys.stderr)
     clock_info = clocks.stop() if rank == 0 else None
     kernel_ms.clear()
 
@@ -296,6 +290,26 @@ def run_cuda(args):
     dm_flops = float(n_local) * (N * (3 * D2 + 6) + dc["modes"] * (4 * D2 + 6))
     dm_tflops = dm_flops / (dm_kernel_ms * 1e-3) / 1e12
 
+    # ---- live FP32-FMA / MUFU.EX2 peaks on this GPU (roofline denominators for the compute-bound kernels), measured
+    # after the workloads so that the clocks have ramped up exactly as they had for the timed kernels ---------------
+    sink = torch.zeros(4, dtype=torch.float32, device=dev)
+    peaks = {}
+    for name, fn in (("fma", lib.aisb_peak_fma_f32), ("ex2", lib.aisb_peak_ex2_f32)):
+        import ctypes as C
+        ops = C.c_double(0)
+        best = 0.0
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(fn(16384, C.c_void_p(sink.data_ptr()), C.byref(ops), _device.stream_ptr()), "peak")
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, ops.value / (e0.elapsed_time(e1) * 1e-3))
+        peaks[name] = best
+    fp32_peak_tflops = 2.0 * peaks["fma"] / 1e12
+    ex2_peak = peaks["ex2"]
+
+    gc.enable()
     # ================================ CPU baseline (rank 0, N = 1 only) ======================================
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
