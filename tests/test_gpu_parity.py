@@ -515,3 +515,60 @@ def test_tpais_replay_on_device(case):
     assert len(x) == len(w) >= 80 and np.all(w > 0) and 0 < t.get_NESS() <= 1
     from ais_benchmarks_b200.metrics import CKLDivergence
     assert np.isfinite(CKLDivergence().compute(p=target, q=t, nsamples=2000))
+
+
+def test_full_size_config4_kde_kld_row_subset():
+    """BASELINE configs[3] at FULL size (1e6 KDE centres x 1e6 evaluation points, D = 8, 16-mode GMM target): the q
+    log-density of a random row subset against the oracle, the split/merge identity on the whole output, and the KLD
+    against the oracle's KLD formula applied to the device log-densities (the reduction itself)."""
+    import bench
+    from ais_benchmarks_b200 import _device
+    from ais_benchmarks_b200.metrics import CKLDivergence
+    from ais_benchmarks_b200.sampling_methods.base import CDeviceKDE
+    mu, sig, w, sup, centres, x = bench.kde_workload(scale=1.0)
+    target = gmm(mu, sig, w, sup)
+    cd, xd = torch.from_numpy(centres).cuda(), torch.from_numpy(x).cuda()
+    kde = CDeviceKDE(cd, None, len(centres), 0.02, 8, sup)
+    lq = kde.log_prob(xd)
+    lp = target.log_prob(xd)
+    rows = np.random.RandomState(0).choice(len(x), size=24, replace=False)
+    ref_q = O.iso_mixture_log_prob(x[rows].astype(np.float64), centres.astype(np.float64), 0.02, chunk=4)
+    assert rel_err(lq.cpu().numpy()[rows], ref_q) < LOGP_TOL
+    assert rel_err(lp.cpu().numpy()[rows], O.gmm_log_prob(x[rows].astype(np.float64), mu, sig, w)) < LOGP_TOL
+    h = len(centres) // 2
+    a = _device.mixture_logpdf(xd, _device.DeviceMixture.kde(cd[:h].contiguous(), None, h, 0.02))
+    b = _device.mixture_logpdf(xd, _device.DeviceMixture.kde(cd[h:].contiguous(), None, len(centres) - h, 0.02))
+    merged = (torch.logaddexp(a.double(), b.double()) + np.log(0.5)).cpu().numpy()
+    assert rel_err(lq.cpu().numpy(), merged) < 2e-6
+    val = CKLDivergence().compute_from_samples(target, kde, xd)
+    ref = O.kld_from_log_probs(lp.double().cpu().numpy(), lq.double().cpu().numpy())
+    assert abs(val - ref) <= 1e-6 * max(1.0, abs(ref))
+
+
+def test_full_size_config5_dm_weights_row_subset():
+    """BASELINE configs[4] at FULL size (1e7 samples x 1024 proposals, D = 32, 64-mode GMM target): log pi, log q and
+    log w of a random row subset against the oracle; normaliser / ESS partials against a float64 reduction of the
+    device log-weights; normalised weights sum to 1."""
+    import bench
+    from ais_benchmarks_b200 import _device
+    mu, sig, w, sup, pmeans, per = bench.dm_workload(scale=1.0)
+    target = gmm(mu, sig, w, sup)
+    pm_d = torch.from_numpy(pmeans).cuda().float().contiguous()
+    qmix = _device.DeviceMixture.kde(pm_d, None, len(pmeans), 0.05)
+    _device.seed(99)
+    xs = _device.sample_iso(pm_d, per, 0.05)
+    assert xs.shape == (len(pmeans) * per, 32) and xs.shape[0] > 9.9e6
+    logw, logp, logq, part = _device.dm_weights(xs, target.device_mixture(), None, qmix, want_logp=True, want_logq=True)
+    rows = np.random.RandomState(1).choice(xs.shape[0], size=256, replace=False)
+    xr = xs[rows].double().cpu().numpy()
+    pm32 = pm_d.double().cpu().numpy()
+    assert rel_err(logq[rows].cpu().numpy(), O.iso_mixture_log_prob(xr, pm32, 0.05)) < LOGP_TOL
+    assert rel_err(logp[rows].cpu().numpy(), O.gmm_log_prob(xr, mu, sig, w)) < LOGP_TOL
+    p = part.cpu().numpy()
+    lw = logw.double()
+    M = float(lw.max())
+    assert p[3] == xs.shape[0] and p[0] == pytest.approx(M, abs=1e-6)
+    assert p[1] == pytest.approx(float(torch.exp(lw - M).sum()), rel=1e-5)
+    assert p[2] == pytest.approx(float(torch.exp(2 * (lw - M)).sum()), rel=1e-5)
+    wn = _device.normalize_weights(logw, p)
+    assert float(wn.double().sum()) == pytest.approx(1.0, abs=1e-4)
