@@ -3,7 +3,7 @@
 #include "reduce.cuh"
 
 #ifndef AISB_MIN_CTAS_SMALL
-#define AISB_MIN_CTAS_SMALL 4  // resident CTAs per SM asked of the compiler for the DP <= 8 pairwise kernels
+#define AISB_MIN_CTAS_SMALL 5  // resident CTAs per SM asked of the compiler for the DP <= 8 pairwise kernels
 #endif
 
 namespace aisb {
@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(kThreads, (KIND != AISB_COV_FULL && DP <= 8) ?
                   float* __restrict__ ws_S) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[kStages];
+  __shared__ OuterAcc outer;
   constexpr int E = points_per_thread(DP);
 
   const int64_t tile = blockIdx.x % ntiles;
@@ -40,15 +41,10 @@ __global__ void __launch_bounds__(kThreads, (KIND != AISB_COV_FULL && DP <= 8) ?
   load_points<DP, E>(x, n, D, vec_ok, tile * (kThreads * E), xr, pidx);
 
   float m[E], S[E];
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    m[e] = kNegBig;
-    S[e] = 0.f;
-  }
   const int64_t k_begin = split * comps_per_split;
   const int64_t k_end = k_begin + comps_per_split < mix.KP ? k_begin + comps_per_split : mix.KP;
   uint32_t it = 0;
-  mixture_pass<KIND, DP, E, HAS_C>(mix.rows, mix.offs, k_begin, k_end, mix.a_iso, smem, bars, it, xr, m, S);
+  mixture_pass<KIND, DP, E, HAS_C>(mix.rows, mix.offs, k_begin, k_end, mix.a_iso, smem, bars, outer, it, xr, m, S);
 
   if (nsplit == 1) {
 #pragma unroll
@@ -87,6 +83,7 @@ __global__ void __launch_bounds__(kThreads)
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[kStages];
   __shared__ float red[kThreads / 32 * 4];
+  __shared__ OuterAcc outer;
   constexpr int E = points_per_thread(DP);
 
   ring_init(bars);
@@ -97,24 +94,14 @@ __global__ void __launch_bounds__(kThreads)
   float m[E], S[E], logp[E], logq[E];
   uint32_t it = 0;
   if (tgt.rows != nullptr) {
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      m[e] = kNegBig;
-      S[e] = 0.f;
-    }
-    mixture_pass<AISB_COV_DIAG, DP, E, true>(tgt.rows, tgt.offs, 0, tgt.KP, 0.f, smem, bars, it, xr, m, S);
+    mixture_pass<AISB_COV_DIAG, DP, E, true>(tgt.rows, tgt.offs, 0, tgt.KP, 0.f, smem, bars, outer, it, xr, m, S);
 #pragma unroll
     for (int e = 0; e < E; ++e) logp[e] = lse_finish(m[e], S[e]);
   } else {
 #pragma unroll
     for (int e = 0; e < E; ++e) logp[e] = pidx[e] < n ? __ldg(logp_in + pidx[e]) : 0.f;
   }
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    m[e] = kNegBig;
-    S[e] = 0.f;
-  }
-  mixture_pass<KIND_Q, DP, E, HAS_C_Q>(prop.rows, prop.offs, 0, prop.KP, prop.a_iso, smem, bars, it, xr, m, S);
+  mixture_pass<KIND_Q, DP, E, HAS_C_Q>(prop.rows, prop.offs, 0, prop.KP, prop.a_iso, smem, bars, outer, it, xr, m, S);
 
   float lw[E];
   bool ok[E];

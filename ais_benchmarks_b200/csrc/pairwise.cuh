@@ -314,88 +314,6 @@ __device__ __forceinline__ void accumulate_chunk2(const float* __restrict__ srow
 }
 
 // ---------------------------------------------------------------------------------------------
-// Lazy-reference variant for mixtures WITHOUT per-component offsets (KDE, equal-weight proposals).
-// The FFMA2 chain of every pair is seeded with -mref (the point's current reference exponent), so it ends
-// directly in t' = t - mref and the common case needs no subtraction and no rescale: S += ex2(t').
-// mref is only moved when a group maximum exceeds it by more than kLazyThresh (or at the first group): the
-// rare slow path shifts mref, rescales S and patches the two groups that are in flight. mref trails the true
-// running maximum by at most kLazyThresh, so terms stay below 2^kLazyThresh and nothing that matters underflows.
-// Saves one FADD2 per pair and the per-group MUFU / FMUL2 of the eager scheme.
-// ---------------------------------------------------------------------------------------------
-constexpr float kLazyThresh = 16.f;
-
-template <int EP, int JJ>
-__device__ __forceinline__ void lse_update2_lazy(float2 (&t)[JJ][EP], float2 (&other)[JJ][EP], float2 (&mref)[EP],
-                                                 float2 (&S)[EP], int& phase) {
-  // phase 0: nothing pending yet (pipeline prologue, `t` is not a real group); 1: `t` is the first real group;
-  // 2: steady state. The phase is uniform across the CTA.
-  if (phase == 0) {
-    phase = 1;
-    return;
-  }
-  const bool fresh = phase == 1;
-  float2 g[EP];
-  bool trig = fresh;
-#pragma unroll
-  for (int pp = 0; pp < EP; ++pp) {
-    float g0 = t[0][pp].x, g1 = t[0][pp].y;
-#pragma unroll
-    for (int jj = 1; jj < JJ; ++jj) {
-      g0 = fmaxf(g0, t[jj][pp].x);
-      g1 = fmaxf(g1, t[jj][pp].y);
-    }
-    g[pp] = make_float2(g0, g1);
-    trig = trig || (g0 > kLazyThresh) || (g1 > kLazyThresh);
-  }
-  if (trig) {
-#pragma unroll
-    for (int pp = 0; pp < EP; ++pp) {
-      // first group: reference exactly on its maximum (may move down); later: only move up. Non-finite maxima
-      // (NaN input, -inf from overflowed coordinates) leave the reference where it is.
-      float d0 = (fresh || g[pp].x > kLazyThresh) ? g[pp].x : 0.f;
-      float d1 = (fresh || g[pp].y > kLazyThresh) ? g[pp].y : 0.f;
-      d0 = (d0 > -1.0e30f && d0 < 1.0e30f) ? d0 : 0.f;
-      d1 = (d1 > -1.0e30f && d1 < 1.0e30f) ? d1 : 0.f;
-      const float2 nd = make_float2(-d0, -d1);
-      mref[pp] = make_float2(mref[pp].x + d0, mref[pp].y + d1);
-      // d < 0 only happens at the first group, where S is still 0: clamp so that 0 * 2^(+big) cannot make a NaN
-      S[pp] = __fmul2_rn(S[pp], make_float2(ex2(fminf(-d0, 0.f)), ex2(fminf(-d1, 0.f))));
-#pragma unroll
-      for (int jj = 0; jj < JJ; ++jj) {
-        t[jj][pp] = __fadd2_rn(t[jj][pp], nd);
-        other[jj][pp] = __fadd2_rn(other[jj][pp], nd);
-      }
-    }
-    phase = 2;
-  }
-#pragma unroll
-  for (int pp = 0; pp < EP; ++pp) {
-    float2 acc = S[pp];
-#pragma unroll
-    for (int jj = 0; jj < JJ; ++jj) acc = __fadd2_rn(acc, make_float2(ex2(t[jj][pp].x), ex2(t[jj][pp].y)));
-    S[pp] = acc;
-  }
-}
-
-template <int KIND, int DP, int EP, int JJ>
-__device__ __forceinline__ void accumulate_chunk2_lazy(const float* __restrict__ srows, int cnt, float a_iso,
-                                                       const float2 (&x2)[EP][DP], float2 (&tP)[JJ][EP],
-                                                       float2 (&mref)[EP], float2 (&S)[EP], int& phase) {
-#pragma unroll 1
-  for (int j0 = 0; j0 < cnt; j0 += 2 * JJ) {
-    float2 tQ[JJ][EP], seed[EP];
-#pragma unroll
-    for (int pp = 0; pp < EP; ++pp) seed[pp] = neg2(mref[pp]);
-    eval_group2<KIND, DP, EP, JJ, false>(srows, nullptr, j0, a_iso, x2, seed, tQ);
-    lse_update2_lazy<EP, JJ>(tP, tQ, mref, S, phase);
-#pragma unroll
-    for (int pp = 0; pp < EP; ++pp) seed[pp] = neg2(mref[pp]);
-    eval_group2<KIND, DP, EP, JJ, false>(srows, nullptr, j0 + JJ, a_iso, x2, seed, tP);
-    lse_update2_lazy<EP, JJ>(tQ, tP, mref, S, phase);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Stream components [k_begin, k_end) of a packed mixture through the smem ring, calling
 // fn(srows, soffs, cnt, k0) on every staged chunk (cnt components starting at global index k0).
 // `it` counts chunks consumed so far by this CTA (carries the mbarrier phase across passes).
@@ -445,17 +363,76 @@ __device__ __forceinline__ void stream_components(const float* __restrict__ g_ro
   it = it0 + nchunks;
 }
 
-// Fold components [k_begin, k_end) into the running (m, S) of the E register-resident points.
+// ---------------------------------------------------------------------------------------------
+// Two-level summation. A float32 running sum over 1e6 comparable terms carries a random-walk error of
+// ~sqrt(1e6) * 2^-24 = 6e-5 (seen as 2e-5 on log-densities in dense regions at 1e6 centres). The per-thread sum S
+// therefore only ever spans a few staged chunks (~1024 components); it is then merged, with the
+// log-sum-exp rescale rule, into a float64 accumulator that lives in shared memory (one slot per thread and point,
+// touched once per chunk, no registers) and is reset. Cost: two MUFU and a DFMA per point per chunk.
+// ---------------------------------------------------------------------------------------------
+struct OuterAcc {
+  float M[4][kThreads];   // reference exponent of the outer sum (log2 domain)
+  double S[4][kThreads];  // outer sum, relative to M
+};
+
+template <int E>
+__device__ __forceinline__ void outer_init(OuterAcc& o) {
+  static_assert(E <= 4, "OuterAcc holds at most 4 points per thread");
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    o.M[e][threadIdx.x] = kNegBig;
+    o.S[e][threadIdx.x] = 0.0;
+  }
+}
+
+// merge the inner (m_e, S_e) into the outer accumulator and restart the inner sum (its reference m_e is kept)
+template <int E>
+__device__ __forceinline__ void outer_fold(OuterAcc& o, const float (&m)[E], float (&S)[E]) {
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    if (S[e] != 0.f) {  // an empty inner sum must not move the outer reference (its own reference is not meaningful yet)
+      const float Mo = o.M[e][threadIdx.x];
+      const float Mn = fmaxf(Mo, m[e]);
+      o.S[e][threadIdx.x] = o.S[e][threadIdx.x] * static_cast<double>(ex2(Mo - Mn)) +
+                            static_cast<double>(S[e]) * static_cast<double>(ex2(m[e] - Mn));
+      o.M[e][threadIdx.x] = Mn;
+      S[e] = 0.f;
+    }
+  }
+}
+
+template <int E>
+__device__ __forceinline__ void outer_finish(const OuterAcc& o, float (&m)[E], float (&S)[E]) {
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    m[e] = o.M[e][threadIdx.x];
+    S[e] = static_cast<float>(o.S[e][threadIdx.x]);
+  }
+}
+
+// Fold components [k_begin, k_end) into (m, S) of the E register-resident points (results replace m, S).
 template <int KIND, int DP, int E, bool HAS_C>
 __device__ __forceinline__ void mixture_pass(const float* __restrict__ g_rows, const float* __restrict__ g_offs,
                                              int64_t k_begin, int64_t k_end, float a_iso, float* smem, uint64_t* bars,
-                                             uint32_t& it, const float (&x)[E][DP], float (&m)[E], float (&S)[E]) {
+                                             OuterAcc& outer, uint32_t& it, const float (&x)[E][DP], float (&m)[E],
+                                             float (&S)[E]) {
   constexpr int JJ = comps_per_step(KIND, DP);
+  // the inner float32 sum spans at most kFoldEvery chunks (~1024 components: random-walk error sqrt(1024) 2^-24 = 2e-6)
+  constexpr int kFoldEvery = chunk_comps(KIND, DP) >= 256 ? 4 : (chunk_comps(KIND, DP) >= 64 ? 16 : 32);
+  int nchunk = 0;
+  outer_init<E>(outer);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    m[e] = kNegBig;
+    S[e] = 0.f;
+  }
   if constexpr (KIND == AISB_COV_FULL) {
     stream_components<KIND, DP, HAS_C>(g_rows, g_offs, k_begin, k_end, smem, bars, it,
                                        [&](const float* srows, const float* soffs, int cnt, int64_t) {
                                          accumulate_chunk<KIND, DP, E, JJ, HAS_C>(srows, soffs, cnt, a_iso, x, m, S);
+                                         if ((++nchunk % kFoldEvery) == 0) outer_fold<E>(outer, m, S);
                                        });
+    outer_fold<E>(outer, m, S);
   } else {
     static_assert(E % 2 == 0, "packed path needs an even number of points per thread");
     constexpr int EP = E / 2;
@@ -469,44 +446,32 @@ __device__ __forceinline__ void mixture_pass(const float* __restrict__ g_rows, c
     for (int jj = 0; jj < JJ; ++jj)
 #pragma unroll
       for (int pp = 0; pp < EP; ++pp) tP[jj][pp] = make_float2(-INFINITY, -INFINITY);
-    if constexpr (HAS_C) {
+    auto fold = [&]() {
 #pragma unroll
       for (int pp = 0; pp < EP; ++pp) {
-        m2[pp] = make_float2(m[2 * pp], m[2 * pp + 1]);
-        S2[pp] = make_float2(S[2 * pp], S[2 * pp + 1]);
+        m[2 * pp] = m2[pp].x;
+        m[2 * pp + 1] = m2[pp].y;
+        S[2 * pp] = S2[pp].x;
+        S[2 * pp + 1] = S2[pp].y;
       }
-      stream_components<KIND, DP, HAS_C>(
-          g_rows, g_offs, k_begin, k_end, smem, bars, it, [&](const float* srows, const float* soffs, int cnt, int64_t) {
-            accumulate_chunk2<KIND, DP, EP, JJ, HAS_C>(srows, soffs, cnt, a_iso, x2, tP, m2, S2);
-          });
-      lse_update2<EP, JJ>(tP, m2, S2);
-    } else {
-      // lazy-reference scheme; the pass starts from scratch (callers enter with m = kNegBig, S = 0)
-      int phase = 0;
-      float2 tDummy[JJ][EP];
+      outer_fold<E>(outer, m, S);
 #pragma unroll
-      for (int pp = 0; pp < EP; ++pp) {
-        m2[pp] = make_float2(0.f, 0.f);
-        S2[pp] = make_float2(0.f, 0.f);
-      }
-      stream_components<KIND, DP, HAS_C>(
-          g_rows, g_offs, k_begin, k_end, smem, bars, it, [&](const float* srows, const float*, int cnt, int64_t) {
-            accumulate_chunk2_lazy<KIND, DP, EP, JJ>(srows, cnt, a_iso, x2, tP, m2, S2, phase);
-          });
-#pragma unroll
-      for (int jj = 0; jj < JJ; ++jj)
-#pragma unroll
-        for (int pp = 0; pp < EP; ++pp) tDummy[jj][pp] = make_float2(-INFINITY, -INFINITY);
-      if (phase != 0) lse_update2_lazy<EP, JJ>(tP, tDummy, m2, S2, phase);
-    }
+      for (int pp = 0; pp < EP; ++pp) S2[pp] = make_float2(0.f, 0.f);
+    };
 #pragma unroll
     for (int pp = 0; pp < EP; ++pp) {
-      m[2 * pp] = m2[pp].x;
-      m[2 * pp + 1] = m2[pp].y;
-      S[2 * pp] = S2[pp].x;
-      S[2 * pp + 1] = S2[pp].y;
+      m2[pp] = make_float2(kNegBig, kNegBig);
+      S2[pp] = make_float2(0.f, 0.f);
     }
+    stream_components<KIND, DP, HAS_C>(
+        g_rows, g_offs, k_begin, k_end, smem, bars, it, [&](const float* srows, const float* soffs, int cnt, int64_t) {
+          accumulate_chunk2<KIND, DP, EP, JJ, HAS_C>(srows, soffs, cnt, a_iso, x2, tP, m2, S2);
+          if ((++nchunk % kFoldEvery) == 0) fold();
+        });
+    lse_update2<EP, JJ>(tP, m2, S2);
+    fold();
   }
+  outer_finish<E>(outer, m, S);
 }
 
 // ---------------------------------------------------------------------------------------------

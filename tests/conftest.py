@@ -35,4 +35,7 @@ def rel_err(got, ref):
     assert np.array_equal(np.isneginf(got[~fin]), np.isneginf(ref[~fin])), "non-finite entries differ"
     if not fin.any():
         return 0.0
-    return float(np.max(np.abs(got[fin] - ref[fin]) / np.maximum(1.0, np.abs(ref[fin]))))
+    err = np.abs(got[fin] - ref[fin]) / np.maximum(1.0, np.abs(ref[fin]))
+    worst = int(np.argmax(err))
+    rel_err.last = "worst entry %d of %d: got %.9g ref %.9g" % (worst, err.size, got[fin][worst], ref[fin][worst])
+    return float(err[worst])
