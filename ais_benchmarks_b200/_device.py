@@ -180,9 +180,47 @@ def mixture_logpdf(x, mix, out=None):
     return out
 
 
-def dm_weights(x, target, logp_in, proposals, want_logp=False, want_logq=False):
-    """Fused DM weights (C ABI: aisb_dm_weights_f32). Returns (logw, logp|None, logq|None, partials[4] device f64)."""
+class TensorCoreOperand:
+    """Pre-arranged B operand of the tcgen05 cross-term path for an ISO_SHARED mixture without offsets."""
+
+    def __init__(self, mix):
+        lib = require_cuda()
+        nfl = lib.aisb_tc_image_floats(mix.K, mix.D)
+        if nfl == 0 or mix.kind != COV_ISO_SHARED or mix.offsets is not None:
+            raise AisbError("tensor-core path needs an ISO_SHARED mixture without offsets and 5 <= D <= 32")
+        self.mix = mix
+        self.image = torch.empty(nfl, dtype=torch.float32, device=mix.rows.device)
+        check(lib.aisb_tc_pack_f32(mix.ref(), _ptr(self.image), stream_ptr()), "aisb_tc_pack_f32")
+
+
+def tc_logq(x, operand, hint, out=None):
+    """log q(x) of operand.mix through the tensor-core path (C ABI: aisb_tc_logq_f32). hint: int32 CUDA [n], index of
+    the component expected to dominate each point (DM-AIS: the proposal the sample was drawn from)."""
     lib = require_cuda()
+    n = x.shape[0]
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=x.device)
+    err = torch.zeros(1, dtype=torch.int32, device=x.device)
+    check(lib.aisb_tc_logq_f32(_ptr(x), n, operand.mix.ref(), _ptr(hint), _ptr(operand.image), _ptr(out), _ptr(err),
+                               stream_ptr()), "aisb_tc_logq_f32")
+    if int(err.item()) != 0:
+        raise AisbError("tensor-core kernel aborted (%d CTAs): barrier protocol time-out" % int(err.item()))
+    return out
+
+
+def tc_eligible(mix):
+    """Tensor-core proposal path: equal-weight isotropic mixtures in 9..32 dimensions (below that the cross term is
+    not a real contraction and the CUDA-core kernel wins)."""
+    return mix.kind == COV_ISO_SHARED and mix.offsets is None and 9 <= mix.D <= 32
+
+
+def dm_weights(x, target, logp_in, proposals, want_logp=False, want_logq=False, hint=None):
+    """DM weights. Without `hint`: the fused CUDA-core kernel (C ABI aisb_dm_weights_f32). With `hint` (int32 CUDA [n],
+    the proposal each sample was drawn from) and an eligible proposal mixture: proposal density on the tensor cores
+    (aisb_dm_weights_hinted_f32). Returns (logw, logp|None, logq|None, partials[4] device f64)."""
+    lib = require_cuda()
+    if hint is not None and tc_eligible(proposals) and x.shape[0] > 0:
+        return _dm_weights_hinted(lib, x, target, logp_in, proposals, want_logp, want_logq, hint)
     n = x.shape[0]
     dev = x.device
     logw = torch.empty(n, dtype=torch.float32, device=dev)
@@ -195,6 +233,31 @@ def dm_weights(x, target, logp_in, proposals, want_logp=False, want_logq=False):
                                   proposals.ref(), _ptr(logw), _ptr(logp), _ptr(logq), _ptr(partials), _ptr(ws),
                                   ws.numel(), stream_ptr()), "aisb_dm_weights_f32")
     return logw, logp, logq, partials
+
+
+def _dm_weights_hinted(lib, x, target, logp_in, proposals, want_logp, want_logq, hint):
+    n, dev = x.shape[0], x.device
+    if getattr(proposals, "_tc_operand", None) is None:
+        proposals._tc_operand = TensorCoreOperand(proposals)
+    logw = torch.empty(n, dtype=torch.float32, device=dev)
+    logp = torch.empty(n, dtype=torch.float32, device=dev) if want_logp else None
+    logq = torch.empty(n, dtype=torch.float32, device=dev) if want_logq else None
+    partials = torch.empty(4, dtype=torch.float64, device=dev)
+    Kmax = max(proposals.K, target.K if target is not None else 1)
+    ws = workspace_for(n, Kmax, proposals.D)
+    hint = hint.to(device=dev, dtype=torch.int32).contiguous()
+    check(lib.aisb_dm_weights_hinted_f32(_ptr(x), n, target.ref() if target is not None else None, _ptr(logp_in),
+                                         proposals.ref(), _ptr(proposals._tc_operand.image), _ptr(hint), _ptr(logw),
+                                         _ptr(logp), _ptr(logq), _ptr(partials), _ptr(ws), ws.numel(), stream_ptr()),
+          "aisb_dm_weights_hinted_f32")
+    return logw, logp, logq, partials
+
+
+def check_partials(p):
+    """Raise if a tensor-core kernel reported an abort through the partial record (n_valid = -1)."""
+    if p[3] < 0:
+        raise AisbError("tensor-core kernel aborted: barrier protocol time-out")
+    return p
 
 
 def logw_partials(logw):

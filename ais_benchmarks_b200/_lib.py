@@ -57,6 +57,10 @@ PROTOTYPES = {
     "aisb_box_mixture_logpdf_f32": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "aisb_sample_iso_f32": (C.c_int, [_vp, _i64, _i32, _i64, _dbl, _u64, _u64, _vp, _vp]),
     "aisb_uniform_box_f32": (C.c_int, [_vp, _vp, _i32, _i64, _u64, _u64, _vp, _vp]),
+    "aisb_tc_image_floats": (_i64, [_i64, _i32]),
+    "aisb_tc_pack_f32": (C.c_int, [_pm, _vp, _vp]),
+    "aisb_tc_logq_f32": (C.c_int, [_vp, _i64, _pm, _vp, _vp, _vp, _vp, _vp]),
+    "aisb_dm_weights_hinted_f32": (C.c_int, [_vp, _i64, _pm, _vp, _pm, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "aisb_peak_fma_f32": (C.c_int, [_i64, _vp, C.POINTER(_dbl), _vp]),
     "aisb_peak_ex2_f32": (C.c_int, [_i64, _vp, C.POINTER(_dbl), _vp]),
 }

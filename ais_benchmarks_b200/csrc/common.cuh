@@ -32,6 +32,10 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int sm_count();  // cached multiprocessor count of the current device
 
+// tensor-core log q launcher (tc.cu); *d_err is incremented by CTAs that aborted on a barrier time-out
+int tc_logq_launch(const float* d_x, int64_t n, const aisb_packed_mixture* mix, const int32_t* d_hint,
+                   const float* d_image, float* d_out, int32_t* d_err, cudaStream_t st);
+
 // ---------------------------------------------------------------------------------------------
 // PTX helpers
 // ---------------------------------------------------------------------------------------------

@@ -140,6 +140,11 @@ __global__ void __launch_bounds__(256) logw_combine_kernel(const float* __restri
   block_weight_partials<E, 256>(lw, ok, red, block_partials + 4 * static_cast<int64_t>(blockIdx.x));
 }
 
+// a tensor-core kernel that aborted (barrier time-out) poisons the partial record: n_valid = -1
+__global__ void tc_abort_to_partials_kernel(const int32_t* __restrict__ err, double* __restrict__ partials) {
+  if (*err != 0) partials[3] = -1.0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // KDE pack: rows[j][2d] = rows[j][2d+1] = -a * samples[idx[j]][d], pad dims 0, pad components 1e18
 // ---------------------------------------------------------------------------------------------
@@ -488,6 +493,67 @@ extern "C" int aisb_dm_weights_f32(const float* d_x, int64_t n, const aisb_packe
   }
   weight_partials_merge_kernel<<<1, 256, 0, st>>>(ws.block_partials, nblocks, d_out_partials);
   AISB_LAUNCH_CHECK("weight_partials_merge_kernel");
+  return AISB_OK;
+}
+
+// DM weights with the proposal density on the tensor cores (hinted screen + exact refinement, tc.cu): target density
+// on the CUDA cores, log q from tc_logq_launch, then the same combine / partial-sum kernels as the unfused path.
+extern "C" int aisb_dm_weights_hinted_f32(const float* d_x, int64_t n, const aisb_packed_mixture* target,
+                                          const float* d_logp_in, const aisb_packed_mixture* proposals,
+                                          const float* d_tc_image, const int32_t* d_hint, float* d_out_logw,
+                                          float* d_out_logp, float* d_out_logq, double* d_out_partials,
+                                          void* d_workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = check_mixture(proposals, "dm_weights_hinted(proposals)");
+  if (rc) return rc;
+  if (target) {
+    rc = check_mixture(target, "dm_weights_hinted(target)");
+    if (rc) return rc;
+    if (target->D != proposals->D) {
+      set_error("dm_weights_hinted: target D=%d != proposal D=%d", target->D, proposals->D);
+      return AISB_ERR_INVALID;
+    }
+  } else if (!d_logp_in) {
+    set_error("dm_weights_hinted: need a target mixture or d_logp_in");
+    return AISB_ERR_INVALID;
+  }
+  if (!d_out_partials || !d_tc_image || !d_hint || n < 1 || !d_x || !d_out_logw) {
+    set_error("dm_weights_hinted: null pointer or n < 1");
+    return AISB_ERR_INVALID;
+  }
+  Plan plan_q, plan_t;
+  if (!make_plan(n, proposals->K, proposals->D, &plan_q)) {
+    set_error("dm_weights_hinted: unsupported D=%d", proposals->D);
+    return AISB_ERR_UNSUPPORTED;
+  }
+  plan_t = plan_q;
+  if (target) make_plan(n, target->K, target->D, &plan_t);
+  Workspace ws{};
+  rc = carve_checked(d_workspace, workspace_bytes, n, plan_q.nsplit >= plan_t.nsplit ? plan_q : plan_t, &ws,
+                     "dm_weights_hinted");
+  if (rc) return rc;
+  const float* lp = d_logp_in;
+  if (target) {
+    float* lp_out = d_out_logp ? d_out_logp : ws.tmp_p;
+    rc = run_logpdf(d_x, n, target, lp_out, plan_t, ws, st);
+    if (rc) return rc;
+    lp = lp_out;
+  } else if (d_out_logp) {
+    AISB_CUDA_CHECK(cudaMemcpyAsync(d_out_logp, d_logp_in, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  }
+  float* lq = d_out_logq ? d_out_logq : ws.tmp_q;
+  const int64_t nblocks = reduce_blocks(n);
+  // the abort counter lives behind the block records (carve() reserves nblocks + 1 records)
+  int32_t* d_err = reinterpret_cast<int32_t*>(ws.block_partials + 8 * nblocks);
+  AISB_CUDA_CHECK(cudaMemsetAsync(d_err, 0, sizeof(int32_t), st));
+  rc = tc_logq_launch(d_x, n, proposals, d_hint, d_tc_image, lq, d_err, st);
+  if (rc) return rc;
+  logw_combine_kernel<<<static_cast<unsigned>(nblocks), 256, 0, st>>>(lp, lq, n, d_out_logw, ws.block_partials);
+  AISB_LAUNCH_CHECK("logw_combine_kernel");
+  weight_partials_merge_kernel<<<1, 256, 0, st>>>(ws.block_partials, nblocks, d_out_partials);
+  AISB_LAUNCH_CHECK("weight_partials_merge_kernel");
+  tc_abort_to_partials_kernel<<<1, 1, 0, st>>>(d_err, d_out_partials);
+  AISB_LAUNCH_CHECK("tc_abort_to_partials_kernel");
   return AISB_OK;
 }
 

@@ -111,12 +111,20 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
         return x if self.device_outputs else x.cpu().numpy().astype(np.float64)
 
     # -- the adapt loop ----------------------------------------------------------------------------
-    def weigh(self, new_samples, target_d):
-        """log w = log pi(x) - log q(x) for a batch + its normaliser/ESS partials (dm_ais.py:72-76)."""
+    def weigh(self, new_samples, target_d, hint=None):
+        """log w = log pi(x) - log q(x) for a batch + its normaliser/ESS partials (dm_ais.py:72-76).
+        hint: int32 CUDA [n], the proposal each sample was drawn from; in 9..32 dimensions it routes the proposal
+        density through the tensor-core kernel (same values, see csrc/tc.cu)."""
         target = target_device_mixture(target_d)
         logp_in = None if target is not None else foreign_target_logp(target_d, new_samples)
-        logw, _, _, partials = _device.dm_weights(new_samples, target, logp_in, self.proposal_mixture())
+        logw, _, _, partials = _device.dm_weights(new_samples, target, logp_in, self.proposal_mixture(), hint=hint)
         return logw, partials
+
+    def _own_proposal(self):
+        """Proposal index of every row of a proposal-major batch of N*K draws."""
+        if getattr(self, "_hint", None) is None or self._hint.shape[0] != self.N * self.K:
+            self._hint = (torch.arange(self.N * self.K, device=_device.device()) // int(self.K)).to(torch.int32)
+        return self._hint
 
     def resample(self, samples, logw):
         """DM-PMC update (dm_ais.py:47-56): each proposal mean <- a sample drawn ~ batch-normalised weights."""
@@ -130,7 +138,7 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
             # K samples from each proposal, proposal-major like dm_ais.py:64-69
             new_samples = _device.sample_iso(self.proposal_means(), int(self.K), float(self.sigma))
             self._num_q_samples += self.N * self.K
-            new_logw, _ = self.weigh(new_samples, target_d)
+            new_logw, _ = self.weigh(new_samples, target_d, hint=self._own_proposal())
             self._num_pi_evals += self.N * self.K
             self.resample(new_samples, new_logw)
             self._append(new_samples, new_logw)

@@ -57,7 +57,7 @@ class CLayeredAIS(CDeterministicMixtureAIS):
         while n_samples > self._n() and elapsed_time < timeout:
             new_samples = _device.sample_iso(self.proposal_means(), int(self.K), float(self.sigma))
             self._num_q_samples += self.N * self.K
-            new_logw, _ = self.weigh(new_samples, target_d)
+            new_logw, _ = self.weigh(new_samples, target_d, hint=self._own_proposal())
             self._num_pi_evals += self.N * self.K
             self.resample(target_d)
             self._append(new_samples, new_logw)

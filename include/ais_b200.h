@@ -241,6 +241,37 @@ int aisb_sample_iso_f32(const float* d_means, int64_t K, int32_t D, int64_t per,
 int aisb_uniform_box_f32(const float* d_lo, const float* d_hi, int32_t D, int64_t n, uint64_t seed, uint64_t offset,
                          float* d_out, void* stream);
 
+/*
+ * Tensor-core (tcgen05 / TMEM) cross-term path for ISO_SHARED mixtures WITHOUT offsets (equal-weight proposals, KDE),
+ * 5 <= D <= 32:  log q(x_i) via  -||u_i||^2 + LSE_j( 2 u_i . v_j - ||v_j||^2 )  with the bracket computed as a TF32
+ * GEMM on the 5th-generation tensor cores (BASELINE.json configs[4], "tensor-core cross-term path").
+ * The tensor-core value (absolute error up to ~0.3 in the exponent) is only a SCREEN: every pair that comes within
+ * 2^-30 of the point's reference term is re-evaluated exactly with the centred FP32 form, so the result meets the same
+ * 1e-5 bar as aisb_mixture_logpdf_f32. The reference term comes from d_hint[i] = index of a
+ * component expected to dominate log q(x_i) (DM-AIS: the proposal x_i was drawn from); a poor hint costs time (more exact
+ * re-evaluations) or, if it is more than ~2^100 below the true maximum, accuracy -- callers without a natural hint use
+ * aisb_mixture_logpdf_f32.
+ *   aisb_tc_image_floats: floats needed for the pre-arranged B operand ("image") of a K-component, D-dim mixture.
+ *   aisb_tc_pack_f32:     build the image from the packed ISO_SHARED rows (once per parameter update).
+ *   aisb_tc_logq_f32:     d_out_logq[n]; d_hint[n] int32; *d_err (int32, zeroed by the caller) is incremented if the
+ *                         kernel aborted on a barrier time-out.
+ */
+int64_t aisb_tc_image_floats(int64_t K, int32_t D);
+int aisb_tc_pack_f32(const aisb_packed_mixture* mix, float* d_image, void* stream);
+int aisb_tc_logq_f32(const float* d_x, int64_t n, const aisb_packed_mixture* mix, const int32_t* d_hint,
+                     const float* d_image, float* d_out_logq, int32_t* d_err, void* stream);
+
+/*
+ * aisb_dm_weights_f32 with the proposal density on the tensor cores (for DM-AIS / LAIS at 9 <= D <= 32, where every
+ * sample has a natural hint: the proposal it was drawn from, dm_ais.py:64-69). Same outputs as aisb_dm_weights_f32;
+ * d_tc_image from aisb_tc_pack_f32 for `proposals`, d_hint[n] int32. If the tensor-core kernel aborted,
+ * d_out_partials[3] (n_valid) is set to -1.
+ */
+int aisb_dm_weights_hinted_f32(const float* d_x, int64_t n, const aisb_packed_mixture* target, const float* d_logp_in,
+                               const aisb_packed_mixture* proposals, const float* d_tc_image, const int32_t* d_hint,
+                               float* d_out_logw, float* d_out_logp, float* d_out_logq, double* d_out_partials,
+                               void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Micro-benchmarks used to measure the FP32-FMA and MUFU.EX2 peaks on the box (bench.py roofline denominators).
  * Each runs `iters` dependent-chain iterations in every thread of a full-chip grid; *ops = FMAs (packed FFMA2 chains,
  * 2 flop each) resp. EX2 evaluations executed. */

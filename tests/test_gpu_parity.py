@@ -572,3 +572,56 @@ def test_full_size_config5_dm_weights_row_subset():
     assert p[2] == pytest.approx(float(torch.exp(2 * (lw - M)).sum()), rel=1e-5)
     wn = _device.normalize_weights(logw, p)
     assert float(wn.double().sum()) == pytest.approx(1.0, abs=1e-4)
+
+
+@pytest.mark.parametrize("D,N,per", [(32, 1024, 40), (16, 300, 50), (12, 129, 77), (9, 64, 33), (32, 100, 3)])
+def test_tensor_core_proposal_density(D, N, per):
+    """tcgen05 screen + exact refinement (csrc/tc.cu) against the oracle on DM-AIS-shaped data (every sample hinted
+    with the proposal it was drawn from), against the CUDA-core kernel (must agree to float32 rounding), and with
+    deliberately wrong hints (accuracy must hold; only speed may suffer)."""
+    from ais_benchmarks_b200 import _device
+    rs = np.random.RandomState(D + N)
+    pm = rs.uniform(-1, 1, size=(N, D))
+    pm_d = torch.from_numpy(pm).cuda().float().contiguous()
+    mix = _device.DeviceMixture.kde(pm_d, None, N, 0.05)
+    assert _device.tc_eligible(mix)
+    _device.seed(D)
+    xs = _device.sample_iso(pm_d, per, 0.05)
+    hint = (torch.arange(xs.shape[0], device="cuda") // per).to(torch.int32)
+    op = _device.TensorCoreOperand(mix)
+    got = _device.tc_logq(xs, op, hint)
+    ref32 = _device.mixture_logpdf(xs, mix)
+    ref64 = O.iso_mixture_log_prob(xs.double().cpu().numpy(), pm_d.double().cpu().numpy(), 0.05)
+    assert rel_err(got.cpu().numpy(), ref64) < LOGP_TOL, rel_err.last
+    assert rel_err(got.cpu().numpy(), ref32.double().cpu().numpy()) < 2e-6, rel_err.last
+    bad = torch.from_numpy(rs.randint(0, N, size=xs.shape[0]).astype(np.int32)).cuda()
+    got_bad = _device.tc_logq(xs, op, bad)
+    assert rel_err(got_bad.cpu().numpy(), ref64) < LOGP_TOL, rel_err.last
+    # points that belong to no proposal in particular (uniform on the support), arbitrary hints
+    xu = torch.from_numpy(rs.uniform(-1, 1, size=(257, D)).astype(np.float32)).cuda()
+    hu = torch.zeros(257, dtype=torch.int32, device="cuda")
+    refu = O.iso_mixture_log_prob(xu.double().cpu().numpy(), pm_d.double().cpu().numpy(), 0.05)
+    assert rel_err(_device.tc_logq(xu, op, hu).cpu().numpy(), refu) < LOGP_TOL, rel_err.last
+
+
+def test_dm_weights_hinted_equals_unhinted():
+    """aisb_dm_weights_hinted_f32 (tensor-core proposals) vs aisb_dm_weights_f32 (fused CUDA-core kernel): same
+    log-weights and partial sums on a 16-D DM-AIS batch; and the sampler routes through it end to end."""
+    from ais_benchmarks_b200 import _device
+    from ais_benchmarks_b200.sampling_methods import CDeterministicMixtureAIS
+    rs = np.random.RandomState(3)
+    D, N, K = 16, 96, 40
+    means = rs.uniform(-0.7, 0.7, size=(5, D)); sig = rs.uniform(0.04, 0.05, size=(5, D)); w = rs.uniform(size=5)
+    target = gmm(means, sig, w, [np.full(D, -1.0), np.full(D, 1.0)])
+    np.random.seed(4)
+    _device.seed(4)
+    s = CDeterministicMixtureAIS({"space_min": np.full(D, -1.0), "space_max": np.full(D, 1.0), "dims": D, "K": K, "N": N,
+                                  "J": 10, "sigma": 0.05})
+    xs = _device.sample_iso(s.proposal_means(), K, 0.05)
+    lw_a, pa = s.weigh(xs, target)
+    lw_b, pb = s.weigh(xs, target, hint=s._own_proposal())
+    assert rel_err(lw_b.cpu().numpy(), lw_a.double().cpu().numpy()) < 5e-6, rel_err.last
+    pa, pb = pa.cpu().numpy(), pb.cpu().numpy()
+    assert pb[3] == N * K and np.allclose(pa, pb, rtol=1e-5)
+    x, wn = s.importance_sample(target, 2 * N * K)
+    assert x.shape == (2 * N * K, D) and abs(wn.sum() - 1) < 1e-5 and 0 < s.get_NESS() <= 1
