@@ -159,7 +159,7 @@ class DeviceMixture:
         n, D = samples.shape
         DP = lib.aisb_padded_dims(D)
         KP = lib.aisb_padded_components(n_c)
-        rows = torch.empty((KP, 2 * DP), dtype=torch.float32, device=samples.device)
+        rows = torch.empty((KP, DP), dtype=torch.float32, device=samples.device)
         check(lib.aisb_kde_pack_f32(_ptr(samples), n, D, _ptr(idx), int(n_c), float(bw), _ptr(rows), stream_ptr()),
               "aisb_kde_pack_f32")
         uo = -math.log(n_c) - 0.5 * D * (LOG_2PI + math.log(bw))

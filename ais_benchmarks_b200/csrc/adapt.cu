@@ -168,12 +168,12 @@ __device__ float mixture_logpdf_point(const float* xp, int D, int DP, int kind, 
     float t = offs ? offs[k] : 0.f;
     if (kind == AISB_COV_ISO_SHARED) {
       for (int d = 0; d < D; ++d) {
-        const float dl = fmaf(xp[d], a_iso, row[2 * d]);
+        const float dl = fmaf(xp[d], a_iso, row[d]);
         t = fmaf(-dl, dl, t);
       }
     } else if (kind == AISB_COV_DIAG) {
       for (int d = 0; d < D; ++d) {
-        const float dl = fmaf(xp[d], row[2 * d], row[2 * DP + 2 * d]);
+        const float dl = fmaf(xp[d], row[d], row[DP + d]);
         t = fmaf(-dl, dl, t);
       }
     } else {

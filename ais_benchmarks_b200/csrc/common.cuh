@@ -111,8 +111,7 @@ __device__ __forceinline__ double warp_max(double v) {
 // Packed layout traits (must match include/ais_b200.h)
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int row_floats(int kind, int DP) {
-  return kind == AISB_COV_ISO_SHARED ? 2 * DP
-                                     : (kind == AISB_COV_DIAG ? 4 * DP : ((DP * (DP + 1) / 2 + DP + 3) / 4) * 4);
+  return kind == AISB_COV_ISO_SHARED ? DP : (kind == AISB_COV_DIAG ? 2 * DP : ((DP * (DP + 1) / 2 + DP + 3) / 4) * 4);
 }
 
 }  // namespace aisb

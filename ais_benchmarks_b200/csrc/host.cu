@@ -145,11 +145,7 @@ extern "C" int aisb_pack_mixture_f64(const double* h_means, const double* h_cov,
     const double logdet = D * std::log(v);
     for (int64_t k = 0; k < K; ++k) {
       // b is built from the float-rounded scale so that fma(x, a, b) cancels exactly at x == mu
-      for (int d = 0; d < D; ++d) {
-        const float b = static_cast<float>(-static_cast<double>(af) * h_means[k * D + d]);
-        h_rows[k * RF + 2 * d] = b;  // every value twice: the (b, b) operand of FFMA2
-        h_rows[k * RF + 2 * d + 1] = b;
-      }
+      for (int d = 0; d < D; ++d) h_rows[k * RF + d] = static_cast<float>(-static_cast<double>(af) * h_means[k * D + d]);
       h_offsets[k] = w[k] > 0.0 ? static_cast<float>(kLog2e * (std::log(w[k]) + base - 0.5 * logdet)) : ninf;
     }
     return AISB_OK;
@@ -167,9 +163,8 @@ extern "C" int aisb_pack_mixture_f64(const double* h_means, const double* h_cov,
         }
         logdet += std::log(v);
         const float af = static_cast<float>(std::sqrt(kLog2e / (2.0 * v)));
-        const float b = static_cast<float>(-static_cast<double>(af) * h_means[k * D + d]);
-        h_rows[k * RF + 2 * d] = h_rows[k * RF + 2 * d + 1] = af;
-        h_rows[k * RF + 2 * DP + 2 * d] = h_rows[k * RF + 2 * DP + 2 * d + 1] = b;
+        h_rows[k * RF + d] = af;
+        h_rows[k * RF + DP + d] = static_cast<float>(-static_cast<double>(af) * h_means[k * D + d]);
       }
       h_offsets[k] = w[k] > 0.0 ? static_cast<float>(kLog2e * (std::log(w[k]) + base - 0.5 * logdet)) : ninf;
     }

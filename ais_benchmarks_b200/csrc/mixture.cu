@@ -146,7 +146,7 @@ __global__ void tc_abort_to_partials_kernel(const int32_t* __restrict__ err, dou
 }
 
 // ---------------------------------------------------------------------------------------------
-// KDE pack: rows[j][2d] = rows[j][2d+1] = -a * samples[idx[j]][d], pad dims 0, pad components 1e18
+// KDE pack: rows[j][d] = -a * samples[idx[j]][d], pad dims 0, pad components 1e18
 // ---------------------------------------------------------------------------------------------
 __global__ void kde_pack_kernel(const float* __restrict__ samples, int64_t n, int D, int DP,
                                 const int64_t* __restrict__ idx, int64_t n_c, int64_t KP, float a,
@@ -165,7 +165,7 @@ __global__ void kde_pack_kernel(const float* __restrict__ samples, int64_t n, in
     src = src < 0 ? 0 : (src >= n ? n - 1 : src);
     v = -a * samples[src * D + d];
   }
-  reinterpret_cast<float2*>(rows)[i] = make_float2(v, v);
+  rows[i] = v;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -13,9 +13,10 @@
 //   * everything is carried in the log2 domain: t = c_k - ||A_k x + b_k||^2, accumulated as an
 //     FFMA chain seeded with c_k, then S += ex2(t - m),
 //   * ISO/DIAG kinds use the sm_100 packed FP32 instructions (FFMA2): two POINTS share one 64-bit
-//     register pair per dimension and the component parameters are stored duplicated ((b,b) pairs),
-//     so one FFMA2 advances two (point, component) pairs: half the issue slots for the same FMA-pipe
-//     work, which leaves issue bandwidth for the MUFU / FMNMX / LDS instructions,
+//     register pair per dimension and the component parameter enters as a scalar-broadcast operand
+//     (FFMA2 Rd, Ra.F32x2, Rb.F32, Rc.F32), so one FFMA2 advances two (point, component) pairs:
+//     half the issue slots for the same FMA-pipe work, which leaves issue bandwidth for the
+//     MUFU / FMNMX / LDS instructions,
 //   * the online-LSE update of group g runs while group g+1 is being evaluated (software pipeline:
 //     the pending group's t values stay in registers), so MUFU.EX2 work interleaves with FFMA2 work
 //     instead of arriving in bursts.
@@ -98,11 +99,10 @@ __device__ __forceinline__ void lds_vec(const float* __restrict__ p, float (&v)[
 template <int KIND, int DP, int E>
 __device__ __forceinline__ void comp_eval(const float* __restrict__ row, float c, float a_iso,
                                           const float (&x)[E][DP], float (&t)[E]) {
-  // scalar evaluation (used by the moment kernel); ISO/DIAG rows hold every parameter twice (FFMA2 layout)
+  // scalar evaluation (used by the moment kernel)
   if constexpr (KIND == AISB_COV_ISO_SHARED) {
     float b[DP];
-#pragma unroll
-    for (int d = 0; d < DP; ++d) b[d] = row[2 * d];
+    lds_vec<DP>(row, b);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       float acc = c;
@@ -115,11 +115,8 @@ __device__ __forceinline__ void comp_eval(const float* __restrict__ row, float c
     }
   } else if constexpr (KIND == AISB_COV_DIAG) {
     float a[DP], b[DP];
-#pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      a[d] = row[2 * d];
-      b[d] = row[2 * DP + 2 * d];
-    }
+    lds_vec<DP>(row, a);
+    lds_vec<DP>(row + DP, b);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       float acc = c;
@@ -192,54 +189,40 @@ __device__ __forceinline__ void accumulate_chunk(const float* __restrict__ srows
 }
 
 // ---------------------------------------------------------------------------------------------
-// Packed (FFMA2) path for ISO / DIAG kinds. Points are held as pairs: x2[pp][d] = (x[2pp][d], x[2pp+1][d]).
-// Row layout (include/ais_b200.h): ISO  (b0,b0,b1,b1,...)            2*DP floats
-//                                  DIAG (a0,a0,a1,a1,...,b0,b0,...)  4*DP floats
+// Packed (FFMA2) path for ISO / DIAG kinds. Points are held as pairs: x2[pp][d] = (x[2pp][d], x[2pp+1][d]); a
+// component parameter is a scalar that the FFMA2 broadcasts to both halves (make_float2(b, b) compiles to the .F32
+// operand form, no register pair is built).
+// Row layout (include/ais_b200.h): ISO  b[0..DP)            DIAG  a[0..DP) then b[0..DP)
 // ---------------------------------------------------------------------------------------------
-template <int N>
-__device__ __forceinline__ void lds_vec2(const float* __restrict__ p, float2 (&v)[N]) {
-  if constexpr (N % 2 == 0) {
-#pragma unroll
-    for (int q = 0; q < N / 2; ++q) {
-      const float4 f = reinterpret_cast<const float4*>(p)[q];
-      v[2 * q + 0] = make_float2(f.x, f.y);
-      v[2 * q + 1] = make_float2(f.z, f.w);
-    }
-  } else {
-#pragma unroll
-    for (int q = 0; q < N; ++q) v[q] = reinterpret_cast<const float2*>(p)[q];
-  }
-}
-
 __device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+__device__ __forceinline__ float2 bc2(float v) { return make_float2(v, v); }
 
 template <int KIND, int DP, int EP>
 __device__ __forceinline__ void comp_eval2(const float* __restrict__ row, const float2 (&seed)[EP], float a_iso,
                                            const float2 (&x2)[EP][DP], float2 (&t2)[EP]) {
-  float2 b2[DP];
+  float b[DP];
   if constexpr (KIND == AISB_COV_ISO_SHARED) {
-    lds_vec2<DP>(row, b2);
-    const float2 a2 = make_float2(a_iso, a_iso);
+    lds_vec<DP>(row, b);
 #pragma unroll
     for (int pp = 0; pp < EP; ++pp) {
       float2 acc = seed[pp];
 #pragma unroll
       for (int d = 0; d < DP; ++d) {
-        const float2 dl = __ffma2_rn(x2[pp][d], a2, b2[d]);
+        const float2 dl = __ffma2_rn(x2[pp][d], bc2(a_iso), bc2(b[d]));
         acc = __ffma2_rn(neg2(dl), dl, acc);
       }
       t2[pp] = acc;
     }
   } else {
-    float2 a2[DP];
-    lds_vec2<DP>(row, a2);
-    lds_vec2<DP>(row + 2 * DP, b2);
+    float a[DP];
+    lds_vec<DP>(row, a);
+    lds_vec<DP>(row + DP, b);
 #pragma unroll
     for (int pp = 0; pp < EP; ++pp) {
       float2 acc = seed[pp];
 #pragma unroll
       for (int d = 0; d < DP; ++d) {
-        const float2 dl = __ffma2_rn(x2[pp][d], a2[d], b2[d]);
+        const float2 dl = __ffma2_rn(x2[pp][d], bc2(a[d]), bc2(b[d]));
         acc = __ffma2_rn(neg2(dl), dl, acc);
       }
       t2[pp] = acc;

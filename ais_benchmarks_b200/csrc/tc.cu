@@ -132,14 +132,14 @@ constexpr float kTcSkip = 64.f;    // chunks entirely below 2^-64 of the referen
 constexpr float kTcRefine = 30.f;  // screened exponents within 2^-30 of the reference term are re-evaluated exactly
 
 // exact log2-domain exponent of (point, component j): the centred FP32 form of the CUDA-core path on the packed
-// ISO_SHARED row (b = -a mu, every value twice)
+// ISO_SHARED row (b = -a mu)
 template <int DP>
-__device__ __noinline__ float tc_exact(const float (&xr)[DP], float a_iso, const float* __restrict__ rows, int64_t j) {
-  const float* row = rows + j * (2 * DP);
+__device__ __forceinline__ float tc_exact(const float (&xr)[DP], float a_iso, const float* __restrict__ rows, int64_t j) {
+  const float* row = rows + j * DP;
   float acc = 0.f;
 #pragma unroll
   for (int d = 0; d < DP; ++d) {
-    const float dl = fmaf(xr[d], a_iso, __ldg(row + 2 * d));
+    const float dl = fmaf(xr[d], a_iso, __ldg(row + d));
     acc = fmaf(-dl, dl, acc);
   }
   return acc;
@@ -153,7 +153,7 @@ __device__ __noinline__ float tc_exact(const float (&xr)[DP], float a_iso, const
 template <int DP>
 __device__ __forceinline__ void tc_fold32(const uint32_t (&r)[32], float c, float (&S)[4], float& m,
                                           const float (&xr)[DP], float a_iso, const float* __restrict__ rows,
-                                          int64_t j0, int64_t K) {
+                                          int64_t j0, int64_t K, int64_t j_hint, float m_hint) {
   // chunk maximum on the raw accumulators first (16 three-input FMNMX on the ALU pipe): a chunk whose largest term is
   // below 2^-kTcSkip of the reference cannot change a float32 sum (K * 2^-64 << 2^-24) and is dropped without touching
   // the FMA or MUFU pipes -- in 32-D that is almost every chunk (far proposals sit at 2^-280)
@@ -172,21 +172,26 @@ __device__ __forceinline__ void tc_fold32(const uint32_t (&r)[32], float c, floa
     S[i & 3] += ex2(fminf(a[i], -kTcRefine));  // a term that matters enters as 2^-kTcRefine until the slow path fixes it
   }
   if (g > -kTcRefine) {
+    uint32_t mask = 0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (a[i] > -kTcRefine && j0 + i < K) {
-        const float t = tc_exact<DP>(xr, a_iso, rows, j0 + i);
-        S[0] -= 9.31322574615478515625e-10f;  // 2^-30: what the fast path added for this column
-        if (t - m > 60.f) {                // a component far above the hinted one: move the reference (keeps ex2 finite)
-          const float f = ex2(m - t);
-          S[0] = S[0] * f + 1.f;
-          S[1] *= f;
-          S[2] *= f;
-          S[3] *= f;
-          m = t;
-        } else {
-          S[0] += ex2(t - m);
-        }
+    for (int i = 0; i < 32; ++i) mask |= (a[i] > -kTcRefine) ? (1u << i) : 0u;
+    while (mask) {  // single call site: tc_exact stays inlined and the point stays in registers
+      const int i = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int64_t j = j0 + i;
+      if (j >= K) continue;
+      S[0] -= 9.31322574615478515625e-10f;  // 2^-30: what the fast path added for this column
+      // the hinted component was evaluated up front: it IS the reference, its term is exactly 1
+      const float t = j == j_hint ? m_hint : tc_exact<DP>(xr, a_iso, rows, j);
+      if (t - m > 60.f) {  // a component far above the reference: move the reference (keeps ex2 finite)
+        const float f = ex2(m - t);
+        S[0] = S[0] * f + 1.f;
+        S[1] *= f;
+        S[2] *= f;
+        S[3] *= f;
+        m = t;
+      } else {
+        S[0] += ex2(t - m);
       }
     }
   }
@@ -194,7 +199,7 @@ __device__ __forceinline__ void tc_fold32(const uint32_t (&r)[32], float c, floa
 
 // ---------------------------------------------------------------------------------------------
 // B image: per tile of 128 components the exact shared-memory image [K/4 chunks][128 rows][4 floats].
-// Input: the ISO_SHARED packed rows (b = -a mu, every value twice). Padding components get w = -1e30.
+// Input: the ISO_SHARED packed rows (b = -a mu). Padding components get w = -1e30.
 // ---------------------------------------------------------------------------------------------
 __global__ void tc_pack_kernel(const float* __restrict__ rows, int64_t K, int D, int DP, float* __restrict__ image) {
   const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -211,7 +216,7 @@ __global__ void tc_pack_kernel(const float* __restrict__ rows, int64_t K, int D,
   }
   double w = 0.0;
   for (int d = 0; d < D; ++d) {
-    const float v = -rows[j * (2 * DP) + 2 * d];
+    const float v = -rows[j * DP + d];
     put(d, to_tf32(v));
     w -= static_cast<double>(v) * static_cast<double>(v);
   }
@@ -346,6 +351,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       int64_t h = hint[pc];
       h = h < 0 ? 0 : (h >= K ? K - 1 : h);
       float m = tc_exact<DP>(xr, a_iso, rows, h);
+      const float m_hint = m;             // exact exponent of the hinted component (reused when the sweep reaches it)
       if (!(m > -1.0e30f)) m = -1.0e30f;  // NaN / -inf inputs: keep the arithmetic finite, the result is -inf / NaN anyway
       float c = static_cast<float>(nu + static_cast<double>(m));
       float S[4] = {0.f, 0.f, 0.f, 0.f};
@@ -368,12 +374,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int c0 = 0; c0 < kTcN; c0 += 64) {
           tc_ld32_issue(taddr + c0 + 32, r1);
           const float m0 = m;
-          if (!(dbg & 1)) tc_fold32<DP>(r0, c, S, m, xr, a_iso, rows, jbase + c0, K);
+          if (!(dbg & 1)) tc_fold32<DP>(r0, c, S, m, xr, a_iso, rows, jbase + c0, K, h, m_hint);
           if (m != m0) c = static_cast<float>(nu + static_cast<double>(m));
           tc_ld_wait();
           if (c0 + 64 < kTcN) tc_ld32_issue(taddr + c0 + 64, r0);
           const float m1 = m;
-          if (!(dbg & 1)) tc_fold32<DP>(r1, c, S, m, xr, a_iso, rows, jbase + c0 + 32, K);
+          if (!(dbg & 1)) tc_fold32<DP>(r1, c, S, m, xr, a_iso, rows, jbase + c0 + 32, K, h, m_hint);
           if (dbg & 1) S[0] += __uint_as_float(r0[3]) + __uint_as_float(r1[5]);
           if (m != m1) c = static_cast<float>(nu + static_cast<double>(m));
           tc_ld_wait();

@@ -64,11 +64,8 @@ typedef enum aisb_cov_kind {
  * to a multiple of AISB_COMP_ALIGN. Padding dims hold 0; padding components hold
  * c = -inf (offsets present) or coordinate 1e18 (no offsets).
  *
- *  ISO_SHARED: rows[KP][2*DP]  = (b_k0, b_k0, b_k1, b_k1, ...),  b_k = -a * mu_k,  a = sqrt(LOG2E / (2 v)) passed as
- *              `iso_scale`. Every value is stored TWICE: the kernels evaluate two points per packed FP32
- *              instruction (sm_100 FFMA2) and read the component parameter as a ready-made (b, b) operand pair.
- *  DIAG:       rows[KP][4*DP]  = (a_k0, a_k0, a_k1, a_k1, ...) then (b_k0, b_k0, ...),
- *              a_kd = sqrt(LOG2E / (2 v_kd)), b_kd = -a_kd mu_kd
+ *  ISO_SHARED: rows[KP][DP]    = b_k = -a * mu_k,  a = sqrt(LOG2E / (2 v)) passed as `iso_scale`
+ *  DIAG:       rows[KP][2*DP]  = a_k[0..DP) then b_k[0..DP),  a_kd = sqrt(LOG2E / (2 v_kd)), b_kd = -a_kd mu_kd
  *  FULL:       rows[KP][RF], RF = DP*(DP+1)/2 + DP rounded up to a multiple of 4
  *              = lower triangle of A_k row-major (A00, A10, A11, A20, ...), then b_k, then zero padding (D <= 32 only)
  *  offsets[KP] = c_k  (may be NULL for ISO_SHARED: all components share `uniform_offset`)
@@ -116,7 +113,7 @@ int aisb_pack_mixture_f64(const double* h_means, const double* h_cov, const doub
  * (sampling_methods/base.py:162-179): n_c isotropic kernels N(x_idx[j], bw*I) with equal weights.
  *   d_samples [n, D]; d_idx [n_c] int64 row indices into d_samples, or NULL (identity, n_c <= n);
  *   bw = kernel VARIANCE (reference quirk: "bw" goes on the covariance diagonal);
- *   d_rows out [aisb_padded_components(n_c) * 2 * DP] (ISO_SHARED layout).
+ *   d_rows out [aisb_padded_components(n_c) * DP] (ISO_SHARED layout).
  * The matching aisb_packed_mixture is {d_rows, NULL, n_c, D, ISO_SHARED, sqrt(LOG2E/(2 bw)),
  *   -log(n_c) - 0.5 * D * log(2 pi bw)}.
  */

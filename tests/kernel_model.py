@@ -14,9 +14,9 @@ def packed_logpdf(x, rows, offs, K, D, kind, iso_scale, DP):
     for k in range(K):
         row = rows[k]
         if kind == 0:
-            z = x * float(iso_scale) + row[0:2 * D:2]
+            z = x * float(iso_scale) + row[:D]
         elif kind == 1:
-            z = x * row[0:2 * D:2] + row[2 * DP:2 * DP + 2 * D:2]
+            z = x * row[:D] + row[DP:DP + D]
         else:
             tri = DP * (DP + 1) // 2
             z = np.empty((n, D))

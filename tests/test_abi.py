@@ -36,7 +36,7 @@ def test_layout_queries():
     assert [lib.aisb_padded_dims(d) for d in (1, 2, 3, 4, 5, 8, 9, 32, 33, 64, 65, 0)] == \
         [1, 2, 4, 4, 8, 8, 16, 32, 64, 64, 0, 0]
     assert lib.aisb_padded_components(1) == 32 and lib.aisb_padded_components(33) == 64
-    assert lib.aisb_packed_row_floats(0, 8) == 16 and lib.aisb_packed_row_floats(1, 8) == 32
+    assert lib.aisb_packed_row_floats(0, 8) == 8 and lib.aisb_packed_row_floats(1, 8) == 16
     assert lib.aisb_packed_row_floats(2, 8) == 44 and lib.aisb_packed_row_floats(2, 3) == 16
     assert lib.aisb_packed_row_floats(2, 64) == 0
     assert lib.aisb_iso_scale(0.02) == pytest.approx(np.sqrt(np.log2(np.e) / 0.04), rel=1e-6)
@@ -49,8 +49,7 @@ def test_pack_diag_matches_oracle(case):
     K, D = means.shape
     rows, offs, _ = DeviceMixture.pack_host(means, sigmas, w, _lib.COV_DIAG)
     DP = _lib.load().aisb_padded_dims(D)
-    assert rows.shape == (_lib.load().aisb_padded_components(K), 4 * DP)
-    assert np.array_equal(rows[:, 0::2], rows[:, 1::2])  # every parameter twice (FFMA2 operand pairs)
+    assert rows.shape == (_lib.load().aisb_padded_components(K), 2 * DP)
     assert np.all(np.isneginf(offs[K:])) and np.all(rows[K:] == 0)
     got = packed_logpdf(x, rows, offs, K, D, 1, 0.0, DP)
     ref = g["logp%d" % case]
