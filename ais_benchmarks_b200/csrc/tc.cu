@@ -46,8 +46,8 @@ constexpr int kTcAccCols = 2 * kTcRowTiles * kTcN;  // 512: all of TMEM
 __host__ __device__ constexpr int tc_kcols(int DP) { return DP + 8; }                // multiple of 8 for DP >= 8
 __host__ __device__ constexpr int tc_tile_floats(int DP) { return tc_kcols(DP) * kTcN; }
 __host__ __device__ constexpr int tc_stages(int DP) { return 4; }
-__host__ __device__ constexpr size_t tc_smem_bytes(int DP) {
-  return sizeof(float) * tc_tile_floats(DP) * (kTcRowTiles + tc_stages(DP)) + 1024;
+__host__ __device__ constexpr size_t tc_smem_bytes(int DP) {  // A tiles are double-buffered across iterations
+  return sizeof(float) * tc_tile_floats(DP) * (2 * kTcRowTiles + tc_stages(DP)) + 1024;
 }
 
 __device__ __forceinline__ float to_tf32(float x) {
@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   constexpr int KC = tc_kcols(DP);
   constexpr int NST = tc_stages(DP);
   constexpr uint32_t TILE_BYTES = sizeof(float) * KC * kTcN;
-  float* sA = reinterpret_cast<float*>(tc_smem);            // kTcRowTiles A tiles
-  float* sB = sA + kTcRowTiles * KC * kTcRows;               // NST B stages
+  float* sA = reinterpret_cast<float*>(tc_smem);            // 2 (iteration parity) x kTcRowTiles A tiles
+  float* sB = sA + 2 * kTcRowTiles * KC * kTcRows;           // NST B stages
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   volatile int* abort_flag = &bars.abort_flag;
@@ -310,7 +310,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           for (int rt = 0; rt < kTcRowTiles; ++rt) {
 #pragma unroll 1
             for (int ks = 0; ks < KC / 8; ++ks) {
-              const uint64_t adesc = tc_smem_desc(a_addr + rt * (KC * kTcRows * 4) + ks * 2 * (kTcRows * 16), kTcRows);
+              const uint64_t adesc = tc_smem_desc(
+                  a_addr + ((itm & 1u) * kTcRowTiles + rt) * (KC * kTcRows * 4) + ks * 2 * (kTcRows * 16), kTcRows);
               const uint64_t bdesc = tc_smem_desc(b_addr + ks * 2 * (kTcN * 16), kTcN);
               if (!(dbg & 2) || ks == 0) tc_mma(tmem_base + (rt * 2 + b) * kTcN, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
             }
@@ -324,28 +325,60 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // ===== A builder + epilogue: thread = point; row tile = warp / 4, TMEM lane = row within the tile =====
     const int rt = threadIdx.x / kTcRows;
     const int row = threadIdx.x % kTcRows;
-    uint32_t itn = 0;
-    for (int64_t tm = blockIdx.x; tm < ntiles_m && !*abort_flag; tm += gridDim.x) {
+    const bool vec = (D == DP) && (reinterpret_cast<uintptr_t>(x) % 16 == 0);
+
+    auto load_point = [&](int64_t tm, float (&xv)[DP]) {
       const int64_t p = tm * kRowsPerIter + threadIdx.x;
       const int64_t pc = p < n ? p : n - 1;
-      // ---- A tile row: [tf32(2u), 1, 1, 1, 0...] ----
-      double nu = 0.0;
-      float xr[DP], hi[DP];
+      if (vec) {
+        const float4* r = reinterpret_cast<const float4*>(x + pc * DP);
 #pragma unroll
-      for (int d = 0; d < DP; ++d) {
-        xr[d] = d < D ? __ldg(x + pc * D + d) : 0.f;
-        const float u = a_iso * xr[d];
-        nu += static_cast<double>(u) * static_cast<double>(u);
-        hi[d] = to_tf32(2.f * u);
+        for (int q = 0; q < DP / 4; ++q) {
+          const float4 f = __ldg(r + q);
+          xv[4 * q] = f.x;
+          xv[4 * q + 1] = f.y;
+          xv[4 * q + 2] = f.z;
+          xv[4 * q + 3] = f.w;
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < DP; ++d) xv[d] = d < D ? __ldg(x + pc * D + d) : 0.f;
       }
-      float4* arow = reinterpret_cast<float4*>(sA + rt * (KC * kTcRows)) + row;  // chunk c at + c * 128 float4
+    };
+    // A tile row [tf32(2u), 1, 1, 1, 0...] into the buffer of iteration parity `par`; returns ||u||^2
+    auto build_a = [&](const float (&xv)[DP], uint32_t par) -> double {
+      double nu = 0.0;
+      float4* arow = reinterpret_cast<float4*>(sA + (par * kTcRowTiles + rt) * (KC * kTcRows)) + row;  // chunk c at + c*128
 #pragma unroll
-      for (int c = 0; c < DP / 4; ++c)
-        arow[c * kTcRows] = make_float4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+      for (int c = 0; c < DP / 4; ++c) {
+        float hv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float u = a_iso * xv[4 * c + e];
+          nu += static_cast<double>(u) * static_cast<double>(u);
+          hv[e] = to_tf32(2.f * u);
+        }
+        arow[c * kTcRows] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      }
       arow[(DP / 4) * kTcRows] = make_float4(1.f, 1.f, 1.f, 0.f);
       arow[(DP / 4 + 1) * kTcRows] = make_float4(0.f, 0.f, 0.f, 0.f);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(&bars.a_ready);
+      return nu;
+    };
+
+    uint32_t itn = 0, itm = 0;
+    float xr[DP], xn[DP];
+    double nu = 0.0, nu_next = 0.0;
+    if (blockIdx.x < ntiles_m) {
+      load_point(blockIdx.x, xr);
+      nu = build_a(xr, 0u);
+    }
+    for (int64_t tm = blockIdx.x; tm < ntiles_m && !*abort_flag; tm += gridDim.x, ++itm) {
+      const int64_t p = tm * kRowsPerIter + threadIdx.x;
+      const int64_t pc = p < n ? p : n - 1;
+      const bool has_next = tm + gridDim.x < ntiles_m;
+      if (has_next) load_point(tm + gridDim.x, xn);  // lands while this iteration's tiles are being swept
 
       // ---- reference term: the hinted component, evaluated exactly (it is picked up again, exactly, by the sweep) ----
       int64_t h = hint[pc];
@@ -358,6 +391,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
       // ---- epilogue: screened sum over the accumulator tiles, TMEM loads one chunk ahead of the arithmetic ----
       bool ok = true;
+      const int build_at = ntiles_n > 1 ? 1 : 0;  // the next iteration's A tile is built in the shadow of this sweep
       for (int tn = 0; tn < ntiles_n && ok; ++tn, ++itn) {
         const uint32_t b = itn & 1u, bph = (itn >> 1) & 1u;
         if (!tc_wait(&bars.tfull[b], bph, abort_flag)) {
@@ -386,8 +420,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
         tc_fence_before();
         mbar_arrive(&bars.tempty[b]);
+        // every MMA of the PREVIOUS iteration (which read the other A buffer) completed before this iteration's first
+        // accumulator was signalled, so that buffer is free
+        if (tn == build_at && has_next) nu_next = build_a(xn, (itm + 1u) & 1u);
       }
       if (ok && p < n) out[p] = (m + log2f((S[0] + S[1]) + (S[2] + S[3]))) * 0.69314718055994530942f + uniform_offset;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) xr[d] = xn[d];
+      nu = nu_next;
     }
   }
 
