@@ -191,6 +191,17 @@ class TensorCoreOperand:
         self.mix = mix
         self.image = torch.empty(nfl, dtype=torch.float32, device=mix.rows.device)
         check(lib.aisb_tc_pack_f32(mix.ref(), _ptr(self.image), stream_ptr()), "aisb_tc_pack_f32")
+        self._screen_error = None
+
+    @property
+    def screen_error(self):
+        """Worst-case absolute error (log2 units) of the TF32 screen for a point as far from the origin as the
+        farthest component: 2^-9 max_j ||a mu_j||^2 (the image trailer holds the norm). The kernel widens each
+        point's refine window by twice its own bound, so a large value costs time, never accuracy."""
+        if self._screen_error is None:
+            vmax = float(self.image[-8].item())
+            self._screen_error = vmax * vmax / 512.0
+        return self._screen_error
 
 
 def tc_logq(x, operand, hint, out=None):
@@ -208,10 +219,23 @@ def tc_logq(x, operand, hint, out=None):
     return out
 
 
+TC_MAX_SCREEN_ERROR = 8.0  # beyond this most pairs would be re-evaluated exactly: the CUDA-core kernel is faster
+
+
 def tc_eligible(mix):
     """Tensor-core proposal path: equal-weight isotropic mixtures in 9..32 dimensions (below that the cross term is
     not a real contraction and the CUDA-core kernel wins)."""
     return mix.kind == COV_ISO_SHARED and mix.offsets is None and 9 <= mix.D <= 32
+
+
+def tc_operand(mix):
+    """The mixture's tensor-core operand (built once per parameter set), or None when the mixture is not eligible or
+    sits so far from the origin that the TF32 screen would not discriminate (see TensorCoreOperand.screen_error)."""
+    if not tc_eligible(mix):
+        return None
+    if getattr(mix, "_tc_operand", None) is None:
+        mix._tc_operand = TensorCoreOperand(mix)
+    return mix._tc_operand if mix._tc_operand.screen_error <= TC_MAX_SCREEN_ERROR else None
 
 
 def dm_weights(x, target, logp_in, proposals, want_logp=False, want_logq=False, hint=None):
@@ -219,8 +243,9 @@ def dm_weights(x, target, logp_in, proposals, want_logp=False, want_logq=False, 
     the proposal each sample was drawn from) and an eligible proposal mixture: proposal density on the tensor cores
     (aisb_dm_weights_hinted_f32). Returns (logw, logp|None, logq|None, partials[4] device f64)."""
     lib = require_cuda()
-    if hint is not None and tc_eligible(proposals) and x.shape[0] > 0:
-        return _dm_weights_hinted(lib, x, target, logp_in, proposals, want_logp, want_logq, hint)
+    operand = tc_operand(proposals) if hint is not None and x.shape[0] > 0 else None
+    if operand is not None:
+        return _dm_weights_hinted(lib, x, target, logp_in, proposals, operand, want_logp, want_logq, hint)
     n = x.shape[0]
     dev = x.device
     logw = torch.empty(n, dtype=torch.float32, device=dev)
@@ -235,10 +260,8 @@ def dm_weights(x, target, logp_in, proposals, want_logp=False, want_logq=False, 
     return logw, logp, logq, partials
 
 
-def _dm_weights_hinted(lib, x, target, logp_in, proposals, want_logp, want_logq, hint):
+def _dm_weights_hinted(lib, x, target, logp_in, proposals, operand, want_logp, want_logq, hint):
     n, dev = x.shape[0], x.device
-    if getattr(proposals, "_tc_operand", None) is None:
-        proposals._tc_operand = TensorCoreOperand(proposals)
     logw = torch.empty(n, dtype=torch.float32, device=dev)
     logp = torch.empty(n, dtype=torch.float32, device=dev) if want_logp else None
     logq = torch.empty(n, dtype=torch.float32, device=dev) if want_logq else None
@@ -247,7 +270,7 @@ def _dm_weights_hinted(lib, x, target, logp_in, proposals, want_logp, want_logq,
     ws = workspace_for(n, Kmax, proposals.D)
     hint = hint.to(device=dev, dtype=torch.int32).contiguous()
     check(lib.aisb_dm_weights_hinted_f32(_ptr(x), n, target.ref() if target is not None else None, _ptr(logp_in),
-                                         proposals.ref(), _ptr(proposals._tc_operand.image), _ptr(hint), _ptr(logw),
+                                         proposals.ref(), _ptr(operand.image), _ptr(hint), _ptr(logw),
                                          _ptr(logp), _ptr(logq), _ptr(partials), _ptr(ws), ws.numel(), stream_ptr()),
           "aisb_dm_weights_hinted_f32")
     return logw, logp, logq, partials

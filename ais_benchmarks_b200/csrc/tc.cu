@@ -128,39 +128,64 @@ __device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-constexpr float kTcSkip = 64.f;    // chunks entirely below 2^-64 of the reference term are skipped
-constexpr float kTcRefine = 30.f;  // screened exponents within 2^-30 of the reference term are re-evaluated exactly
+constexpr float kTcRefine = 30.f;    // screened exponents within 2^-30 of the reference term are re-evaluated exactly
+constexpr float kTcSkipMargin = 34.f;  // chunks entirely below 2^-(refine + 34) of the reference term are skipped
+constexpr int kTcTrailer = 8;        // floats behind the image: operand magnitudes for the per-point screen error bound
 
-// exact log2-domain exponent of (point, component j): the centred FP32 form of the CUDA-core path on the packed
-// ISO_SHARED row (b = -a mu)
-template <int DP>
-__device__ __forceinline__ float tc_exact(const float (&xr)[DP], float a_iso, const float* __restrict__ rows, int64_t j) {
-  const float* row = rows + j * DP;
-  float acc = 0.f;
-#pragma unroll
-  for (int d = 0; d < DP; ++d) {
-    const float dl = fmaf(xr[d], a_iso, __ldg(row + d));
-    acc = fmaf(-dl, dl, acc);
-  }
-  return acc;
+// The screen's absolute error grows with the operand magnitudes (TF32 inputs: relative 2^-11 each, 2^-10 per product).
+// Each point widens its refine window by twice its own worst-case bound E, so a term that matters is never left to
+// the screen; for data far from the origin the kernel degrades towards exact evaluation instead of losing accuracy.
+struct TcWindow {
+  float refine;   // kTcRefine + 2E
+  float skip;     // refine + kTcSkipMargin
+  float floor_;   // 2^-refine: what the fast path adds for a column that the slow path then replaces
+};
+__device__ __forceinline__ TcWindow tc_window(float err_bound) {
+  TcWindow w;
+  w.refine = kTcRefine + 2.f * err_bound;
+  w.skip = w.refine + kTcSkipMargin;
+  w.floor_ = ex2(-w.refine);
+  return w;
 }
 
-// fold 32 screened accumulator values (columns j0 .. j0+31) into the partial sums, relative to the fixed reference
-// exponent m:   screened term  e = ex2(v - c),  c = ||u||^2 + m   (v = 2u.v_j - ||v_j||^2 = t + ||u||^2).
-// Fast path: four independent partial sums, no predicates. If any screened exponent comes within kTcRefine of the
-// reference (tracked with a running max on the ALU pipe) the rare slow path swaps the screened term of each such
-// column for its exact value.
+// exact log2-domain exponent of (point, component j): the centred FP32 form of the CUDA-core path on the packed
+// ISO_SHARED row (b = -a mu), read from global memory (L1/L2 resident)
 template <int DP>
-__device__ __forceinline__ void tc_fold32(const uint32_t (&r)[32], float c, float (&S)[4], float& m,
-                                          const float (&xr)[DP], float a_iso, const float* __restrict__ rows,
-                                          int64_t j0, int64_t K, int64_t j_hint, float m_hint) {
-  // chunk maximum on the raw accumulators first (16 three-input FMNMX on the ALU pipe): a chunk whose largest term is
-  // below 2^-kTcSkip of the reference cannot change a float32 sum (K * 2^-64 << 2^-24) and is dropped without touching
-  // the FMA or MUFU pipes -- in 32-D that is almost every chunk (far proposals sit at 2^-280)
+struct TcExactIso {
+  const float (&xr)[DP];
+  float a_iso;
+  const float* __restrict__ rows;
+  __device__ __forceinline__ float operator()(int64_t j) const {
+    const float* row = rows + j * DP;
+    float acc = 0.f;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      const float dl = fmaf(xr[d], a_iso, __ldg(row + d));
+      acc = fmaf(-dl, dl, acc);
+    }
+    return acc;
+  }
+};
+
+__device__ __forceinline__ float tc_chunk_max(const uint32_t (&r)[32]) {
   float gr = __uint_as_float(r[0]);
 #pragma unroll
   for (int i = 1; i < 32; ++i) gr = fmaxf(gr, __uint_as_float(r[i]));
-  if (!(gr - c > -kTcSkip)) {
+  return gr;
+}
+
+// fold 32 screened accumulator values (columns j0 .. j0+31, chunk maximum gr) into the partial sums, relative to the
+// fixed reference exponent m:   screened term  e = ex2(v - c)   (v = t + ||u||^2, c = ||u||^2 + m).
+// Fast path: four independent partial sums, no predicates. If any screened exponent comes within the refine window of
+// the reference the rare slow path swaps the screened term of each such column for its exact value.
+template <class EX>
+__device__ __forceinline__ void tc_fold32(const uint32_t (&r)[32], float gr, float c, const TcWindow& win, float (&S)[4],
+                                          float& m, const EX& exact, int64_t j0, int64_t K, int64_t j_hint,
+                                          float m_hint) {
+  // chunk maximum on the raw accumulators first (16 three-input FMNMX on the ALU pipe): a chunk whose largest term is
+  // far below the reference cannot change a float32 sum (K * 2^-64 << 2^-24) and is dropped without touching the FMA
+  // or MUFU pipes -- in 32-D that is almost every chunk (far proposals sit at 2^-280)
+  if (!(gr - c > -win.skip)) {
     if (gr == gr) return;  // NaN falls through to the arithmetic path and propagates
   }
   float a[32];
@@ -169,20 +194,20 @@ __device__ __forceinline__ void tc_fold32(const uint32_t (&r)[32], float c, floa
   for (int i = 0; i < 32; ++i) {
     a[i] = __uint_as_float(r[i]) - c;
     g = fmaxf(g, a[i]);
-    S[i & 3] += ex2(fminf(a[i], -kTcRefine));  // a term that matters enters as 2^-kTcRefine until the slow path fixes it
+    S[i & 3] += ex2(fminf(a[i], -win.refine));  // a term that matters enters as 2^-refine until the slow path fixes it
   }
-  if (g > -kTcRefine) {
+  if (g > -win.refine) {
     uint32_t mask = 0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) mask |= (a[i] > -kTcRefine) ? (1u << i) : 0u;
-    while (mask) {  // single call site: tc_exact stays inlined and the point stays in registers
+    for (int i = 0; i < 32; ++i) mask |= (a[i] > -win.refine) ? (1u << i) : 0u;
+    while (mask) {  // single call site: the exact evaluation stays inlined and the point stays in registers
       const int i = __ffs(mask) - 1;
       mask &= mask - 1;
       const int64_t j = j0 + i;
       if (j >= K) continue;
-      S[0] -= 9.31322574615478515625e-10f;  // 2^-30: what the fast path added for this column
-      // the hinted component was evaluated up front: it IS the reference, its term is exactly 1
-      const float t = j == j_hint ? m_hint : tc_exact<DP>(xr, a_iso, rows, j);
+      S[0] -= win.floor_;  // what the fast path added for this column
+      // a hinted component was evaluated up front: it IS the reference, its term is exactly 1
+      const float t = j == j_hint ? m_hint : exact(j);
       if (t - m > 60.f) {  // a component far above the reference: move the reference (keeps ex2 finite)
         const float f = ex2(m - t);
         S[0] = S[0] * f + 1.f;
@@ -201,10 +226,12 @@ __device__ __forceinline__ void tc_fold32(const uint32_t (&r)[32], float c, floa
 // B image: per tile of 128 components the exact shared-memory image [K/4 chunks][128 rows][4 floats].
 // Input: the ISO_SHARED packed rows (b = -a mu). Padding components get w = -1e30.
 // ---------------------------------------------------------------------------------------------
+// Trailer (zeroed by the caller): [0] = max_j ||v_j|| (as ordered int bits).
 __global__ void tc_pack_kernel(const float* __restrict__ rows, int64_t K, int D, int DP, float* __restrict__ image) {
   const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t KT = (K + kTcN - 1) / kTcN * kTcN;
   if (j >= KT) return;
+  int* trailer = reinterpret_cast<int*>(image + (KT / kTcN) * static_cast<int64_t>(tc_kcols(DP)) * kTcN);
   const int kc = tc_kcols(DP);
   float* tile = image + (j / kTcN) * static_cast<int64_t>(kc) * kTcN;
   const int r = static_cast<int>(j % kTcN);
@@ -226,6 +253,7 @@ __global__ void tc_pack_kernel(const float* __restrict__ rows, int64_t K, int D,
   put(DP, wh);
   put(DP + 1, wm);
   put(DP + 2, wl);
+  atomicMax(trailer, __float_as_int(static_cast<float>(sqrt(-w)) * 1.0001f));  // non-negative floats order as ints
 }
 
 struct TcBars {
@@ -370,6 +398,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     uint32_t itn = 0, itm = 0;
     float xr[DP], xn[DP];
     double nu = 0.0, nu_next = 0.0;
+    const float vmax = __ldg(image + static_cast<int64_t>(ntiles_n) * KC * kTcN);
     if (blockIdx.x < ntiles_m) {
       load_point(blockIdx.x, xr);
       nu = build_a(xr, 0u);
@@ -383,11 +412,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       // ---- reference term: the hinted component, evaluated exactly (it is picked up again, exactly, by the sweep) ----
       int64_t h = hint[pc];
       h = h < 0 ? 0 : (h >= K ? K - 1 : h);
-      float m = tc_exact<DP>(xr, a_iso, rows, h);
+      const TcExactIso<DP> exact{xr, a_iso, rows};
+      float m = exact(h);
       const float m_hint = m;             // exact exponent of the hinted component (reused when the sweep reaches it)
       if (!(m > -1.0e30f)) m = -1.0e30f;  // NaN / -inf inputs: keep the arithmetic finite, the result is -inf / NaN anyway
       float c = static_cast<float>(nu + static_cast<double>(m));
       float S[4] = {0.f, 0.f, 0.f, 0.f};
+      // worst-case screen error of this point: sum_d |2 u_d v_jd| 2^-10 <= 2^-9 ||u|| max_j ||v_j||
+      const TcWindow win = tc_window(0.001953125f * sqrtf(static_cast<float>(nu)) * vmax);
 
       // ---- epilogue: screened sum over the accumulator tiles, TMEM loads one chunk ahead of the arithmetic ----
       bool ok = true;
@@ -408,12 +440,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int c0 = 0; c0 < kTcN; c0 += 64) {
           tc_ld32_issue(taddr + c0 + 32, r1);
           const float m0 = m;
-          if (!(dbg & 1)) tc_fold32<DP>(r0, c, S, m, xr, a_iso, rows, jbase + c0, K, h, m_hint);
+          if (!(dbg & 1)) tc_fold32(r0, tc_chunk_max(r0), c, win, S, m, exact, jbase + c0, K, h, m_hint);
           if (m != m0) c = static_cast<float>(nu + static_cast<double>(m));
           tc_ld_wait();
           if (c0 + 64 < kTcN) tc_ld32_issue(taddr + c0 + 64, r0);
           const float m1 = m;
-          if (!(dbg & 1)) tc_fold32<DP>(r1, c, S, m, xr, a_iso, rows, jbase + c0 + 32, K, h, m_hint);
+          if (!(dbg & 1)) tc_fold32(r1, tc_chunk_max(r1), c, win, S, m, exact, jbase + c0 + 32, K, h, m_hint);
           if (dbg & 1) S[0] += __uint_as_float(r0[3]) + __uint_as_float(r1[5]);
           if (m != m1) c = static_cast<float>(nu + static_cast<double>(m));
           tc_ld_wait();
@@ -462,6 +494,7 @@ static int launch_tc(const float* x, int64_t n, int D, const aisb_packed_mixture
   return AISB_OK;
 }
 
+
 }  // namespace aisb
 
 using namespace aisb;
@@ -469,7 +502,7 @@ using namespace aisb;
 extern "C" int64_t aisb_tc_image_floats(int64_t K, int32_t D) {
   const int DP = aisb_padded_dims(D);
   if (K < 1 || DP < 8 || DP > 32) return 0;
-  return (K + kTcN - 1) / kTcN * static_cast<int64_t>(tc_tile_floats(DP));
+  return (K + kTcN - 1) / kTcN * static_cast<int64_t>(tc_tile_floats(DP)) + kTcTrailer;
 }
 
 extern "C" int aisb_tc_pack_f32(const aisb_packed_mixture* mix, float* d_image, void* stream) {
@@ -480,8 +513,10 @@ extern "C" int aisb_tc_pack_f32(const aisb_packed_mixture* mix, float* d_image, 
   }
   const int DP = aisb_padded_dims(mix->D);
   const int64_t KT = (mix->K + kTcN - 1) / kTcN * kTcN;
-  tc_pack_kernel<<<static_cast<unsigned>((KT + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      mix->d_rows, mix->K, mix->D, DP, d_image);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AISB_CUDA_CHECK(cudaMemsetAsync(d_image + (KT / kTcN) * static_cast<int64_t>(tc_tile_floats(DP)), 0,
+                                  sizeof(float) * kTcTrailer, st));
+  tc_pack_kernel<<<static_cast<unsigned>((KT + 127) / 128), 128, 0, st>>>(mix->d_rows, mix->K, mix->D, DP, d_image);
   AISB_LAUNCH_CHECK("tc_pack_kernel");
   return AISB_OK;
 }

@@ -244,7 +244,8 @@ int aisb_uniform_box_f32(const float* d_lo, const float* d_hi, int32_t D, int64_
  * GEMM on the 5th-generation tensor cores (BASELINE.json configs[4], "tensor-core cross-term path").
  * The tensor-core value (absolute error up to ~0.3 in the exponent) is only a SCREEN: every pair that comes within
  * 2^-30 of the point's reference term is re-evaluated exactly with the centred FP32 form, so the result meets the same
- * 1e-5 bar as aisb_mixture_logpdf_f32. The reference term comes from d_hint[i] = index of a
+ * 1e-5 bar as aisb_mixture_logpdf_f32. Each point widens that window by twice its own worst-case
+ * screen error (from the operand magnitudes), so data far from the origin costs time, not accuracy. The reference term comes from d_hint[i] = index of a
  * component expected to dominate log q(x_i) (DM-AIS: the proposal x_i was drawn from); a poor hint costs time (more exact
  * re-evaluations) or, if it is more than ~2^100 below the true maximum, accuracy -- callers without a natural hint use
  * aisb_mixture_logpdf_f32.

@@ -604,6 +604,33 @@ def test_tensor_core_proposal_density(D, N, per):
     assert rel_err(_device.tc_logq(xu, op, hu).cpu().numpy(), refu) < LOGP_TOL, rel_err.last
 
 
+def test_tensor_core_screen_far_from_origin():
+    """Coordinates far from the origin inflate the TF32 screen error (|2 u.v| 2^-10 ~ tens of log2 units here):
+    every point widens its refine window by its own bound, so the kernel falls back to exact evaluation instead of
+    losing accuracy; the Python dispatcher does not pick the tensor-core path for such a mixture in the first place."""
+    from ais_benchmarks_b200 import _device
+    rs = np.random.RandomState(11)
+    D, N, per = 32, 200, 9
+    pm = 8.0 + rs.uniform(-1, 1, size=(N, D))
+    pm_d = torch.from_numpy(pm).cuda().float().contiguous()
+    mix = _device.DeviceMixture.kde(pm_d, None, N, 0.05)
+    _device.seed(5)
+    xs = _device.sample_iso(pm_d, per, 0.05)
+    hint = (torch.arange(xs.shape[0], device="cuda") // per).to(torch.int32)
+    op = _device.TensorCoreOperand(mix)
+    assert op.screen_error > 20 and _device.tc_operand(mix) is None
+    ref64 = O.iso_mixture_log_prob(xs.double().cpu().numpy(), pm_d.double().cpu().numpy(), 0.05)
+    ref32 = _device.mixture_logpdf(xs, mix).double().cpu().numpy()
+    # at |x| ~ 8 the float32 representation of a*mu alone costs 1.4e-5 (CUDA-core kernel included): the tensor-core
+    # path must reproduce the CUDA-core result to rounding and stay within that float32 limit of the oracle
+    for h in (hint, torch.zeros_like(hint)):
+        got = _device.tc_logq(xs, op, h).cpu().numpy()
+        assert rel_err(got, ref32) < 2e-6, rel_err.last
+        assert rel_err(got, ref64) < 5e-5, rel_err.last
+    near = _device.DeviceMixture.kde((pm_d - 8.0).contiguous(), None, N, 0.05)
+    assert _device.tc_operand(near) is not None and _device.tc_operand(near).screen_error < 2
+
+
 def test_dm_weights_hinted_equals_unhinted():
     """aisb_dm_weights_hinted_f32 (tensor-core proposals) vs aisb_dm_weights_f32 (fused CUDA-core kernel): same
     log-weights and partial sums on a 16-D DM-AIS batch; and the sampler routes through it end to end."""
