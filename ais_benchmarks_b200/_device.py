@@ -312,6 +312,45 @@ def kld_partials(lp, lq):
     return partials
 
 
+def pair_partials(lp, lq, floor):
+    """kld_partials with the inlier set {lp > floor and lq > floor} (C ABI aisb_pair_partials_f32)."""
+    lib = require_cuda()
+    n = lp.shape[0]
+    partials = torch.empty(8, dtype=torch.float64, device=lp.device)
+    ws = workspace(64 * (n // 2048 + 2) + 512)
+    check(lib.aisb_pair_partials_f32(_ptr(lp), _ptr(lq), n, float(floor), _ptr(partials), _ptr(ws), ws.numel(),
+                                     stream_ptr()), "aisb_pair_partials_f32")
+    return partials
+
+
+def pair_log_norms(partials_host):
+    """(Lp, Lq) = inlier log-sum-exps of a (merged) pair-partials record; (-inf, -inf) for an empty inlier set."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        p = partials_host
+        if p[5] <= 0:
+            return -np.inf, -np.inf
+        return float(p[0] + np.log(p[1])), float(p[3] + np.log(p[4]))
+
+
+def jsd_terms(lp, lq, floor, log_norm_p, log_norm_q):
+    """Device tensor {sum of JSD terms in nats, dropped NaN terms} (C ABI aisb_jsd_terms_f32)."""
+    lib = require_cuda()
+    out = torch.empty(2, dtype=torch.float64, device=lp.device)
+    check(lib.aisb_jsd_terms_f32(_ptr(lp), _ptr(lq), lp.shape[0], float(floor), float(log_norm_p), float(log_norm_q),
+                                 _ptr(out), stream_ptr()), "aisb_jsd_terms_f32")
+    return out
+
+
+def weighted_mean(x, logw, log_norm):
+    """sum_i x_i exp(logw_i - log_norm) as a float64 device tensor [D] (C ABI aisb_weighted_mean_f32)."""
+    lib = require_cuda()
+    n, D = x.shape
+    out = torch.empty(D, dtype=torch.float64, device=x.device)
+    check(lib.aisb_weighted_mean_f32(_ptr(x), n, D, _ptr(logw), float(log_norm), _ptr(out), stream_ptr()),
+          "aisb_weighted_mean_f32")
+    return out
+
+
 def kld_finalize(partials_host):
     lib = _lib.load()
     p = (C.c_double * 8)(*[float(v) for v in partials_host])

@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("AISB_LIB") or os.path.join(_HERE, "libais_b200.so")
 
 AISB_OK = 0
 COV_ISO_SHARED, COV_DIAG, COV_FULL = 0, 1, 2
+LOG_TINY = -745.13  # AISB_LOG_TINY: log-domain image of "prob > 0" in float64
 COMP_ALIGN = 32
 MAX_DIMS = 64
 
@@ -51,6 +52,9 @@ PROTOTYPES = {
     "aisb_kld_partials_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "aisb_kld_partials_merge": (None, [C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_dbl)]),
     "aisb_kld_finalize": (_dbl, [C.POINTER(_dbl)]),
+    "aisb_pair_partials_f32": (C.c_int, [_vp, _vp, _i64, C.c_float, _vp, _vp, _sz, _vp]),
+    "aisb_jsd_terms_f32": (C.c_int, [_vp, _vp, _i64, C.c_float, _dbl, _dbl, _vp, _vp]),
+    "aisb_weighted_mean_f32": (C.c_int, [_vp, _i64, _i32, _vp, _dbl, _vp, _vp]),
     "aisb_mpmc_moments_f32": (C.c_int, [_vp, _i64, _pm, _vp, _vp, _dbl, _vp, _vp]),
     "aisb_raw_moments_f32": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "aisb_lais_mh_f32": (C.c_int, [_vp, _i64, _pm, _vp, _vp, _i32, _vp, _vp, _vp]),

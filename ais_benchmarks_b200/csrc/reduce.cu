@@ -77,8 +77,11 @@ __global__ void normalize_weights_kernel(const float* __restrict__ logw, int64_t
 }
 
 // KLD block record (8 doubles): { m_p, S_p, A, m_q, S_q, n_inlier, n_posinf_q, n_total }
+// Inliers: lp > floor and lq > floor (floor = -inf for the KLD; the float64 underflow threshold of exp() for the
+// linear-domain JSD of the reference, divergences.py:170-173).
 __global__ void __launch_bounds__(256) kld_partials_kernel(const float* __restrict__ lp, const float* __restrict__ lq,
-                                                           int64_t n, double* __restrict__ block_partials) {
+                                                           int64_t n, float floor_,
+                                                           double* __restrict__ block_partials) {
   constexpr int E = 8, NW = 8;
   __shared__ float redf[2 * NW];
   __shared__ double redd[6 * NW];
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(256) kld_partials_kernel(const float* __restri
     p[e] = valid ? lp[i] : -INFINITY;
     q[e] = valid ? lq[i] : -INFINITY;
     // reference: inliers = (lp > -inf) & (lq > -inf)  (NaN compares false)  divergences.py:138-139
-    in[e] = valid && (p[e] > -INFINITY) && (q[e] > -INFINITY);
+    in[e] = valid && (p[e] > floor_) && (q[e] > floor_);
     if (valid) ntot += 1.f;
     if (in[e]) {
       if (p[e] < INFINITY) mp = fmaxf(mp, p[e]);
@@ -220,6 +223,68 @@ __global__ void kld_partials_merge_kernel(const double* __restrict__ bp, int64_t
   }
 }
 
+// JSD terms (divergences.py:183-195) from log densities and the inlier normalisers Lp, Lq of a kld_partials pass with
+// the same floor:  a = lp - Lp, b = lq - Lq, log m = logaddexp(a, b) - log 2,
+// term = 0.5 e^a (a - log m) + 0.5 e^b (b - log m); NaN terms are dropped and counted (:192).
+// out2 += { sum of terms (nats), dropped terms }   (float64 atomics; HBM-bound stream, 8 B per point)
+__global__ void __launch_bounds__(256) jsd_terms_kernel(const float* __restrict__ lp, const float* __restrict__ lq,
+                                                        int64_t n, float floor_, double Lp, double Lq,
+                                                        double* __restrict__ out2) {
+  __shared__ double red[2][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double sum = 0.0, dropped = 0.0;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float p = lp[i], q = lq[i];
+    if (!(p > floor_) || !(q > floor_)) continue;
+    const double a = static_cast<double>(p) - Lp, b = static_cast<double>(q) - Lq;
+    const double hi = fmax(a, b), lo = fmin(a, b);
+    const double lm = hi + log1p(exp(lo - hi)) - 0.69314718055994530942;
+    const double t = 0.5 * exp(a) * (a - lm) + 0.5 * exp(b) * (b - lm);
+    if (t == t) {
+      sum += t;
+    } else {
+      dropped += 1.0;
+    }
+  }
+  sum = warp_sum(sum);
+  dropped = warp_sum(dropped);
+  if (lane == 0) {
+    red[0][warp] = sum;
+    red[1][warp] = dropped;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    atomicAdd(out2 + threadIdx.x, t);
+  }
+}
+
+// Self-normalised expectation of a point set (statistics.py:39-45):  out[d] += sum_i x[i][d] exp(logw[i] - log_norm).
+// Elements are read flat (coalesced); the per-thread stride is a multiple of D so that a thread always sees the same
+// coordinate and keeps ONE float64 accumulator. 4 (D + 1) / D bytes per element, HBM-bound.
+__global__ void __launch_bounds__(256) weighted_mean_kernel(const float* __restrict__ x, int64_t n, int D,
+                                                            const float* __restrict__ logw, double log_norm,
+                                                            double* __restrict__ out) {
+  __shared__ double acc[AISB_MAX_DIMS];
+  const int T = (256 / D) * D;  // active threads: a multiple of D
+  if (threadIdx.x < D) acc[threadIdx.x] = 0.0;
+  __syncthreads();
+  if (threadIdx.x < T) {
+    const int64_t total = n * D;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * T;
+    double s = 0.0;
+    for (int64_t e = static_cast<int64_t>(blockIdx.x) * T + threadIdx.x; e < total; e += stride) {
+      const double w = exp(static_cast<double>(__ldg(logw + e / D)) - log_norm);
+      s += w * static_cast<double>(__ldg(x + e));
+    }
+    atomicAdd(&acc[threadIdx.x % D], s);
+  }
+  __syncthreads();
+  if (threadIdx.x < D) atomicAdd(out + threadIdx.x, acc[threadIdx.x]);
+}
+
 static int64_t reduce_blocks(int64_t n) { return (n + 2047) / 2048; }
 
 static int check_ws(void* d_ws, size_t ws_bytes, size_t need, double** out, const char* who) {
@@ -274,9 +339,15 @@ extern "C" int aisb_normalize_weights_f32(const float* d_logw, int64_t n, const 
 
 extern "C" int aisb_kld_partials_f32(const float* d_lp, const float* d_lq, int64_t n, double* d_out_partials,
                                      void* d_workspace, size_t workspace_bytes, void* stream) {
+  return aisb_pair_partials_f32(d_lp, d_lq, n, -INFINITY, d_out_partials, d_workspace, workspace_bytes, stream);
+}
+
+extern "C" int aisb_pair_partials_f32(const float* d_lp, const float* d_lq, int64_t n, float floor_,
+                                      double* d_out_partials, void* d_workspace, size_t workspace_bytes,
+                                      void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!d_out_partials || n < 0 || (n > 0 && (!d_lp || !d_lq))) {
-    set_error("kld_partials: null pointer or negative n");
+  if (!d_out_partials || n < 0 || (n > 0 && (!d_lp || !d_lq)) || floor_ != floor_) {
+    set_error("pair_partials: null pointer, negative n or NaN floor");
     return AISB_ERR_INVALID;
   }
   const int64_t nblocks = reduce_blocks(n);
@@ -284,10 +355,45 @@ extern "C" int aisb_kld_partials_f32(const float* d_lp, const float* d_lq, int64
   int rc = check_ws(d_workspace, workspace_bytes, sizeof(double) * 8 * (nblocks + 1), &bp, "kld_partials");
   if (rc) return rc;
   if (nblocks > 0) {
-    kld_partials_kernel<<<static_cast<unsigned>(nblocks), 256, 0, st>>>(d_lp, d_lq, n, bp);
+    kld_partials_kernel<<<static_cast<unsigned>(nblocks), 256, 0, st>>>(d_lp, d_lq, n, floor_, bp);
     AISB_LAUNCH_CHECK("kld_partials_kernel");
   }
   kld_partials_merge_kernel<<<1, 256, 0, st>>>(bp, nblocks, d_out_partials);
   AISB_LAUNCH_CHECK("kld_partials_merge_kernel");
+  return AISB_OK;
+}
+
+extern "C" int aisb_jsd_terms_f32(const float* d_lp, const float* d_lq, int64_t n, float floor_, double log_norm_p,
+                                  double log_norm_q, double* d_out2, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!d_out2 || n < 0 || (n > 0 && (!d_lp || !d_lq)) || floor_ != floor_) {
+    set_error("jsd_terms: null pointer, negative n or NaN floor");
+    return AISB_ERR_INVALID;
+  }
+  AISB_CUDA_CHECK(cudaMemsetAsync(d_out2, 0, 2 * sizeof(double), st));
+  if (n == 0) return AISB_OK;
+  const int64_t want = (n + 2047) / 2048;  // ~8 points per thread
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  jsd_terms_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, st>>>(d_lp, d_lq, n, floor_, log_norm_p,
+                                                                                  log_norm_q, d_out2);
+  AISB_LAUNCH_CHECK("jsd_terms_kernel");
+  return AISB_OK;
+}
+
+extern "C" int aisb_weighted_mean_f32(const float* d_x, int64_t n, int32_t D, const float* d_logw, double log_norm,
+                                      double* d_out, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!d_out || n < 0 || D < 1 || D > AISB_MAX_DIMS || (n > 0 && (!d_x || !d_logw))) {
+    set_error("weighted_mean: null pointer, negative n or D=%d outside 1..%d", D, AISB_MAX_DIMS);
+    return AISB_ERR_INVALID;
+  }
+  AISB_CUDA_CHECK(cudaMemsetAsync(d_out, 0, D * sizeof(double), st));
+  if (n == 0) return AISB_OK;
+  const int T = (256 / D) * D;
+  const int64_t want = (n * D + 8 * T - 1) / (8 * T);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  weighted_mean_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, st>>>(d_x, n, D, d_logw, log_norm,
+                                                                                      d_out);
+  AISB_LAUNCH_CHECK("weighted_mean_kernel");
   return AISB_OK;
 }

@@ -1,4 +1,5 @@
 from .base import CMetric
-from .divergences import CDivergence, CKLDivergence
+from .divergences import CDivergence, CJSDivergence, CKLDivergence
+from .statistics import CExpectedValueMSE
 
-__all__ = ["CMetric", "CDivergence", "CKLDivergence"]
+__all__ = ["CMetric", "CDivergence", "CKLDivergence", "CJSDivergence", "CExpectedValueMSE"]

@@ -1,5 +1,5 @@
-"""KL divergence metric with the reference's interface
-(reference ais_benchmarks/metrics/divergences.py:59-153).
+"""KL and JS divergence metrics with the reference's interface
+(reference ais_benchmarks/metrics/divergences.py:59-195).
 
 compute(p=, q=, nsamples=) draws uniform evaluation points on p's support, evaluates both log
 densities on the GPU (for q built by a sampler's KDE this is the pairwise N_eval x N_kde kernel)
@@ -10,6 +10,11 @@ and reduces them to the self-normalised discrete KL with ONE device pass
     KLD = sum_I exp(lp_i - Lp) (lp_i - lq_i) - Lp + Lq,   Lp = LSE_I lp,  Lq = LSE_I lq
 
 which equals the reference's normalise-in-log-space-then-sum (divergences.py:136-153) exactly.
+
+The JSD (divergences.py:156-195) reuses the same two device vectors: one pass for the inlier normalisers
+(aisb_pair_partials_f32 with the float64 underflow floor, the log-domain image of the reference's `prob > 0`),
+one pass for the terms (aisb_jsd_terms_f32). With `sharded = True` every rank evaluates its own rows and only
+the 8- and 2-double records travel (parallel.py).
 """
 import numpy as np
 import torch
@@ -33,6 +38,39 @@ def _log_prob_device(dist, x_dev, x_np_getter):
     return torch.from_numpy(lp).to(x_dev.device, torch.float32)
 
 
+def evaluation_points(metric, kwargs):
+    """The argument contract and the uniform evaluation points of CDivergence.compute / CExpectedValueMSE.compute
+    (divergences.py:77-87, statistics.py:29-37)."""
+    assert "p" in kwargs.keys() and hasattr(kwargs["p"], "log_prob"), \
+        "p must implement a log_prob method. p is of type %s" % (type(kwargs["p"]))
+    assert "q" in kwargs.keys() and hasattr(kwargs["q"], "log_prob"), \
+        "q must implement a log_prob method. q is of type %s" % (type(kwargs["q"]))
+    assert "nsamples" in kwargs.keys()
+    p = kwargs["p"]
+    lo, hi = p.support()[0], p.support()[1]
+    if metric.device_points:
+        _device.require_cuda()
+        dev = _device.device()
+        return _device.uniform_box(torch.from_numpy(np.asarray(lo, dtype=np.float32)).to(dev),
+                                   torch.from_numpy(np.asarray(hi, dtype=np.float32)).to(dev), int(kwargs["nsamples"]))
+    # same host RNG call as divergences.py:84-85, so np.random.seed reproduces the evaluation points
+    return np.random.uniform(lo, hi, size=(kwargs["nsamples"], p.dims))
+
+
+def device_log_probs(p, q, samples):
+    """(x, lp, lq) as float32 device tensors for the evaluation points `samples` (numpy or CUDA tensor)."""
+    dims = getattr(p, "dims", None) or samples.shape[-1]
+    x_dev, was_numpy = _device.to_device_points(samples, dims)
+    cache = {}
+
+    def x_np():
+        if "x" not in cache:
+            cache["x"] = samples if was_numpy else x_dev.cpu().numpy().astype(np.float64)
+        return cache["x"]
+
+    return x_dev, _log_prob_device(p, x_dev, x_np), _log_prob_device(q, x_dev, x_np)
+
+
 class CDivergence(CMetric):
     def __init__(self):
         super().__init__()
@@ -42,6 +80,8 @@ class CDivergence(CMetric):
         self.disjoint_support = True
         # True: evaluation points are drawn by the device Philox kernel instead of np.random.uniform
         self.device_points = False
+        # True (under torch.distributed): `samples` are this rank's rows; the partial records are merged over the ranks
+        self.sharded = False
 
     def pre(self, **kwargs):
         pass
@@ -53,23 +93,7 @@ class CDivergence(CMetric):
         pass
 
     def compute(self, **kwargs):
-        assert "p" in kwargs.keys() and hasattr(kwargs["p"], "log_prob"), \
-            "p must implement a log_prob method. p is of type %s" % (type(kwargs["p"]))
-        assert "q" in kwargs.keys() and hasattr(kwargs["q"], "log_prob"), \
-            "q must implement a log_prob method. q is of type %s" % (type(kwargs["q"]))
-        assert "nsamples" in kwargs.keys()
-        p = kwargs["p"]
-        lo, hi = p.support()[0], p.support()[1]
-        if self.device_points:
-            _device.require_cuda()
-            dev = _device.device()
-            samples = _device.uniform_box(torch.from_numpy(np.asarray(lo, dtype=np.float32)).to(dev),
-                                          torch.from_numpy(np.asarray(hi, dtype=np.float32)).to(dev),
-                                          int(kwargs["nsamples"]))
-        else:
-            # same host RNG call as divergences.py:84-85, so np.random.seed reproduces the evaluation points
-            samples = np.random.uniform(lo, hi, size=(kwargs["nsamples"], p.dims))
-        return self.compute_from_samples(p, kwargs["q"], samples)
+        return self.compute_from_samples(kwargs.get("p"), kwargs.get("q"), evaluation_points(self, kwargs))
 
     def compute_from_samples(self, p, q, samples):
         raise NotImplementedError
@@ -86,18 +110,15 @@ class CKLDivergence(CDivergence):
 
     def compute_from_samples(self, p, q, samples):
         """divergences.py:101-108 with both log densities and the reduction on the device."""
-        dims = getattr(p, "dims", None) or samples.shape[-1]
-        x_dev, was_numpy = _device.to_device_points(samples, dims)
-        cache = {}
+        _, lp, lq = device_log_probs(p, q, samples)
+        return self.compute_from_device_log_probs(lp, lq)
 
-        def x_np():
-            if "x" not in cache:
-                cache["x"] = samples if was_numpy else x_dev.cpu().numpy().astype(np.float64)
-            return cache["x"]
-
-        lp = _log_prob_device(p, x_dev, x_np)
-        lq = _log_prob_device(q, x_dev, x_np)
+    def compute_from_device_log_probs(self, lp, lq):
+        """The reduction alone, on float32 device vectors (shared with the fused evaluation loop)."""
         self.partials = _device.kld_partials(lp, lq).cpu().numpy()
+        if self.sharded:
+            from .. import parallel
+            self.partials = parallel.merge_kld_partials(parallel.all_gather_records(self.partials))
         self._warn(self.partials)
         self.value = _device.kld_finalize(self.partials)
         return self.value
@@ -153,3 +174,40 @@ class CKLDivergence(CDivergence):
                 q_samples_logprob[mask] -= Lq
             return res.cpu().numpy()
         return res
+
+
+class CJSDivergence(CDivergence):
+    """Jensen-Shannon divergence in bits (divergences.py:156-195), both densities and both reductions on the device."""
+
+    def __init__(self):
+        super().__init__()
+        self.name = "JSD"
+        self.type = "divergence"
+        self.is_symmetric = True
+        self.disjoint_support = False
+        self.log2 = np.log(2)
+        self.partials = None
+        self.dropped = 0
+
+    def compute_from_samples(self, p, q, samples):
+        _, lp, lq = device_log_probs(p, q, samples)
+        return self.compute_from_device_log_probs(lp, lq)
+
+    def compute_from_device_log_probs(self, lp, lq):
+        from .. import parallel
+        floor = _device._lib.LOG_TINY  # the reference filters on linear-domain prob > 0 (:170-173)
+        part = _device.pair_partials(lp, lq, floor).cpu().numpy()
+        if self.sharded:
+            part = parallel.merge_kld_partials(parallel.all_gather_records(part))
+        self.partials = part
+        if part[7] > 0 and part[5] / part[7] < .1:
+            print("WARNING. JSD compute. Only %6.3f%% inliers" % (part[5] / part[7] * 100))
+        if part[5] <= 0:
+            self.value = 0.0  # empty sums (:188-195)
+            return self.value
+        log_norm_p, log_norm_q = _device.pair_log_norms(part)
+        terms = _device.jsd_terms(lp, lq, floor, log_norm_p, log_norm_q)
+        terms = parallel.all_gather_records(terms).sum(axis=0) if self.sharded else terms.cpu().numpy()
+        self.dropped = int(terms[1])
+        self.value = float(terms[0] / self.log2)
+        return self.value

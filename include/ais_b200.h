@@ -189,6 +189,28 @@ void aisb_kld_partials_merge(const double* a, const double* b, double* out);
 double aisb_kld_finalize(const double* partials);
 
 /*
+ * JSD and EVMSE on the same (lp, lq) device vectors.
+ *   aisb_pair_partials_f32: aisb_kld_partials_f32 with the inlier set { lp > floor and lq > floor }. The JSD of the
+ *       reference works on linear-domain probabilities and keeps the pairs with p > 0 and q > 0
+ *       (metrics/divergences.py:165-173): in the log domain that is floor = AISB_LOG_TINY, below which float64 exp()
+ *       returns 0.
+ *   aisb_jsd_terms_f32: with a = lp - log_norm_p, b = lq - log_norm_q (the inlier normalisers m + log S of the
+ *       merged pair partials), log m = logaddexp(a, b) - log 2:
+ *       d_out2 = { sum_I 0.5 e^a (a - log m) + 0.5 e^b (b - log m)  [nats],  number of NaN terms dropped }
+ *       (divergences.py:180-192); JSD = d_out2[0] / log 2 (:194-195). d_out2 is zeroed by the call.
+ *   aisb_weighted_mean_f32: d_out[D] = sum_i x_i exp(d_logw[i] - log_norm), the self-normalised expectation of
+ *       metrics/statistics.py:39-45 when log_norm = LSE(d_logw) (aisb_logw_partials_f32 + aisb_weight_partials_logsum);
+ *       EVMSE = || E_p[x] - E_q[x] ||^2 (:46-48). d_out is zeroed by the call. 1 <= D <= AISB_MAX_DIMS.
+ */
+#define AISB_LOG_TINY (-745.13f)
+int aisb_pair_partials_f32(const float* d_lp, const float* d_lq, int64_t n, float floor, double* d_out_partials,
+                           void* d_workspace, size_t workspace_bytes, void* stream);
+int aisb_jsd_terms_f32(const float* d_lp, const float* d_lq, int64_t n, float floor, double log_norm_p,
+                       double log_norm_q, double* d_out2, void* stream);
+int aisb_weighted_mean_f32(const float* d_x, int64_t n, int32_t D, const float* d_logw, double log_norm,
+                           double* d_out, void* stream);
+
+/*
  * M-PMC Rao-Blackwellised moment accumulation (sampling_methods/m_pmc.py:57-61, 102-105):
  *   rho_{d,i} = exp(log alpha_d + log q_d(x_i) - log q(x_i)),
  *   out[d][0]      = sum_i w~_i rho_{d,i}            (alpha_d numerator)

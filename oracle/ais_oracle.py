@@ -275,3 +275,62 @@ def mvn_kld_closed_form(m0, S0, m1, S1):
     iS1 = np.linalg.inv(S1)
     diff = m1 - m0
     return 0.5 * (np.trace(iS1 @ S0) + diff @ iS1 @ diff - k + np.log(np.linalg.det(S1) / np.linalg.det(S0)))
+
+
+# ----------------------------------------------------------------------------------------------
+# JSD and EVMSE
+# ----------------------------------------------------------------------------------------------
+LOG_TINY = -745.13  # exp() of anything below is 0.0 in float64: the log-domain image of the reference's "prob > 0"
+
+
+def jsd_from_probs(p, q):
+    """metrics/divergences.py:165-195 on linear-domain probabilities: inliers = both > 0 and not NaN (:170-173),
+    normalise each side over the inliers (:180-181), m = (p + q) / 2 renormalised (:183-186),
+    0.5 p log(p/m) + 0.5 q log(q/m) (:188-189), NaN terms dropped (:192), divided by log 2 (:194-195)."""
+    p = np.array(p, dtype=np.float64)
+    q = np.array(q, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        inl = (p > 0) & (q > 0) & ~np.isnan(q) & ~np.isnan(p)
+        pn = p[inl] / np.sum(p[inl])
+        qn = q[inl] / np.sum(q[inl])
+        m = 0.5 * (pn + qn)
+        m = m / np.sum(m)
+        res = 0.5 * pn * np.log(pn / m) + 0.5 * qn * np.log(qn / m)
+        res = res[~np.isnan(res)]
+    return float(res.sum() / np.log(2))
+
+
+def jsd_from_log_probs(lp, lq):
+    """The same quantity from log densities (what the device path computes; the reference calls p.prob / q.prob, whose
+    underflow to 0.0 is the inlier threshold LOG_TINY here): a = lp - LSE_I(lp), b = lq - LSE_I(lq),
+    log m = logaddexp(a, b) - log 2, term = 0.5 e^a (a - log m) + 0.5 e^b (b - log m)."""
+    lp = np.asarray(lp, dtype=np.float64)
+    lq = np.asarray(lq, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        inl = (lp > LOG_TINY) & (lq > LOG_TINY)
+        if not inl.any():
+            return 0.0
+        a = lp[inl] - np.logaddexp.reduce(lp[inl])
+        b = lq[inl] - np.logaddexp.reduce(lq[inl])
+        lm = np.logaddexp(a, b) - np.log(2)
+        res = 0.5 * np.exp(a) * (a - lm) + 0.5 * np.exp(b) * (b - lm)
+        res = res[~np.isnan(res)]
+    return float(res.sum() / np.log(2))
+
+
+def expected_values(x, p, q):
+    """metrics/statistics.py:39-45: self-normalised expectations of the evaluation points under p and q."""
+    x = np.asarray(x, dtype=np.float64)
+    p = np.array(p, dtype=np.float64)
+    q = np.array(q, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        p = p / np.sum(p)
+        q = q / np.sum(q)
+    return np.sum(x * p.reshape(-1, 1), axis=0), np.sum(x * q.reshape(-1, 1), axis=0)
+
+
+def evmse(x, p, q):
+    """metrics/statistics.py:46-48: squared distance between the two expected values."""
+    ev_p, ev_q = expected_values(x, p, q)
+    d = ev_p - ev_q
+    return float(d @ d)

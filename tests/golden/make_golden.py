@@ -18,7 +18,8 @@ from oracle import ref_harness  # noqa: E402
 ref_harness.load()
 from ais_benchmarks.distributions import (CGaussianMixtureModel, CMixtureModel, CMultivariateNormal,  # noqa: E402
                                           CMultivariateUniform)
-from ais_benchmarks.metrics.divergences import CKLDivergence  # noqa: E402
+from ais_benchmarks.metrics.divergences import CJSDivergence, CKLDivergence  # noqa: E402
+from ais_benchmarks.metrics.statistics import CExpectedValueMSE  # noqa: E402
 from ais_benchmarks.sampling_methods import (CDeterministicMixtureAIS, CLayeredAIS, CMixturePMC,  # noqa: E402
                                              CTreePyramidSampling)
 from ais_benchmarks.sampling_methods.base import CMixtureSamplingMethod  # noqa: E402
@@ -208,6 +209,60 @@ def make_kde_kld():
     save("kde_kld", **out)
 
 
+class _FixedProbs:
+    """Stand-in distribution whose prob() returns a fixed vector (edge cases of the linear-domain metrics)."""
+
+    def __init__(self, probs):
+        self.probs = np.asarray(probs, dtype=np.float64)
+
+    def prob(self, samples):
+        return self.probs.copy()
+
+    log_prob = prob
+
+
+def make_metrics():
+    """JSD (metrics/divergences.py:156-195) and EVMSE (metrics/statistics.py:29-48) of the reference on the KDE
+    fixtures of kde_kld.npz (same p, q, evaluation points), plus edge cases with zero / NaN probabilities."""
+    g = np.load(os.path.join(OUT, "kde_kld.npz"))
+    out = {}
+    for i in range(int(g["n"])):
+        means, sigmas, weights = g["tmeans%d" % i], g["tsigmas%d" % i], g["tweights%d" % i]
+        dims = means.shape[1]
+        sup = [np.full(dims, -1.0), np.full(dims, 1.0)]
+        p = CGaussianMixtureModel({"means": means, "sigmas": sigmas, "weights": weights, "support": sup})
+        centres = g["centres%d" % i]
+        q = CGaussianMixtureModel({"means": centres, "sigmas": np.full(centres.shape, float(g["bw%d" % i])),
+                                   "support": sup})
+        x = g["x%d" % i]
+        assert np.allclose(q.log_prob(x), g["lq%d" % i], rtol=1e-12, atol=1e-12)
+        out["jsd%d" % i] = np.array(CJSDivergence().compute_from_samples(p, q, x.copy()))
+        out["evmse%d" % i] = np.array(CExpectedValueMSE().compute_from_samples(p, q, x.copy()))
+        pp, qq = p.prob(x), q.prob(x)
+        out["ev_p%d" % i] = np.sum(x * (pp / pp.sum()).reshape(-1, 1), axis=0)
+        out["ev_q%d" % i] = np.sum(x * (qq / qq.sum()).reshape(-1, 1), axis=0)
+    # closed-form-ish Gaussian pair: JSD of two unit normals one sigma apart, on seeded uniform points
+    pn = CMultivariateNormal({"mean": np.array([0.0]), "sigma": np.array([[1.0]])})
+    qn = CMultivariateNormal({"mean": np.array([1.0]), "sigma": np.array([[1.0]])})
+    np.random.seed(70)
+    xn = np.random.uniform(pn.support()[0], pn.support()[1], size=(20000, 1))
+    out["norm_x"] = xn
+    out["norm_jsd"] = np.array(CJSDivergence().compute_from_samples(pn, qn, xn.copy()))
+    out["norm_evmse"] = np.array(CExpectedValueMSE().compute_from_samples(pn, qn, xn.copy()))
+    # edge cases: zero probabilities on either side, NaN, a value that underflows after normalisation
+    ep = np.array([0.2, 0.0, 0.3, 0.1, np.nan, 0.4, 1e-300, 0.05])
+    eq = np.array([0.1, 0.2, 0.0, 0.3, 0.2, 0.4, 0.3, np.nan])
+    out["edge_p"], out["edge_q"] = ep, eq
+    with np.errstate(all="ignore"):
+        out["edge_jsd"] = np.array(CJSDivergence().compute_from_samples(_FixedProbs(ep), _FixedProbs(eq), np.zeros((8, 1))))
+    ex = np.arange(12, dtype=np.float64).reshape(6, 2) / 7.0
+    fp, fq = np.array([0.2, 0.0, 0.3, 0.1, 0.9, 0.4]), np.array([0.1, 0.2, 0.0, 0.3, 0.2, 0.4])
+    out["edge_x"], out["edge_fp"], out["edge_fq"] = ex, fp, fq
+    out["edge_evmse"] = np.array(CExpectedValueMSE().compute_from_samples(_FixedProbs(fp), _FixedProbs(fq), ex.copy()))
+    out["n"] = np.array(int(g["n"]))
+    save("metrics", **out)
+
+
 def make_mpmc():
     """Two M-PMC iterations (sampling_methods/m_pmc.py:80-118): the first from isotropic proposals, the second from the
     adapted ones (full covariance when the 10*I failsafe does not fire)."""
@@ -356,6 +411,7 @@ if __name__ == "__main__":
     make_mixture()
     make_dm_weights()
     make_kde_kld()
+    make_metrics()
     make_mpmc()
     make_lais()
     make_uniform()

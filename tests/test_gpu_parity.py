@@ -255,6 +255,70 @@ def test_kde_kld_golden(case):
     assert abs(val2 - ref) <= W_TOL * max(1.0, abs(ref))
 
 
+@pytest.mark.parametrize("case", range(3))
+def test_jsd_evmse_golden(case):
+    """CJSDivergence (divergences.py:156-195) and CExpectedValueMSE (statistics.py:29-48) on the KDE fixtures against
+    the values the reference returned for the same p, q and evaluation points."""
+    from ais_benchmarks_b200.metrics import CExpectedValueMSE, CJSDivergence
+    from ais_benchmarks_b200.sampling_methods.base import CDeviceKDE
+    g, k = load_golden("metrics"), load_golden("kde_kld")
+    target = gmm(k["tmeans%d" % case], k["tsigmas%d" % case], k["tweights%d" % case])
+    centres, bw, x = k["centres%d" % case], float(k["bw%d" % case]), k["x%d" % case]
+    kde = CDeviceKDE(torch.from_numpy(centres).cuda().float(), None, len(centres), bw, x.shape[1], [x.min(0), x.max(0)])
+    jsd = CJSDivergence()
+    val = jsd.compute_from_samples(target, kde, x)
+    ref = float(g["jsd%d" % case])
+    assert abs(val - ref) <= W_TOL * max(1.0, abs(ref)), (val, ref)
+    assert jsd.value == val and jsd.dropped == 0
+    ev = CExpectedValueMSE()
+    val = ev.compute_from_samples(target, kde, torch.from_numpy(x).cuda())  # device points in, same statistic
+    ref = float(g["evmse%d" % case])
+    assert abs(val - ref) <= W_TOL * max(1.0, abs(ref)), (val, ref)
+    assert np.allclose(ev.ev_p, g["ev_p%d" % case], atol=1e-4) and np.allclose(ev.ev_q, g["ev_q%d" % case], atol=1e-4)
+
+
+def test_jsd_evmse_edge_cases_and_compute():
+    from ais_benchmarks_b200.distributions import CMultivariateNormal, CMultivariateUniform
+    from ais_benchmarks_b200.metrics import CExpectedValueMSE, CJSDivergence
+    g = load_golden("metrics")
+    with np.errstate(all="ignore"):
+        lp = torch.from_numpy(np.log(g["edge_p"])).cuda().float()
+        lq = torch.from_numpy(np.log(g["edge_q"])).cuda().float()
+        fp = torch.from_numpy(np.log(g["edge_fp"])).cuda().float()
+        fq = torch.from_numpy(np.log(g["edge_fq"])).cuda().float()
+    # zero / NaN probabilities on either side are not inliers (divergences.py:170-173)
+    assert CJSDivergence().compute_from_device_log_probs(lp, lq) == pytest.approx(float(g["edge_jsd"]), rel=1e-5)
+    ex = torch.from_numpy(g["edge_x"]).cuda().float()
+    assert CExpectedValueMSE().compute_from_device_log_probs(ex, fp, fq) == pytest.approx(float(g["edge_evmse"]), rel=1e-4)
+    # empty inlier set -> 0.0; a NaN density -> NaN expectation, as in the reference
+    none = torch.full((5,), -np.inf, device="cuda")
+    assert CJSDivergence().compute_from_device_log_probs(none, torch.zeros(5, device="cuda")) == 0.0
+    assert np.isnan(CExpectedValueMSE().compute_from_device_log_probs(ex, lp[:6].contiguous(), fq))
+    # compute(): seeded host evaluation points reproduce the reference's value on the same points
+    p = CMultivariateNormal({"mean": np.array([0.0]), "sigma": np.array([[1.0]])})
+    q = CMultivariateNormal({"mean": np.array([1.0]), "sigma": np.array([[1.0]])})
+    np.random.seed(70)
+    assert CJSDivergence().compute(p=p, q=q, nsamples=20000) == pytest.approx(float(g["norm_jsd"]), abs=W_TOL)
+    np.random.seed(70)
+    assert CExpectedValueMSE().compute(p=p, q=q, nsamples=20000) == pytest.approx(float(g["norm_evmse"]), rel=W_TOL)
+    assert abs(CJSDivergence().compute(p=p, q=p, nsamples=5000)) < 1e-6
+    # disjoint supports: no inliers -> 0.0 (the reference warns and returns the empty sum)
+    pu = CMultivariateUniform({"center": np.array([0.0]), "radius": np.array([.1])})
+    qu = CMultivariateUniform({"center": np.array([1.0]), "radius": np.diag([.1])})
+    assert CJSDivergence().compute(p=pu, q=qu, nsamples=1000) == 0.0
+    with pytest.raises(AssertionError):
+        CJSDivergence().compute(p=p, q=object(), nsamples=10)
+    # D that does not divide the block (weighted_mean_kernel keeps (256 / D) * D threads active), large n
+    rs = np.random.RandomState(9)
+    for D in (1, 3, 7, 64):
+        x = rs.normal(size=(40001, D)).astype(np.float32)
+        lw = rs.normal(size=40001).astype(np.float32) * 3
+        from ais_benchmarks_b200 import _device
+        got = _device.weighted_mean(torch.from_numpy(x).cuda(), torch.from_numpy(lw).cuda(), 0.25).cpu().numpy()
+        ref = (x.astype(np.float64) * np.exp(lw.astype(np.float64) - 0.25)[:, None]).sum(0)
+        assert np.allclose(got, ref, rtol=1e-9, atol=1e-9)
+
+
 def test_kld_edge_cases_and_known_answers():
     from ais_benchmarks_b200.distributions import CMultivariateNormal, CMultivariateUniform
     from ais_benchmarks_b200.metrics import CKLDivergence

@@ -75,6 +75,32 @@ def test_kde_and_kld_match_reference():
     assert O.kld_from_log_probs(np.full(4, -np.inf), np.zeros(4)) == float(g["empty_kld"]) == 0.0
 
 
+def test_jsd_and_evmse_match_reference():
+    """metrics/divergences.py:156-195 and metrics/statistics.py:29-48 on the KDE fixtures, a Gaussian pair and the
+    zero / NaN edge cases; the log-domain JSD (what the device computes) must agree with the linear-domain one."""
+    g, k = load_golden("metrics"), load_golden("kde_kld")
+    with np.errstate(all="ignore"):
+        for i in range(int(g["n"])):
+            x, lp, lq = k["x%d" % i], k["lp%d" % i], k["lq%d" % i]
+            pp = O.gmm_prob(x, k["tmeans%d" % i], k["tsigmas%d" % i], k["tweights%d" % i])
+            qq = np.exp(lq)
+            assert O.jsd_from_probs(pp, qq) == pytest.approx(float(g["jsd%d" % i]), rel=1e-9)
+            assert O.jsd_from_log_probs(lp, lq) == pytest.approx(float(g["jsd%d" % i]), rel=1e-9)
+            assert O.evmse(x, pp, qq) == pytest.approx(float(g["evmse%d" % i]), rel=1e-9)
+            ev_p, ev_q = O.expected_values(x, pp, qq)
+            close(ev_p, g["ev_p%d" % i], 1e-10)
+            close(ev_q, g["ev_q%d" % i], 1e-10)
+        xn = g["norm_x"]
+        pn, qn = O.mvn_prob(xn, np.array([0.0]), np.eye(1)), O.mvn_prob(xn, np.array([1.0]), np.eye(1))
+        assert O.jsd_from_probs(pn, qn) == pytest.approx(float(g["norm_jsd"]), rel=1e-10)
+        assert O.jsd_from_log_probs(np.log(pn), np.log(qn)) == pytest.approx(float(g["norm_jsd"]), rel=1e-10)
+        assert O.evmse(xn, pn, qn) == pytest.approx(float(g["norm_evmse"]), rel=1e-10)
+        assert O.jsd_from_probs(g["edge_p"], g["edge_q"]) == pytest.approx(float(g["edge_jsd"]), rel=1e-12)
+        assert O.jsd_from_log_probs(np.log(g["edge_p"]), np.log(g["edge_q"])) == pytest.approx(float(g["edge_jsd"]), rel=1e-12)
+        assert O.evmse(g["edge_x"], g["edge_fp"], g["edge_fq"]) == pytest.approx(float(g["edge_evmse"]), rel=1e-12)
+    assert O.jsd_from_log_probs(np.full(3, -np.inf), np.zeros(3)) == 0.0
+
+
 def test_kld_known_answers_of_reference_tests():
     """tests/metrics/test_metric_kldivergence.py:77-135: within 1 % of the closed-form Gaussian KL on 1e5 uniform
     points; and identical (to rounding) to what the reference itself returned on the same seeded points."""

@@ -43,7 +43,20 @@ def _worker(rank, world, port, out_dir):
     ness = _device.weight_ess(rec) / rec[3]
     t = torch.full((3,), float(rank + 1), dtype=torch.float64)
     parallel.all_reduce_sum(t)
-    np.save(os.path.join(out_dir, "r%d.npy" % rank), np.array([kld, ness, rec[3], t[0].item(), s, e]))
+    # JSD / EVMSE with sharded evaluation points: the record exchange of CJSDivergence / CExpectedValueMSE (sharded=True)
+    x = g["x1"]
+    pair = parallel.merge_kld_partials(parallel.all_gather_records(_kld_record(lp[s:e], lq[s:e])))
+    Lp, Lq = _device.pair_log_norms(pair)
+    a, b = lp[s:e] - Lp, lq[s:e] - Lq
+    lm = np.logaddexp(a, b) - np.log(2)
+    terms = np.array([(0.5 * np.exp(a) * (a - lm) + 0.5 * np.exp(b) * (b - lm)).sum(), 0.0])
+    jsd = parallel.all_gather_records(terms).sum(axis=0)[0] / np.log(2)
+    evs = []
+    for lw_ in (lp, lq):
+        norm = _device.weight_logsum(parallel.global_weight_partials(_weight_record(lw_[s:e])))
+        evs.append(parallel.all_gather_records((x[s:e] * np.exp(lw_[s:e] - norm)[:, None]).sum(axis=0)).sum(axis=0))
+    evmse = float((evs[0] - evs[1]) @ (evs[0] - evs[1]))
+    np.save(os.path.join(out_dir, "r%d.npy" % rank), np.array([kld, ness, rec[3], t[0].item(), s, e, jsd, evmse]))
     dist.destroy_process_group()
 
 
@@ -53,11 +66,14 @@ def test_world2_gloo_partials(tmp_path):
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     g = load_golden("kde_kld")
     gw = load_golden("dm_weights")
+    gm = load_golden("metrics")
     res = [np.load(os.path.join(str(tmp_path), "r%d.npy" % r)) for r in range(world)]
     for r in res:
         assert r[0] == pytest.approx(float(g["kld1"]), rel=1e-10)      # KLD over the union of both shards
         assert r[1] == pytest.approx(float(gw["ness1"]), rel=1e-10)    # NESS from the merged weight record
         assert r[2] == len(gw["w1"]) and r[3] == 3.0
+        assert r[6] == pytest.approx(float(gm["jsd1"]), rel=1e-9)      # JSD / EVMSE from merged records
+        assert r[7] == pytest.approx(float(gm["evmse1"]), rel=1e-9)
     assert res[0][0] == res[1][0]                                      # identical on every rank
     n = len(g["lp1"])
     assert (res[0][4], res[0][5], res[1][4], res[1][5]) == (0, n // 2, n // 2, n)
