@@ -283,6 +283,16 @@ def check_partials(p):
     return p
 
 
+def mixture_component_draws(weights, n, dev):
+    """n component indices of a mixture with host weights `weights` (CMixtureModel.py:79-83). When every weight has
+    been zeroed (degenerate adaptation) the reference's np.random.multinomial(1, zeros) puts its one count in the
+    LAST category, so every draw comes from the last component; replicated here."""
+    w = np.asarray(weights, dtype=np.float64)
+    if not (w.sum() > 0):
+        return torch.full((int(n),), len(w) - 1, dtype=torch.int64, device=dev)
+    return torch.multinomial(torch.from_numpy(w).to(dev), int(n), replacement=True)
+
+
 def logw_partials(logw):
     lib = require_cuda()
     n = logw.shape[0]

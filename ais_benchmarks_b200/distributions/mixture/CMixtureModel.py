@@ -154,10 +154,7 @@ class CMixtureModel(CDistribution):
         kind, packed = self._packed()
         dev = _device.device()
         n = int(n_samples)
-        w = torch.from_numpy(np.asarray(self.weights, dtype=np.float64)).to(dev)
-        if float(w.sum()) <= 0:
-            raise ValueError("cannot sample from a mixture whose weights are all zero")
-        idx = torch.multinomial(w, n, replacement=True)
+        idx = _device.mixture_component_draws(self.weights, n, dev)
         if kind == "gauss":
             means, cov, ckind = gaussian_pack_args(self.models)
             z = _device.sample_iso(torch.zeros((1, self.dims), dtype=torch.float32, device=dev), n, 1.0)

@@ -306,6 +306,9 @@ def foreign_target_logp(target_d, x_dev):
     return torch.from_numpy(lp).to(x_dev.device, torch.float32)
 
 
+mixture_component_draws = _device.mixture_component_draws
+
+
 def multinomial_resample(logw, n_draws):
     """n_draws indices ~ Categorical(w / sum w), w = exp(logw) (dm_ais.py:47-54). Invalid (NaN / +inf) weights
     count as zero. Inverse-CDF on the device: cumsum + searchsorted, float64."""

@@ -20,7 +20,8 @@ from .. import _device
 from .._lib import COV_FULL
 from ..distributions import CMixtureModel, CMultivariateNormal
 from ..distributions.mixture.CMixtureModel import sanitize_weights
-from .base import CMixtureISSamplingMethod, foreign_target_logp, target_device_mixture
+from .base import (CMixtureISSamplingMethod, foreign_target_logp, mixture_component_draws,
+                   target_device_mixture)
 
 
 class CMixturePMC(CMixtureISSamplingMethod):
@@ -89,8 +90,7 @@ class CMixturePMC(CMixtureISSamplingMethod):
     def _sample_device(self, n):
         """Ancestral sampling from the proposal mixture on the device (m_pmc.py:86 -> CMixtureModel.sample)."""
         dev = _device.device()
-        w = torch.from_numpy(self._mix_weights).to(dev)
-        idx = torch.multinomial(w, int(n), replacement=True)
+        idx = mixture_component_draws(self._mix_weights, n, dev)
         z = _device.sample_iso(torch.zeros((1, self.ndims), dtype=torch.float32, device=dev), int(n), 1.0)
         L = np.linalg.cholesky(0.5 * (self._covs + np.transpose(self._covs, (0, 2, 1))))
         Ld = torch.from_numpy(L).to(dev, torch.float32)[idx]

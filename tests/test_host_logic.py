@@ -210,3 +210,63 @@ def test_tpais_rejects_dead_reference_methods():
         CTreePyramidSampling(dict(base, method="bogus"))
     with pytest.raises(AssertionError):
         CTreePyramidSampling(dict(base, method="simple", kernel="triangle"))
+
+
+def test_benchmark_loaders_and_results_round_trip(tmp_path):
+    """benchmark/CBenchmark.py: the reference's YAML schema (CBenchmark.py:58-137), its results.txt row format (:318-326)
+    and the skip-with-a-note rule for methods that are not on the accelerated path."""
+    import os
+    from ais_benchmarks_b200.benchmark import CBenchmark
+    from ais_benchmarks_b200.benchmark.CBenchmark import _literal, time_to_hms
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ais_benchmarks_b200", "benchmark")
+    b = CBenchmark()
+    b.load_config(os.path.join(here, "def_config.yaml"))
+    assert b.metrics == ["KLD", "JSD", "EVMSE", "T"] and b.n_experiments == 1 and b.rseed == 0
+    b.load_benchmark(os.path.join(here, "def_benchmark.yaml"))
+    assert [t.name for t in b.targets] == ["gmm", "gmm", "normal"] and b.ndims == [1, 2, 1]
+    assert b.nsamples == [500, 1000, 1000] and b.eval_sampl == [2000] * 3 and b.batch_sizes == [2] * 3
+    assert isinstance(b.targets[0], CGaussianMixtureModel) and isinstance(b.targets[2], CMultivariateNormal)
+    assert _literal("'simple'") == "simple" and _literal(0.9) == 0.9 and _literal("[1, 2]") == [1, 2]
+    assert _literal("np.zeros(3)") == "np.zeros(3)"  # not a literal: left alone, never evaluated
+    assert time_to_hms(3723.5) == (1, 2, 3.5)
+    bad = tmp_path / "bad.yaml"
+    bad.write_text("targets:\n  - {name: x, type: Banana2D, params: {}, batch_size: 1, nsamples: 1, nsamples_eval: 1}\n")
+    with pytest.raises(ValueError):
+        b.load_benchmark(str(bad))
+
+    class Method:
+        name, num_proposal_samples, num_proposal_evals, num_target_evals = "dm_ais", 150, 750, 150
+        get_NESS = staticmethod(lambda: 0.4321)
+        get_acceptance_rate = staticmethod(lambda: 1.0)
+
+    class Target:
+        dims, name = 2, "gmm"
+
+    out = tmp_path / "results.txt"
+    out.write_text(CBenchmark.results_header(["KLD", "JSD", "T"]))
+    CBenchmark.write_results({"KL": 1.25, "JSD": 0.5, "time": 0.001}, Method, Target, 150, str(out))
+    CBenchmark.write_results({"KL": 0.75, "JSD": 0.25, "time": 0.002}, Method, Target, 300, str(out))
+    lines = out.read_text().splitlines()
+    assert lines[0] == "dims output_samples KLD JSD T NESS method target_d accept_rate proposal_samples proposal_evals target_evals"
+    assert lines[1] == "02 0150   1.25000   0.50000   0.00100    0.432 dm_ais gmm 1.000 150 750 150"
+    table = CBenchmark.read_results(str(out))
+    assert table["output_samples"] == [150.0, 300.0] and table["KLD"] == [1.25, 0.75] and table["method"] == ["dm_ais"] * 2
+
+
+@no_gpu
+def test_benchmark_methods_and_no_cpu_fallback(tmp_path):
+    import os
+    from ais_benchmarks_b200.benchmark import CBenchmark
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ais_benchmarks_b200", "benchmark")
+    y = tmp_path / "m.yaml"
+    y.write_text("methods:\n  - {name: rej, type: CRejectionSampling, debug: false, params: {scaling: 1}}\n")
+    b = CBenchmark()
+    b.load_methods(str(y), np.array([-1.0]), np.array([1.0]), 1)
+    assert b.methods == [] and b.skipped_methods == ["rej"]
+    b.load_methods(os.path.join(here, "def_methods.yaml"), np.array([-1.0]), np.array([1.0]), 1)
+    assert [m.name for m in b.methods] == ["m_pmc", "TP_AISr_ESS90", "lais", "dm_ais"] and b.skipped_methods == []
+    assert b.methods[1].method == "simple" and b.methods[3].K == 10
+    b.load_benchmark(os.path.join(here, "def_benchmark.yaml"))
+    with pytest.raises(AisbError):  # no CPU fallback: the evaluation loop fails loudly without CUDA
+        CBenchmark.evaluate_method(1, b.targets[2], b.methods[3], max_samples=50, sampling_eval_samples=100,
+                                   metrics=["KLD"], n_reps=1, batch_size=2)
