@@ -238,20 +238,23 @@ def tc_operand(mix):
     return mix._tc_operand if mix._tc_operand.screen_error <= TC_MAX_SCREEN_ERROR else None
 
 
-def dm_weights(x, target, logp_in, proposals, want_logp=False, want_logq=False, hint=None):
+def dm_weights(x, target, logp_in, proposals, want_logp=False, want_logq=False, hint=None, out_logw=None,
+               out_partials=None):
     """DM weights. Without `hint`: the fused CUDA-core kernel (C ABI aisb_dm_weights_f32). With `hint` (int32 CUDA [n],
     the proposal each sample was drawn from) and an eligible proposal mixture: proposal density on the tensor cores
-    (aisb_dm_weights_hinted_f32). Returns (logw, logp|None, logq|None, partials[4] device f64)."""
+    (aisb_dm_weights_hinted_f32). Returns (logw, logp|None, logq|None, partials[4] device f64). out_logw [n] float32 /
+    out_partials [4] float64 (contiguous CUDA views) receive the results in place when given (streamed weighting)."""
     lib = require_cuda()
     operand = tc_operand(proposals) if hint is not None and x.shape[0] > 0 else None
     if operand is not None:
-        return _dm_weights_hinted(lib, x, target, logp_in, proposals, operand, want_logp, want_logq, hint)
+        return _dm_weights_hinted(lib, x, target, logp_in, proposals, operand, want_logp, want_logq, hint, out_logw,
+                                  out_partials)
     n = x.shape[0]
     dev = x.device
-    logw = torch.empty(n, dtype=torch.float32, device=dev)
+    logw = torch.empty(n, dtype=torch.float32, device=dev) if out_logw is None else out_logw
     logp = torch.empty(n, dtype=torch.float32, device=dev) if want_logp else None
     logq = torch.empty(n, dtype=torch.float32, device=dev) if want_logq else None
-    partials = torch.empty(4, dtype=torch.float64, device=dev)
+    partials = torch.empty(4, dtype=torch.float64, device=dev) if out_partials is None else out_partials
     Kmax = max(proposals.K, target.K if target is not None else 1)
     ws = workspace_for(max(n, 1), Kmax, proposals.D)
     check(lib.aisb_dm_weights_f32(_ptr(x), n, target.ref() if target is not None else None, _ptr(logp_in),
@@ -260,12 +263,13 @@ def dm_weights(x, target, logp_in, proposals, want_logp=False, want_logq=False, 
     return logw, logp, logq, partials
 
 
-def _dm_weights_hinted(lib, x, target, logp_in, proposals, operand, want_logp, want_logq, hint):
+def _dm_weights_hinted(lib, x, target, logp_in, proposals, operand, want_logp, want_logq, hint, out_logw=None,
+                       out_partials=None):
     n, dev = x.shape[0], x.device
-    logw = torch.empty(n, dtype=torch.float32, device=dev)
+    logw = torch.empty(n, dtype=torch.float32, device=dev) if out_logw is None else out_logw
     logp = torch.empty(n, dtype=torch.float32, device=dev) if want_logp else None
     logq = torch.empty(n, dtype=torch.float32, device=dev) if want_logq else None
-    partials = torch.empty(4, dtype=torch.float64, device=dev)
+    partials = torch.empty(4, dtype=torch.float64, device=dev) if out_partials is None else out_partials
     Kmax = max(proposals.K, target.K if target is not None else 1)
     ws = workspace_for(n, Kmax, proposals.D)
     hint = hint.to(device=dev, dtype=torch.int32).contiguous()
@@ -310,6 +314,85 @@ def normalize_weights(logw, partials_host):
     p = (C.c_double * 4)(*[float(v) for v in partials_host])
     check(lib.aisb_normalize_weights_f32(_ptr(logw), n, p, _ptr(out), stream_ptr()), "aisb_normalize_weights_f32")
     return out
+
+
+def merge_weight_records(records):
+    """records: float64 CUDA [G, 4] (one weight record per rank / streamed chunk) -> merged record, float64 CUDA [4].
+    Device-side counterpart of aisb_weight_partials_merge: no host synchronisation (C ABI aisb_weight_records_merge)."""
+    lib = require_cuda()
+    records = records.reshape(-1, 4).contiguous()
+    out = torch.empty(4, dtype=torch.float64, device=records.device)
+    check(lib.aisb_weight_records_merge(_ptr(records), records.shape[0], _ptr(out), stream_ptr()),
+          "aisb_weight_records_merge")
+    return out
+
+
+def merge_kld_records(records):
+    """records: float64 CUDA [G, 8] -> merged KLD record, float64 CUDA [8] (C ABI aisb_kld_records_merge)."""
+    lib = require_cuda()
+    records = records.reshape(-1, 8).contiguous()
+    out = torch.empty(8, dtype=torch.float64, device=records.device)
+    check(lib.aisb_kld_records_merge(_ptr(records), records.shape[0], _ptr(out), stream_ptr()),
+          "aisb_kld_records_merge")
+    return out
+
+
+def normalize_weights_dev(logw, record, out=None):
+    """Normalised weights from a (merged) weight record that stays in HBM (C ABI aisb_normalize_weights_dev_f32).
+    -> (w float32 CUDA [n], stats float64 CUDA [3] = {log sum w, ESS, n_finite}); nothing is read back here."""
+    lib = require_cuda()
+    n = logw.shape[0]
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=logw.device)
+    stats = torch.empty(3, dtype=torch.float64, device=logw.device)
+    check(lib.aisb_normalize_weights_dev_f32(_ptr(logw), n, _ptr(record), _ptr(out), _ptr(stats), stream_ptr()),
+          "aisb_normalize_weights_dev_f32")
+    return out, stats
+
+
+_copy_streams = {}
+
+
+def _copy_stream():
+    dev = torch.cuda.current_device()
+    if dev not in _copy_streams:
+        _copy_streams[dev] = torch.cuda.Stream(device=dev)
+    return _copy_streams[dev]
+
+
+def dm_weights_streamed(x_host, target, proposals, hint=None, chunk_rows=None, x_out=None):
+    """DM weights of a HOST-resident (ideally pinned) float32 sample matrix [n, D]: the rows are copied to HBM in chunks
+    on a copy stream while the weight kernel works on the previous chunk, so the PCIe transfer hides the arithmetic.
+    Every chunk leaves one weight record; they are merged on the device. -> (x_dev, logw, merged record [4] CUDA f64).
+    `hint`: int32 CUDA [n] as in dm_weights."""
+    require_cuda()
+    n, D = x_host.shape
+    dev = device()
+    xd = torch.empty((n, D), dtype=torch.float32, device=dev) if x_out is None else x_out
+    logw = torch.empty(n, dtype=torch.float32, device=dev)
+    if chunk_rows is None:
+        # ~8 chunks, each a multiple of 1024 rows (keeps every chunk 16-byte aligned and tile-aligned), >= 64k rows
+        chunk_rows = max(65536, ((n + 7) // 8 + 1023) // 1024 * 1024)
+    bounds = list(range(0, n, chunk_rows)) + [n]
+    nchunks = max(1, len(bounds) - 1)
+    records = torch.empty((nchunks, 4), dtype=torch.float64, device=dev)
+    main, side = torch.cuda.current_stream(), _copy_stream()
+    side.wait_stream(main)           # xd / logw allocations and earlier users of a recycled block
+    events = []
+    with torch.cuda.stream(side):
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            xd[a:b].copy_(x_host[a:b], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            events.append(ev)
+    if n == 0:
+        dm_weights(xd, target, None, proposals, hint=hint, out_logw=logw, out_partials=records[0])
+    for c, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
+        main.wait_event(events[c])
+        dm_weights(xd[a:b], target, None, proposals, hint=None if hint is None else hint[a:b], out_logw=logw[a:b],
+                   out_partials=records[c])
+    xd.record_stream(side)
+    return xd, logw, (records[0] if nchunks == 1 else merge_weight_records(records))
 
 
 def kld_partials(lp, lq):

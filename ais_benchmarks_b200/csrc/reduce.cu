@@ -25,7 +25,8 @@ __global__ void weight_partials_merge_kernel(const double* __restrict__ bp, int6
     const double f = exp(bp[4 * b] - M);
     s1 += bp[4 * b + 1] * f;
     s2 += bp[4 * b + 2] * f * f;
-    cnt += bp[4 * b + 3];
+    // a record poisoned by an aborted tensor-core kernel (n_valid = -1) poisons the merged record
+    cnt += bp[4 * b + 3] < 0.0 ? -1.0e300 : bp[4 * b + 3];
   }
   s1 = warp_sum(s1);
   s2 = warp_sum(s2);
@@ -47,7 +48,7 @@ __global__ void weight_partials_merge_kernel(const double* __restrict__ bp, int6
     out4[0] = M;
     out4[1] = a;
     out4[2] = b2;
-    out4[3] = c;
+    out4[3] = c < 0.0 ? -1.0 : c;
   }
 }
 
@@ -74,6 +75,40 @@ __global__ void normalize_weights_kernel(const float* __restrict__ logw, int64_t
   if (p >= n) return;
   // (lw - M) is exact-ish near the maximum where the weights are largest; logS is O(log n)
   out[p] = expf((logw[p] - M) - logS);
+}
+
+// Same, with the (merged) record in device memory: thread 0 derives the two constants, block 0 also writes the
+// summary statistics {log sum w, ESS, n_finite}.
+__global__ void __launch_bounds__(256) normalize_weights_dev_kernel(const float* __restrict__ logw, int64_t n,
+                                                                    const double* __restrict__ rec,
+                                                                    float* __restrict__ out,
+                                                                    double* __restrict__ stats) {
+  __shared__ float shc[2];
+  if (threadIdx.x == 0) {
+    const double M = rec[0], S1 = rec[1], S2 = rec[2];
+    const float Mf = static_cast<float>(M);
+    shc[0] = Mf;
+    shc[1] = static_cast<float>(log(S1) + (M - static_cast<double>(Mf)));
+    if (blockIdx.x == 0 && stats) {
+      stats[0] = M + log(S1);
+      stats[1] = S2 > 0.0 ? S1 * S1 / S2 : 0.0;
+      stats[2] = rec[3];
+    }
+  }
+  __syncthreads();
+  const float M = shc[0], logS = shc[1];
+  const int64_t base = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
+  if (base + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(logw + base);
+    float4 r;
+    r.x = expf((v.x - M) - logS);
+    r.y = expf((v.y - M) - logS);
+    r.z = expf((v.z - M) - logS);
+    r.w = expf((v.w - M) - logS);
+    *reinterpret_cast<float4*>(out + base) = r;
+  } else {
+    for (int64_t p = base; p < n; ++p) out[p] = expf((logw[p] - M) - logS);
+  }
 }
 
 // KLD block record (8 doubles): { m_p, S_p, A, m_q, S_q, n_inlier, n_posinf_q, n_total }
@@ -334,6 +369,46 @@ extern "C" int aisb_normalize_weights_f32(const float* d_logw, int64_t n, const 
   normalize_weights_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_logw, n, M, logS, d_out_w);
   AISB_LAUNCH_CHECK("normalize_weights_kernel");
+  return AISB_OK;
+}
+
+extern "C" int aisb_weight_records_merge(const double* d_records, int64_t n_records, double* d_out_partials,
+                                         void* stream) {
+  if (!d_records || !d_out_partials || n_records < 1) {
+    set_error("weight_records_merge: null pointer or n_records < 1");
+    return AISB_ERR_INVALID;
+  }
+  weight_partials_merge_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_records, n_records, d_out_partials);
+  AISB_LAUNCH_CHECK("weight_partials_merge_kernel");
+  return AISB_OK;
+}
+
+extern "C" int aisb_kld_records_merge(const double* d_records, int64_t n_records, double* d_out_partials,
+                                      void* stream) {
+  if (!d_records || !d_out_partials || n_records < 1) {
+    set_error("kld_records_merge: null pointer or n_records < 1");
+    return AISB_ERR_INVALID;
+  }
+  kld_partials_merge_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_records, n_records, d_out_partials);
+  AISB_LAUNCH_CHECK("kld_partials_merge_kernel");
+  return AISB_OK;
+}
+
+extern "C" int aisb_normalize_weights_dev_f32(const float* d_logw, int64_t n, const double* d_partials, float* d_out_w,
+                                              double* d_out_stats, void* stream) {
+  if (n < 0 || !d_partials || (n > 0 && (!d_logw || !d_out_w))) {
+    set_error("normalize_weights_dev: null pointer or negative n");
+    return AISB_ERR_INVALID;
+  }
+  if ((reinterpret_cast<uintptr_t>(d_logw) | reinterpret_cast<uintptr_t>(d_out_w)) & 15) {
+    set_error("normalize_weights_dev: d_logw and d_out_w must be 16-byte aligned");
+    return AISB_ERR_INVALID;
+  }
+  // n == 0 still launches one block so that the statistics are written
+  const int64_t blocks = n > 0 ? (n + 1023) / 1024 : 1;
+  normalize_weights_dev_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_logw, n, d_partials, d_out_w, d_out_stats);
+  AISB_LAUNCH_CHECK("normalize_weights_dev_kernel");
   return AISB_OK;
 }
 

@@ -51,6 +51,26 @@ def all_gather_records(record):
     return out.cpu().numpy().reshape(ws, -1)
 
 
+def all_gather_records_dev(record):
+    """record: 1-D float64 tensor on the communication device -> [world, len] tensor on the same device, identical on
+    every rank. With NCCL nothing is copied to the host and nothing synchronises: the gather is stream-ordered."""
+    _, ws = world()
+    rec = record.reshape(1, -1)
+    if ws == 1:
+        return rec
+    rec = rec.contiguous()
+    out = torch.empty((ws, rec.shape[1]), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(out, rec)
+    return out
+
+
+def global_weight_record_dev(local_record):
+    """Device-resident counterpart of global_weight_partials: all ranks' weight records gathered over NCCL and merged
+    by a one-block kernel; the result (float64 CUDA [4]) feeds _device.normalize_weights_dev without a host round trip."""
+    recs = all_gather_records_dev(local_record)
+    return local_record if recs.shape[0] == 1 else _device.merge_weight_records(recs)
+
+
 def merge_weight_partials(records):
     acc = np.asarray(records[0], dtype=np.float64)
     for r in records[1:]:

@@ -258,36 +258,57 @@ def run_cuda(args):
     dm_kernel = []
 
     def dm_step(resident=True):
-        xd = xs if resident else xs_pin.to(dev, non_blocking=True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        logw, _, _, part = _device.dm_weights(xd, tmix, None, qmix, hint=own)   # target (CUDA cores) + proposals (tcgen05)
-        e1.record()
-        g = parallel.global_weight_partials(_device.check_partials(part.cpu().numpy()))   # 4 doubles D2H (+ all-gather)
-        wn = _device.normalize_weights(logw, g)                          # normalised weights stay in HBM
-        dm_kernel.append((e0, e1))
-        return _device.weight_ess(g) / n_total, wn
+        """One weighting of the whole sample set: log pi, log q over all proposals, log w, the normaliser / ESS record,
+        its cross-rank merge and the normalised weights. Nothing in a resident step touches the host: the record is
+        all-gathered over NCCL and merged by a one-block kernel, the statistics {log sum w, ESS, n} stay in HBM until
+        somebody reads them. resident=False: the samples start in pinned host memory and are streamed to HBM in
+        chunks under the weight kernel (the public streamed entry point), and the statistics are read back."""
+        if resident:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            logw, _, _, part = _device.dm_weights(xs, tmix, None, qmix, hint=own)  # target (CUDA cores) + proposals (tcgen05)
+            e1.record()
+            dm_kernel.append((e0, e1))
+        else:
+            _, logw, part = _device.dm_weights_streamed(xs_pin, tmix, qmix, hint=own, x_out=xs_stage)
+        g = parallel.global_weight_record_dev(part)                     # device all-gather + merge kernel
+        wn, stats = _device.normalize_weights_dev(logw, g)              # normalised weights + statistics stay in HBM
+        return stats, wn
 
+    def dm_result(stats):
+        st = stats.cpu().numpy()                                         # 3 doubles D2H
+        if st[2] < 0:
+            raise RuntimeError("tensor-core kernel aborted: barrier protocol time-out")
+        return st[1] / n_total
+
+    xs_stage = torch.empty_like(xs)
     for _ in range(args.warmup):
-        ness, _ = dm_step()
+        stats, _ = dm_step()
+    ness = dm_result(stats)
     dm_kernel.clear()
     barrier()
     t0.record()
+    pending = []
     for _ in range(args.steps):
-        ness, _ = dm_step()
+        stats, _ = dm_step()
+        pending.append(stats)
     t1.record()
     barrier()
     dm_ms = max_over_ranks(t0.elapsed_time(t1)) / args.steps
+    ness_steps = [dm_result(st) for st in pending]                      # every timed step's result is checked
+    assert all(abs(v - ness) <= 1e-9 * max(1.0, abs(ness)) for v in ness_steps), (ness, ness_steps)
     dm_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in dm_kernel]))
     dm_kernel.clear()
-    dm_step(resident=False)
+    stats, _ = dm_step(resident=False)
+    ness_e = dm_result(stats)
     barrier()
     w0 = time.perf_counter()
     for _ in range(args.steps):
-        ness_e, wn = dm_step(resident=False)
-        _ = wn[:1].cpu()
+        stats, wn = dm_step(resident=False)
+        ness_e = dm_result(stats)                                        # host reads the step's result every step
     barrier()
     dm_e2e_ms = max_over_ranks((time.perf_counter() - w0) * 1e3) / args.steps
+    assert abs(ness_e - ness) <= 1e-6 * max(1.0, abs(ness)), (ness_e, ness)
     dm_flops = float(n_local) * (N * (3 * D2 + 6) + dc["modes"] * (4 * D2 + 6))
     dm_tflops = dm_flops / (dm_kernel_ms * 1e-3) / 1e12
 
@@ -334,7 +355,10 @@ def run_cuda(args):
             "gpu_launches": 6 * args.steps,
             "clocks": clock_info,
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / fp32_peak_tflops, "traffic": None,
+                         "frac": achieved_tflops / fp32_peak_tflops,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch (ncu --set full capture,
+                         # profiles/r1_ncu_kde_kernel_fullsize_v5.txt); algorithmic bytes: 68 MB
+                         "traffic": 100072192 if (world == 1 and scale == 1.0) else None,
                          "kernel": "logpdf_kernel<ISO_SHARED, 8, no offsets>", "kernel_ms": pair_kernel_ms,
                          "flop_per_pair": flop_per_pair,
                          "peak_source": "live FFMA micro-benchmark in this run (aisb_peak_fma_f32); nominal 74.5",
@@ -348,7 +372,7 @@ def run_cuda(args):
                                               "proposals, sigma=0.05; samples sharded over %d GPU(s)" %
                                               (n_total, N, world), "ness": ness},
                        "e2e": {"value": n_total / (dm_e2e_ms * 1e-3), "unit": "samples/s",
-                               "h2d_bytes_per_step": int(xs_pin.numel() * 4), "d2h_bytes_per_step": 36,
+                               "h2d_bytes_per_step": int(xs_pin.numel() * 4), "d2h_bytes_per_step": 24,
                                "ms_per_step": dm_e2e_ms},
                        # the proposal density runs on the tensor cores (tc_logq_kernel): its epilogue reads one FP32
                        # accumulator per (sample, proposal) pair out of TMEM, and that read (64 B/clk/SM per the
@@ -365,7 +389,9 @@ def run_cuda(args):
                                                   "peak_pairs_per_s": ex2_peak,
                                                   "note": "peak = 16 accumulator words per clk per SM = the measured "
                                                           "MUFU.EX2 rate; achieved includes the target pass"}},
-                       "gpu_launches": 6 * args.steps},
+                       # target logpdf + tc_logq + logw_combine + block-record merge + abort flag + normalise
+                       # (+ the cross-rank record merge for N > 1)
+                       "gpu_launches": (6 if world == 1 else 7) * args.steps},
         }
         print_json(out)
     if world > 1:

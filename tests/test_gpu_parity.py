@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 
 LOGP_TOL = 1e-5
 W_TOL = 1e-4
+KLD_TOL = 1e-4
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -222,6 +223,72 @@ def test_dm_weights_unfused_paths():
         ref_lw = ref_p - ref_q
         assert p[3] == n
         assert p[0] + np.log(p[1]) == pytest.approx(np.log(np.exp(ref_lw - ref_lw.max()).sum()) + ref_lw.max(), abs=1e-4)
+
+
+def test_device_resident_records_and_streamed_weighting():
+    """Device-side record merge + normalisation (no host round trip) and the chunked host->device streamed weighting
+    give the values of the host-merged path; checked against the float64 oracle too."""
+    from ais_benchmarks_b200 import _device
+    rs = np.random.RandomState(11)
+    for D, N, per in [(2, 64, 400), (32, 128, 700), (8, 33, 129)]:
+        mu = rs.uniform(-0.7, 0.7, size=(4, D))
+        sig = rs.uniform(0.04, 0.05, size=(4, D))
+        w = np.array([0.1, 0.2, 0.3, 0.4])
+        target = gmm(mu, sig, w)
+        pm = rs.uniform(-1, 1, size=(N, D))
+        hint_h = np.repeat(np.arange(N), per).astype(np.int32)
+        x = (pm[hint_h] + rs.standard_normal((N * per, D)) * np.sqrt(0.05)).astype(np.float32)
+        n = len(x)
+        pm_d = torch.from_numpy(pm).cuda().float().contiguous()
+        q = _device.DeviceMixture.kde(pm_d, None, N, 0.05)
+        tmix = target.device_mixture()
+        xd = torch.from_numpy(x).cuda()
+        hint = torch.from_numpy(hint_h).cuda()
+        logw, _, _, part = _device.dm_weights(xd, tmix, None, q, hint=hint)
+        ph = part.cpu().numpy()
+        w_host = _device.normalize_weights(logw, ph).cpu().numpy()
+        # (1) record in HBM -> same weights, statistics = host helpers
+        w_dev, stats = _device.normalize_weights_dev(logw, part)
+        st = stats.cpu().numpy()
+        assert np.array_equal(w_dev.cpu().numpy(), w_host)
+        assert st[0] == pytest.approx(_device.weight_logsum(ph), rel=1e-12)
+        assert st[1] == pytest.approx(_device.weight_ess(ph), rel=1e-12)
+        assert st[2] == n
+        # (2) records of row shards merged on the device = host merge rule = the one-shot record
+        cuts = [0, n // 3 // 4 * 4, n // 2 // 4 * 4, n]
+        recs = torch.stack([_device.logw_partials(logw[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+        merged = _device.merge_weight_records(recs).cpu().numpy()
+        rh = recs.cpu().numpy()
+        host = _device.weight_merge(_device.weight_merge(rh[0], rh[1]), rh[2])
+        assert merged[0] == host[0] and merged[3] == host[3] == n
+        assert merged[1] == pytest.approx(host[1], rel=1e-12) and merged[2] == pytest.approx(host[2], rel=1e-12)
+        assert merged[0] + np.log(merged[1]) == pytest.approx(ph[0] + np.log(ph[1]), abs=1e-6)
+        # (3) streamed from pinned host memory in 3 chunks: bit-identical log weights, same normaliser
+        xp = torch.from_numpy(x).pin_memory()
+        chunk = ((n + 2) // 3 + 1023) // 1024 * 1024
+        xs, logw_s, rec_s = _device.dm_weights_streamed(xp, tmix, q, hint=hint, chunk_rows=chunk)
+        assert torch.equal(xs, xd)
+        assert torch.equal(logw_s, logw)
+        rs_ = rec_s.cpu().numpy()
+        assert rs_[3] == n and rs_[0] + np.log(rs_[1]) == pytest.approx(ph[0] + np.log(ph[1]), abs=1e-6)
+        w_s, _ = _device.normalize_weights_dev(logw_s, rec_s)
+        assert np.max(np.abs(w_s.cpu().numpy() - w_host)) <= 2e-6 * w_host.max()
+        # (4) float64 oracle on the same float32 samples
+        x64 = x.astype(np.float64)
+        ref_lw = O.gmm_log_prob(x64, mu, sig, w) - O.iso_mixture_log_prob(x64, pm_d.double().cpu().numpy(), 0.05)
+        ref_w = np.exp(ref_lw - ref_lw.max())
+        ref_w /= ref_w.sum()
+        big = ref_w > 1e-9
+        assert np.max(np.abs(w_s.cpu().numpy()[big] - ref_w[big]) / ref_w[big]) < W_TOL
+    # KLD records on the device
+    lp = torch.from_numpy(rs.normal(size=5000).astype(np.float32)).cuda()
+    lq = torch.from_numpy(rs.normal(size=5000).astype(np.float32)).cuda()
+    recs = torch.stack([_device.kld_partials(lp[:2000], lq[:2000]), _device.kld_partials(lp[2000:], lq[2000:])])
+    merged = _device.merge_kld_records(recs).cpu().numpy()
+    whole = _device.kld_partials(lp, lq).cpu().numpy()
+    assert _device.kld_finalize(merged) == pytest.approx(_device.kld_finalize(whole), rel=1e-9)
+    assert _device.kld_finalize(merged) == pytest.approx(
+        O.kld_from_log_probs(lp.double().cpu().numpy(), lq.double().cpu().numpy()), rel=KLD_TOL)
 
 
 @pytest.mark.parametrize("case", range(3))
