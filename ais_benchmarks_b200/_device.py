@@ -542,6 +542,19 @@ def sample_iso(means, per, var):
     return out
 
 
+def sample_mixture(means, chol, idx):
+    """means [K, D], chol [K, D, D] (lower-triangular Cholesky factors) float32 CUDA, idx int64 CUDA [n] -> [n, D] draws
+    means[idx] + chol[idx] z (C ABI aisb_sample_mixture_f32)."""
+    lib = require_cuda()
+    K, D = means.shape
+    n = idx.shape[0]
+    out = torch.empty((n, D), dtype=torch.float32, device=means.device)
+    off = _next_offset(n * ((D + 3) // 4) * 4)
+    check(lib.aisb_sample_mixture_f32(_ptr(means), _ptr(chol), K, D, _ptr(idx), n, _rng_state["seed"], off, _ptr(out),
+                                      stream_ptr()), "aisb_sample_mixture_f32")
+    return out
+
+
 def uniform_box(lo, hi, n):
     """lo, hi [D] float32 CUDA -> [n, D] uniform draws."""
     lib = require_cuda()

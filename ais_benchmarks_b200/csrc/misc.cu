@@ -105,6 +105,49 @@ __global__ void sample_iso_kernel(const float* __restrict__ means, int64_t K, in
   }
 }
 
+// Ancestral sampling from a Gaussian mixture with full covariances (CMixtureModel.sample, CMixtureModel.py:79-89, with
+// CMultivariateNormal.sample, CMultivariateNormal.py:64-65, as the leaf): thread = draw;
+//   out[i] = means[idx[i]] + L[idx[i]] z_i,   z_i ~ N(0, I) from Philox, L lower-triangular (row-major [K, D, D]).
+template <int DP>
+__global__ void __launch_bounds__(128) sample_mixture_kernel(const float* __restrict__ means,
+                                                             const float* __restrict__ chol, int64_t K, int D,
+                                                             const int64_t* __restrict__ idx, int64_t n, uint64_t seed,
+                                                             uint64_t offset, float* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  int64_t k = idx[i];
+  k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+  constexpr int G = (DP + 3) / 4;
+  float z[G * 4];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    float z4[4];
+    normal4(static_cast<uint64_t>(i) * G + g + offset, seed, z4);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) z[4 * g + e] = z4[e];
+  }
+  const float* L = chol + k * static_cast<int64_t>(D) * D;
+  const float* mu = means + k * static_cast<int64_t>(D);
+#pragma unroll
+  for (int r = 0; r < DP; ++r) {
+    if (r < D) {
+      float acc = __ldg(mu + r);
+#pragma unroll
+      for (int c = 0; c <= r; ++c) acc = fmaf(__ldg(L + r * D + c), z[c], acc);
+      out[i * D + r] = acc;
+    }
+  }
+}
+
+template <int DP>
+static int launch_sample_mixture(const float* means, const float* chol, int64_t K, int D, const int64_t* idx, int64_t n,
+                                 uint64_t seed, uint64_t offset, float* out, cudaStream_t st) {
+  sample_mixture_kernel<DP><<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(means, chol, K, D, idx, n, seed,
+                                                                                   offset, out);
+  AISB_LAUNCH_CHECK("sample_mixture_kernel");
+  return AISB_OK;
+}
+
 __global__ void uniform_box_kernel(const float* __restrict__ lo, const float* __restrict__ hi, int D, int64_t n,
                                    uint64_t seed, uint64_t offset, float* __restrict__ out) {
   const int64_t total = n * D;
@@ -209,6 +252,29 @@ extern "C" int aisb_sample_iso_f32(const float* d_means, int64_t K, int32_t D, i
       d_means, K, D, per, static_cast<float>(sqrt(var)), seed, offset, d_out);
   AISB_LAUNCH_CHECK("sample_iso_kernel");
   return AISB_OK;
+}
+
+extern "C" int aisb_sample_mixture_f32(const float* d_means, const float* d_chol, int64_t K, int32_t D,
+                                       const int64_t* d_idx, int64_t n, uint64_t seed, uint64_t offset, float* d_out,
+                                       void* stream) {
+  if (!d_means || !d_chol || !d_idx || !d_out || K < 1 || n < 0 || D < 1 || D > AISB_MAX_DIMS) {
+    set_error("sample_mixture: invalid argument");
+    return AISB_ERR_INVALID;
+  }
+  if (n == 0) return AISB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (aisb_padded_dims(D)) {
+    case 1: return launch_sample_mixture<1>(d_means, d_chol, K, D, d_idx, n, seed, offset, d_out, st);
+    case 2: return launch_sample_mixture<2>(d_means, d_chol, K, D, d_idx, n, seed, offset, d_out, st);
+    case 4: return launch_sample_mixture<4>(d_means, d_chol, K, D, d_idx, n, seed, offset, d_out, st);
+    case 8: return launch_sample_mixture<8>(d_means, d_chol, K, D, d_idx, n, seed, offset, d_out, st);
+    case 16: return launch_sample_mixture<16>(d_means, d_chol, K, D, d_idx, n, seed, offset, d_out, st);
+    case 32: return launch_sample_mixture<32>(d_means, d_chol, K, D, d_idx, n, seed, offset, d_out, st);
+    case 64: return launch_sample_mixture<64>(d_means, d_chol, K, D, d_idx, n, seed, offset, d_out, st);
+    default: break;
+  }
+  set_error("sample_mixture: unsupported D=%d", D);
+  return AISB_ERR_UNSUPPORTED;
 }
 
 extern "C" int aisb_uniform_box_f32(const float* d_lo, const float* d_hi, int32_t D, int64_t n, uint64_t seed,

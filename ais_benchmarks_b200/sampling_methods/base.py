@@ -37,6 +37,7 @@ class CSamplingMethod(metaclass=ABCMeta):
         self._num_q_samples = 0
         self._samples_dev = None   # float32 [n, D] CUDA
         self._logw_dev = None      # float32 [n] CUDA, log of the reference's self.weights
+        self._buf_s = self._buf_w = None  # growth buffers behind the two views (see _append)
         self._samples_np = None
         self._weights_np = None
         self._partials = None      # host float64[4] record of the accumulated log-weights
@@ -83,8 +84,27 @@ class CSamplingMethod(metaclass=ABCMeta):
             self._logw_dev = None
 
     def _append(self, new_samples, new_logw):
-        self._samples_dev = new_samples if self._samples_dev is None else torch.cat((self._samples_dev, new_samples))
-        self._logw_dev = new_logw if self._logw_dev is None else torch.cat((self._logw_dev, new_logw))
+        """Accumulate a batch (the reference grows self.samples / self.weights with np.vstack / np.concatenate on
+        every iteration, O(n^2) copying: dm_ais.py:69,79-80). Here the state lives in capacity-doubling HBM buffers and
+        self._samples_dev / self._logw_dev are prefix views of them, so a run of many small iterations copies O(n)."""
+        n0, k = self._n(), int(new_samples.shape[0])
+        if n0 == 0:
+            # first batch: adopt the tensors as they are (no copy; a 1e7-sample batch must not be duplicated)
+            self._buf_s, self._buf_w = new_samples, new_logw
+        else:
+            owned = (self._buf_s is not None and self._samples_dev.data_ptr() == self._buf_s.data_ptr()
+                     and self._logw_dev.data_ptr() == self._buf_w.data_ptr())
+            if not owned or n0 + k > self._buf_s.shape[0]:
+                cap = max(n0 + k, 2 * n0)
+                buf_s = torch.empty((cap, new_samples.shape[1]), dtype=torch.float32, device=new_samples.device)
+                buf_w = torch.empty(cap, dtype=torch.float32, device=new_samples.device)
+                buf_s[:n0].copy_(self._samples_dev)
+                buf_w[:n0].copy_(self._logw_dev)
+                self._buf_s, self._buf_w = buf_s, buf_w
+            self._buf_s[n0:n0 + k].copy_(new_samples)
+            self._buf_w[n0:n0 + k].copy_(new_logw)
+        self._samples_dev = self._buf_s[:n0 + k]
+        self._logw_dev = self._buf_w[:n0 + k]
         self._samples_np = self._weights_np = self._partials = None
 
     def _n(self):

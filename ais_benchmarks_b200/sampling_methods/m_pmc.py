@@ -42,6 +42,7 @@ class CMixturePMC(CMixtureISSamplingMethod):
         self._mix_weights = sanitize_weights(self.wproposals.copy())
         self._mixture = None
         self._objects = None
+        self._sampler_params = None
 
     # -- proposal mixture --------------------------------------------------------------------------
     def proposal_mixture(self):
@@ -88,14 +89,16 @@ class CMixturePMC(CMixtureISSamplingMethod):
         return _device.exp_from_device(_device.mixture_logpdf(x, self.proposal_mixture()), as_numpy)
 
     def _sample_device(self, n):
-        """Ancestral sampling from the proposal mixture on the device (m_pmc.py:86 -> CMixtureModel.sample)."""
+        """Ancestral sampling from the proposal mixture on the device (m_pmc.py:86 -> CMixtureModel.sample): component
+        indices from a device multinomial, then ONE kernel for x = mu_k + L_k z (C ABI aisb_sample_mixture_f32). The
+        Cholesky factors are computed on the host in float64 once per parameter update (N small D x D matrices)."""
         dev = _device.device()
+        if self._sampler_params is None:
+            L = np.linalg.cholesky(0.5 * (self._covs + np.transpose(self._covs, (0, 2, 1))))
+            self._sampler_params = (torch.from_numpy(self._means).to(dev, torch.float32).contiguous(),
+                                    torch.from_numpy(L).to(dev, torch.float32).contiguous())
         idx = mixture_component_draws(self._mix_weights, n, dev)
-        z = _device.sample_iso(torch.zeros((1, self.ndims), dtype=torch.float32, device=dev), int(n), 1.0)
-        L = np.linalg.cholesky(0.5 * (self._covs + np.transpose(self._covs, (0, 2, 1))))
-        Ld = torch.from_numpy(L).to(dev, torch.float32)[idx]
-        mu = torch.from_numpy(self._means).to(dev, torch.float32)[idx]
-        return (mu + torch.bmm(Ld, z.unsqueeze(-1)).squeeze(-1)).contiguous()
+        return _device.sample_mixture(self._sampler_params[0], self._sampler_params[1], idx.contiguous())
 
     def sample(self, n_samples):
         self._num_q_samples += n_samples
@@ -121,24 +124,24 @@ class CMixturePMC(CMixtureISSamplingMethod):
         n = samples.shape[0]
         s1_t, s2_t = _device.raw_moments(samples)
         s1, s2 = s1_t.cpu().numpy(), s2_t.cpu().numpy()
-        covs = np.empty_like(self._covs)
-        for d in range(self.N):
-            with np.errstate(invalid="ignore", over="ignore"):
-                if self.paper_covariance:
-                    raise NotImplementedError("paper_covariance needs the weighted second-moment kernel (next round)")
-                # quirk Q3: raw scatter about mu_d, (X - mu)^T (X - mu) = S2 - mu s1^T - s1 mu^T + n mu mu^T
-                cov = s2 - np.outer(mu[d], s1) - np.outer(s1, mu[d]) + n * np.outer(mu[d], mu[d])
-            if np.any(np.isnan(cov)) or np.any(cov > 10):
-                cov = np.diag(np.ones(self.ndims) * 10)
-            # CMultivariateNormal.set_moments asserts det > 0 (CMultivariateNormal.py:55-56)
-            assert np.linalg.det(cov) > 0
-            covs[d] = cov
+        if self.paper_covariance:
+            raise NotImplementedError("paper_covariance needs the weighted second-moment kernel (next round)")
+        # quirk Q3: raw scatter about mu_d, (X - mu)^T (X - mu) = S2 - mu s1^T - s1 mu^T + n mu mu^T, for all N
+        # proposals at once (the reference loops over proposals and samples, m_pmc.py:62-72)
+        with np.errstate(invalid="ignore", over="ignore"):
+            covs = (s2[None, :, :] - mu[:, :, None] * s1[None, None, :] - s1[None, :, None] * mu[:, None, :]
+                    + n * mu[:, :, None] * mu[:, None, :])
+            bad = np.isnan(covs).any(axis=(1, 2)) | (covs > 10).any(axis=(1, 2))
+        covs[bad] = np.diag(np.ones(self.ndims) * 10)
+        # CMultivariateNormal.set_moments asserts det > 0 (CMultivariateNormal.py:55-56)
+        assert np.all(np.linalg.det(covs) > 0)
         self._means, self._covs = mu, covs
         self.wproposals = alpha
         self.wproposals = self.wproposals / self.wproposals.sum()
         self._mix_weights = sanitize_weights(self.wproposals.copy())
         self._mixture = None
         self._objects = None
+        self._sampler_params = None
 
     def importance_sample(self, target_d, n_samples, timeout=60):
         elapsed_time = 0

@@ -270,6 +270,12 @@ int aisb_box_mixture_logpdf_f32(const float* d_x, int64_t n, int32_t D, const fl
  *      (DM-AIS / LAIS: K samples from each of N proposals, dm_ais.py:64-69).
  *  aisb_uniform_box_f32: out[i, d] ~ U(lo_d, hi_d)  (CDivergence.compute eval points, divergences.py:84-85).
  */
+/*  aisb_sample_mixture_f32: ancestral draws from a full-covariance Gaussian mixture, given the component of every draw:
+ *      out[i, :] = means[idx[i], :] + chol[idx[i]] z_i,  z_i ~ N(0, I)   (chol: lower-triangular factors, row-major
+ *      [K, D, D]). Replaces CMixtureModel.sample (CMixtureModel.py:79-89) over CMultivariateNormal.sample
+ *      (CMultivariateNormal.py:64-65) once the component indices have been drawn (m_pmc.py:86). */
+int aisb_sample_mixture_f32(const float* d_means, const float* d_chol, int64_t K, int32_t D, const int64_t* d_idx,
+                            int64_t n, uint64_t seed, uint64_t offset, float* d_out, void* stream);
 int aisb_sample_iso_f32(const float* d_means, int64_t K, int32_t D, int64_t per, double var, uint64_t seed,
                         uint64_t offset, float* d_out, void* stream);
 int aisb_uniform_box_f32(const float* d_lo, const float* d_hi, int32_t D, int64_t n, uint64_t seed, uint64_t offset,

@@ -104,13 +104,13 @@ def config3():
           % (dt * 1e3, K / dt))
     check_weights("C3 M-PMC it.1", x[:K], wn[:K], lambda v: O.gmm_log_prob(v, m0[0], m0[1], m0[2]), mu, sig, w)
     (s, _, x, wn), dt = timed(lambda: mpmc(3), reps=2)
-    print("    importance_sample (3 iterations, full-covariance proposals after the first adapt): %.3f ms -> %.3e samples/s"
+    print("    importance_sample (3 iterations): %.3f ms -> %.3e samples/s"
           % (dt * 1e3, s._n() / dt))
-    print("      stage timings of one iteration on the adapted (full-covariance) proposals:")
+    print("      stage timings of one iteration on the adapted proposals:")
     xs, dt = timed(lambda: s.sample_batch())
     print("        sample_batch %.3f ms" % (dt * 1e3))
     (logw, logq, part), dt = timed(lambda: s.weigh(xs, target))
-    print("        weigh (log pi, log q over %d full-cov proposals, log w, record) %.3f ms -> %.3e pairs/s"
+    print("        weigh (log pi, log q over %d adapted proposals [10*I after the Q3 failsafe], log w, record) %.3f ms -> %.3e pairs/s"
           % (N, dt * 1e3, K * N / dt))
     ph = part.cpu().numpy()
     _, dt = timed(lambda: _device.mpmc_moments(xs, s.proposal_mixture(), logq, logw, _device.weight_logsum(ph)))

@@ -571,6 +571,84 @@ def test_device_sampling_statistics():
     assert not torch.equal(y, x[:20].reshape(-1, 3)[:20])  # the stream advances between calls
 
 
+@pytest.mark.parametrize("D", [1, 3, 8, 33])
+def test_mixture_sampling_kernel_statistics(D):
+    """x = mu_k + L_k z draws (C ABI aisb_sample_mixture_f32): per-component mean / covariance, independence of the
+    draws, and M-PMC's proposal sampler on top of it (CMixtureModel.sample semantics, CMixtureModel.py:79-89)."""
+    from ais_benchmarks_b200 import _device
+    rs = np.random.RandomState(D)
+    K, n = 3, 240000
+    mu = rs.uniform(-3, 3, size=(K, D))
+    A = rs.normal(size=(K, D, D)) * 0.3
+    cov = A @ np.transpose(A, (0, 2, 1)) + 0.2 * np.eye(D)[None]
+    L = np.linalg.cholesky(cov)
+    _device.seed(7)
+    idx = torch.from_numpy(np.repeat(np.arange(K), n // K)).cuda()
+    x = _device.sample_mixture(torch.from_numpy(mu).cuda().float(), torch.from_numpy(L).cuda().float().contiguous(), idx)
+    assert x.shape == (n, D)
+    xs = x.double().cpu().numpy().reshape(K, n // K, D)
+    for k in range(K):
+        assert np.allclose(xs[k].mean(0), mu[k], atol=0.02 * np.sqrt(np.diag(cov[k]).max()) * 3)
+        emp = np.cov(xs[k].T).reshape(D, D)
+        assert np.max(np.abs(emp - cov[k])) < 0.03 * np.abs(cov[k]).max() + 0.01
+    # whitened draws are standard normal: fourth moment 3, no correlation between consecutive draws
+    z = np.linalg.solve(L[0], (xs[0] - mu[0]).T).T
+    assert abs((z ** 4).mean() - 3.0) < 0.1
+    assert abs((z[1:, 0] * z[:-1, 0]).mean()) < 0.02
+    y = _device.sample_mixture(torch.from_numpy(mu).cuda().float(), torch.from_numpy(L).cuda().float().contiguous(), idx)
+    assert not torch.equal(x, y)  # the Philox stream advances between calls
+
+
+def test_mpmc_proposal_sampler():
+    from ais_benchmarks_b200 import _device
+    from ais_benchmarks_b200.sampling_methods import CMixturePMC
+    np.random.seed(3)
+    _device.seed(3)
+    D = 4
+    s = CMixturePMC({"space_min": np.full(D, -1.0), "space_max": np.full(D, 1.0), "dims": D, "K": 100, "N": 5, "J": 10,
+                     "sigma": 0.01, "device_outputs": True})
+    s._mix_weights = np.array([0.5, 0.0, 0.25, 0.25, 0.0])
+    x = s.sample(200000).double().cpu().numpy()
+    # every draw sits within 6 sd of a component with non-zero weight; component frequencies follow the weights
+    d2 = ((x[:, None, :] - s._means[None]) ** 2).sum(-1)
+    near = d2.argmin(1)
+    assert np.all(d2.min(1) < 36 * 0.01 * D)
+    freq = np.bincount(near, minlength=5) / len(x)
+    assert np.allclose(freq, s._mix_weights, atol=0.01)
+    assert s.num_proposal_samples == 200000
+
+
+def test_sampler_state_growth_buffers():
+    """_append keeps the accumulated samples / log weights in capacity-doubling buffers: values, order, and earlier
+    views survive many small iterations (the reference's vstack/concatenate growth, dm_ais.py:69,79-80)."""
+    from ais_benchmarks_b200.sampling_methods import CDeterministicMixtureAIS
+    np.random.seed(0)
+    s = CDeterministicMixtureAIS({"space_min": np.full(2, -1.0), "space_max": np.full(2, 1.0), "dims": 2, "K": 1,
+                                  "N": 4, "J": 1, "sigma": 0.1})
+    rs = np.random.RandomState(0)
+    chunks, views = [], []
+    for it in range(40):
+        k = int(rs.randint(1, 50))
+        xs = torch.from_numpy(rs.normal(size=(k, 2)).astype(np.float32)).cuda()
+        lw = torch.from_numpy(rs.normal(size=k).astype(np.float32)).cuda()
+        s._append(xs, lw)
+        chunks.append((xs.cpu().numpy(), lw.cpu().numpy()))
+        views.append((s._samples_dev, s._n()))
+    allx = np.concatenate([c[0] for c in chunks])
+    allw = np.concatenate([c[1] for c in chunks])
+    assert np.array_equal(s._samples_dev.cpu().numpy(), allx) and np.array_equal(s._logw_dev.cpu().numpy(), allw)
+    assert s._samples_dev.is_contiguous() and s._buf_s.shape[0] >= len(allx)
+    for v, n in views[::7]:
+        assert np.array_equal(v.cpu().numpy(), allx[:n])
+    assert np.allclose(s.samples, allx) and np.allclose(s.weights, np.exp(allw.astype(np.float64)))
+    s.weights = np.ones(3)
+    s.samples = np.zeros((3, 2))
+    s._append(torch.ones((2, 2), device="cuda"), torch.zeros(2, device="cuda"))
+    assert s._n() == 5 and np.array_equal(s.samples[3:], np.ones((2, 2)))
+    s.reset()
+    assert s._n() == 0 and s._buf_s is None
+
+
 def test_raw_moments():
     from ais_benchmarks_b200 import _device
     rs = np.random.RandomState(9)
