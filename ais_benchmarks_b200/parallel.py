@@ -4,6 +4,8 @@ rows, mixture parameters replicated, and ONLY the small partial records exchange
   * KLD:      8 doubles per rank  (m_p, S_p, A, m_q, S_q, n_in, n_posinf_q, n_total)
   * weights:  4 doubles per rank  (M, S1, S2, n_valid)
   * M-PMC:    K x (D+1) doubles   (all-reduce SUM of the moment accumulators)
+  * DM-AIS / LAIS adaptation: the N new proposal means (N x D floats), the one non-scalar exchange
+    (two-level multinomial resampling: resample_global; chain shards: all_gather_rows)
 
 The records are all-gathered and merged on every rank with the log-sum-exp rescale rule
 (C ABI aisb_kld_partials_merge / aisb_weight_partials_merge), so every rank ends with the same
@@ -111,3 +113,100 @@ def sharded_kld(p, q, samples):
     metric = CKLDivergence()
     metric.compute_from_samples(p, q, samples[start:stop])
     return global_kld(metric.partials)
+
+
+# ----------------------------------------------------------------------------------------------------
+# Adaptation steps over row-sharded samples
+# ----------------------------------------------------------------------------------------------------
+def _comm(t):
+    """Tensor on the communication device (CUDA for NCCL, CPU for gloo)."""
+    dev = _comm_device()
+    return t if t.device.type == dev.type else t.to(dev)
+
+
+def broadcast_array(a, src=0):
+    """numpy array of rank `src` on every rank (replicated proposal parameters start identical)."""
+    _, ws = world()
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if ws == 1:
+        return a
+    t = _comm(torch.from_numpy(a.copy()))
+    dist.broadcast(t, src=src)
+    return t.cpu().numpy()
+
+
+def all_gather_rows(rows, counts):
+    """rows: [counts[rank], D] tensor of this rank -> [sum(counts), D] on rows.device, rank-major, identical on
+    every rank. `counts` (one int per rank) must be known to all ranks."""
+    rank, ws = world()
+    if ws == 1:
+        return rows
+    total, cmax = int(sum(counts)), int(max(counts))
+    pad = torch.zeros((cmax, rows.shape[1]), dtype=rows.dtype, device=rows.device)
+    pad[:rows.shape[0]] = rows
+    send = _comm(pad).contiguous()
+    recv = torch.empty((ws * cmax, rows.shape[1]), dtype=rows.dtype, device=send.device)
+    dist.all_gather_into_tensor(recv, send)
+    recv = recv.reshape(ws, cmax, rows.shape[1])
+    out = torch.cat([recv[r, :int(counts[r])] for r in range(ws)]).to(rows.device)
+    assert out.shape[0] == total
+    return out
+
+
+def shard_log_mass(logw):
+    """Host record {m, sum exp(logw - m)} of this rank's log weights; invalid (NaN / +inf) weights count as zero,
+    as in sampling_methods.base.multinomial_resample."""
+    if logw.shape[0] == 0:
+        return np.array([-np.inf, 0.0])
+    lw = logw.double()
+    lw = torch.where(torch.isfinite(lw) | (lw == -np.inf), lw, torch.full_like(lw, -np.inf))
+    m = torch.max(lw)
+    if not torch.isfinite(m):
+        return np.array([-np.inf, 0.0])
+    return np.array([float(m), float(torch.exp(lw - m).sum())])
+
+
+def resample_global(samples, logw, n_draws):
+    """DM-PMC resampling (dm_ais.py:47-56) over row-sharded samples: n_draws rows ~ Categorical(w / sum w) over the
+    UNION of all ranks' rows, as a two-level multinomial -- shard counts ~ Multinomial(n_draws, shard masses) drawn by
+    rank 0 and broadcast, then counts[rank] rows drawn locally -- followed by an all-gather of the chosen rows
+    (n_draws x D floats). Every rank returns the same [n_draws, D] tensor. Degenerate weights (zero total mass) fall
+    back to uniform draws, like the single-GPU path."""
+    from .sampling_methods.base import multinomial_resample
+    rank, ws = world()
+    if ws == 1:
+        return samples[multinomial_resample(logw, n_draws)]
+    recs = all_gather_records(shard_log_mass(logw))                      # [G, 2]
+    finite = np.isfinite(recs[:, 0])
+    mass = np.zeros(ws)
+    if finite.any():
+        M = recs[finite, 0].max()
+        mass[finite] = recs[finite, 1] * np.exp(recs[finite, 0] - M)
+    sizes = all_gather_records(np.array([float(logw.shape[0])]))[:, 0]
+    uniform = not (mass.sum() > 0)
+    p = sizes / sizes.sum() if uniform else mass / mass.sum()
+    counts = torch.zeros(ws, dtype=torch.int64)
+    if rank == 0:
+        counts = torch.from_numpy(np.random.multinomial(int(n_draws), p).astype(np.int64))
+    counts = _comm(counts)
+    dist.broadcast(counts, src=0)
+    counts = [int(c) for c in counts.cpu().tolist()]
+    c = counts[rank]
+    if c == 0:
+        chosen = samples[:0]
+    elif uniform:
+        chosen = samples[torch.randint(0, samples.shape[0], (c,), device=samples.device)]
+    else:
+        chosen = samples[multinomial_resample(logw, c)]
+    return all_gather_rows(chosen, counts)
+
+
+def all_reduce_sum_host(a):
+    """SUM over ranks of a small numpy float64 array (M-PMC sufficient statistics)."""
+    _, ws = world()
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if ws == 1:
+        return a
+    t = _comm(torch.from_numpy(a.copy()))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()

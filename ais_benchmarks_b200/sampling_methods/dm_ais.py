@@ -24,12 +24,17 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
             - space_min / space_max: space boundaries; dims: number of dimensions
             - K: samples per proposal; N: number of proposals; J: iteration cap (unused, like the reference)
             - sigma: proposal VARIANCE (covariance = sigma * I, dm_ais.py:38-39)
+            - sharded (optional, under torch.distributed): every rank draws and weighs its share of the K draws per
+              proposal; the proposal means stay replicated (two-level multinomial resampling + an all-gather of the N
+              chosen means per iteration); returned samples are this rank's rows, their weights are normalised over
+              ALL ranks and iterations
         """
         super(CDeterministicMixtureAIS, self).__init__(params)
         self.K = params["K"]
         self.N = params["N"]
         self.J = params["J"]
         self.sigma = params["sigma"]
+        self.sharded = bool(params.get("sharded", False))
         self._means = None
         self._mixture = None
         self._objects = None
@@ -40,6 +45,10 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
         super(CDeterministicMixtureAIS, self).reset()
         # proposal centres ~ U(space_min, space_max) from the host RNG, as dm_ais.py:36-37
         centres = np.random.uniform(self.space_min, self.space_max, size=(self.N, self.ndims))
+        if self.sharded:
+            from .. import parallel
+            centres = parallel.broadcast_array(centres)   # replicated parameters start identical on every rank
+        self._n_all_ranks = 0
         self._set_means_host(centres)
 
     def _set_means_host(self, centres):
@@ -120,31 +129,63 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
         logw, _, _, partials = _device.dm_weights(new_samples, target, logp_in, self.proposal_mixture(), hint=hint)
         return logw, partials
 
-    def _own_proposal(self):
-        """Proposal index of every row of a proposal-major batch of N*K draws."""
-        if getattr(self, "_hint", None) is None or self._hint.shape[0] != self.N * self.K:
-            self._hint = (torch.arange(self.N * self.K, device=_device.device()) // int(self.K)).to(torch.int32)
+    def _own_proposal(self, per=None):
+        """Proposal index of every row of a proposal-major batch of N*per draws."""
+        per = int(self.K if per is None else per)
+        if getattr(self, "_hint", None) is None or self._hint.shape[0] != self.N * per:
+            self._hint = (torch.arange(self.N * per, device=_device.device()) // max(per, 1)).to(torch.int32)
         return self._hint
 
+    def _draws_per_proposal(self):
+        """K, or this rank's share of the K draws per proposal when sharded."""
+        if not self.sharded:
+            return int(self.K)
+        from .. import parallel
+        a, b = parallel.shard_rows(int(self.K))
+        return b - a
+
     def resample(self, samples, logw):
-        """DM-PMC update (dm_ais.py:47-56): each proposal mean <- a sample drawn ~ batch-normalised weights."""
+        """DM-PMC update (dm_ais.py:47-56): each proposal mean <- a sample drawn ~ batch-normalised weights (over the
+        batches of all ranks when sharded)."""
+        if self.sharded:
+            from .. import parallel
+            self._set_means_dev(parallel.resample_global(samples, logw, self.N))
+            return
         idx = multinomial_resample(logw, self.N)
         self._set_means_dev(samples[idx])
+
+    def _global_partials(self):
+        """Weight record of the accumulated log weights, merged over the ranks when sharded."""
+        rec = self._weight_partials()
+        if self.sharded:
+            from .. import parallel
+            rec = parallel.global_weight_partials(rec)
+        return rec
+
+    def get_approx_NESS(self):
+        if not self.sharded:
+            return super(CDeterministicMixtureAIS, self).get_approx_NESS()
+        rec = self._global_partials()
+        return _device.weight_ess(rec) / rec[3]
 
     def importance_sample(self, target_d, n_samples, timeout=60):
         elapsed_time = 0
         t_ini = time.time()
-        while n_samples > self._n() and elapsed_time < timeout:
+        per = self._draws_per_proposal()
+        # n_samples is the total wanted over all ranks; every iteration adds N*K of them
+        # (sharded: the loop is driven by the sample count alone -- a per-rank clock must not desynchronise the collectives)
+        while n_samples > (self._n_all_ranks if self.sharded else self._n()) and (self.sharded or elapsed_time < timeout):
             # K samples from each proposal, proposal-major like dm_ais.py:64-69
-            new_samples = _device.sample_iso(self.proposal_means(), int(self.K), float(self.sigma))
-            self._num_q_samples += self.N * self.K
-            new_logw, _ = self.weigh(new_samples, target_d, hint=self._own_proposal())
-            self._num_pi_evals += self.N * self.K
+            new_samples = _device.sample_iso(self.proposal_means(), per, float(self.sigma))
+            self._num_q_samples += self.N * per
+            new_logw, _ = self.weigh(new_samples, target_d, hint=self._own_proposal(per))
+            self._num_pi_evals += self.N * per
             self.resample(new_samples, new_logw)
             self._append(new_samples, new_logw)
+            self._n_all_ranks += self.N * int(self.K)
             elapsed_time = time.time() - t_ini
-        # weights / weights.sum() over ALL iterations (dm_ais.py:86)
-        norm_w = _device.normalize_weights(self._logw_dev, self._weight_partials())
+        # weights / weights.sum() over ALL iterations (dm_ais.py:86) -- and all ranks
+        norm_w = _device.normalize_weights(self._logw_dev, self._global_partials())
         return self._out(self._samples_dev), (norm_w if self.device_outputs else norm_w.double().cpu().numpy())
 
     def _update_model(self):

@@ -32,11 +32,19 @@ class CMixturePMC(CMixtureISSamplingMethod):
         self.J = params["J"]
         self.sigma = params["sigma"]
         self.paper_covariance = bool(params.get("paper_covariance", False))
+        # sharded (under torch.distributed): every rank draws and weighs its share of the K samples of an iteration;
+        # the sufficient statistics (weight record, alpha / mu numerators, raw moments) are summed over the ranks and
+        # every rank performs the identical float64 parameter update
+        self.sharded = bool(params.get("sharded", False))
         self.reset()
 
     def reset(self):
         super(CMixturePMC, self).reset()
         self._means = np.random.uniform(self.space_min, self.space_max, size=(self.N, self.ndims))
+        if self.sharded:
+            from .. import parallel
+            self._means = parallel.broadcast_array(self._means)
+        self._n_all_ranks = 0
         self._covs = np.tile(np.diag(np.array([self.sigma] * self.ndims, dtype=np.float64)), (self.N, 1, 1))
         self.wproposals = np.array([1 / self.N] * self.N)
         self._mix_weights = sanitize_weights(self.wproposals.copy())
@@ -118,12 +126,19 @@ class CMixturePMC(CMixtureISSamplingMethod):
         """alpha, mu, Sigma update (m_pmc.py:53-78) from device-side sufficient statistics."""
         log_norm = _device.weight_logsum(partials_host)  # log sum_i w_i: weights are batch-normalised (m_pmc.py:108)
         mom = _device.mpmc_moments(samples, self.proposal_mixture(), logq, logw, log_norm).cpu().numpy()
+        if self.sharded:
+            from .. import parallel
+            mom = parallel.all_reduce_sum_host(mom)
         alpha = mom[:, 0].copy()                           # eq. 14.1 (Rao-Blackwellised)
         with np.errstate(divide="ignore", invalid="ignore"):
             mu = mom[:, 1:] / alpha[:, None]               # eq. 14.2
         n = samples.shape[0]
         s1_t, s2_t = _device.raw_moments(samples)
         s1, s2 = s1_t.cpu().numpy(), s2_t.cpu().numpy()
+        if self.sharded:
+            flat = parallel.all_reduce_sum_host(np.concatenate([s1, s2.reshape(-1), [float(n)]]))
+            D = self.ndims
+            s1, s2, n = flat[:D], flat[D:D + D * D].reshape(D, D), int(round(flat[-1]))
         if self.paper_covariance:
             raise NotImplementedError("paper_covariance needs the weighted second-moment kernel (next round)")
         # quirk Q3: raw scatter about mu_d, (X - mu)^T (X - mu) = S2 - mu s1^T - s1 mu^T + n mu mu^T, for all N
@@ -146,21 +161,32 @@ class CMixturePMC(CMixtureISSamplingMethod):
     def importance_sample(self, target_d, n_samples, timeout=60):
         elapsed_time = 0
         t_ini = time.time()
-        while n_samples > self._n() and elapsed_time < timeout:
+        # (sharded: the loop is driven by the sample count alone -- a per-rank clock must not desynchronise the collectives)
+        while n_samples > (self._n_all_ranks if self.sharded else self._n()) and (self.sharded or elapsed_time < timeout):
             new_samples = self.sample_batch()
+            k = int(new_samples.shape[0])
             logw, logq, partials = self.weigh(new_samples, target_d)
-            self._num_pi_evals += self.K
-            self._num_q_evals += self.K * (self.N + 1)
+            self._num_pi_evals += k
+            self._num_q_evals += k * (self.N + 1)
             ph = partials.cpu().numpy()
+            if self.sharded:
+                from .. import parallel
+                ph = parallel.global_weight_partials(ph)   # the batch is the union of all ranks' draws
             self.adapt(new_samples, logw, logq, ph)
             # accumulated weights are the batch-normalised ones (quirk Q4)
             self._append(new_samples, logw - float(_device.weight_logsum(ph)))
+            self._n_all_ranks += int(self.K)
             elapsed_time = time.time() - t_ini
         return self._out(self._samples_dev), self._out(self._logw_dev, exp=True)
 
     def sample_batch(self):
-        self._num_q_samples += self.K
-        return self._sample_device(self.K)
+        k = int(self.K)
+        if self.sharded:
+            from .. import parallel
+            a, b = parallel.shard_rows(k)
+            k = b - a
+        self._num_q_samples += k
+        return self._sample_device(k)
 
     def _update_model(self):
         pass

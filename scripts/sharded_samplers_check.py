@@ -1,0 +1,117 @@
+"""Sharded adapt loops on N GPUs (torchrun, one rank per GPU): DM-AIS, LAIS and M-PMC with `sharded: True`.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
+      scripts/sharded_samplers_check.py
+
+Checks, on every rank: replicated proposal parameters stay bit-identical across ranks after every call; the
+returned weights are normalised over ALL ranks; NESS agrees on every rank; the weights of this rank's rows match the
+float64 oracle evaluated with the proposal parameters that generated them; the adapted proposals have moved towards
+the target (KLD of the proposal mixture falls). Prints one line per sampler on rank 0 and exits non-zero on failure.
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import bench
+from ais_benchmarks_b200 import _device, parallel
+from ais_benchmarks_b200.distributions import CGaussianMixtureModel
+from ais_benchmarks_b200.metrics import CKLDivergence
+from ais_benchmarks_b200.sampling_methods import CDeterministicMixtureAIS, CLayeredAIS, CMixturePMC
+from oracle import ais_oracle as O
+
+
+def same_on_all_ranks(t, what):
+    t = t.detach().to("cuda", torch.float64).contiguous().reshape(-1)
+    ws = dist.get_world_size()
+    out = torch.empty(ws * t.numel(), dtype=torch.float64, device="cuda")
+    dist.all_gather_into_tensor(out, t)
+    out = out.reshape(ws, -1)
+    assert bool((out == out[0:1]).all() or (torch.isnan(out).all())), "%s differs across ranks" % what
+
+
+def global_sum(v):
+    t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t)
+    return float(t[0])
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    D, N = 8, 64
+    mu, sig, w, sup = bench.random_gmm(0, D, 16)
+    target = CGaussianMixtureModel({"means": mu, "sigmas": sig, "weights": w, "support": sup})
+    metric = CKLDivergence()
+    np.random.seed(5)                      # same evaluation points on every rank
+    x_eval = np.random.uniform(sup[0], sup[1], size=(20000, D))
+    lines = []
+
+    def run(cls, extra, K, iters, name):
+        np.random.seed(1000 + rank)        # ranks disagree on purpose: rank 0's draw must win
+        _device.seed(77 + rank)
+        params = {"space_min": sup[0], "space_max": sup[1], "dims": D, "K": K, "N": N, "J": 1000, "sigma": 0.05,
+                  "device_outputs": True, "sharded": True}
+        params.update(extra)
+        s = cls(params)
+        per_iter = K if cls is CMixturePMC else N * K
+        if cls is CMixturePMC:
+            same_on_all_ranks(torch.from_numpy(s._means), name + " initial means")
+            pm0 = (s._means.copy(), np.array([np.diag(c) for c in s._covs]), s._mix_weights.copy())
+        else:
+            same_on_all_ranks(s.proposal_means(), name + " initial means")
+            pm0 = s.proposal_means().double().cpu().numpy()
+        kld0 = metric.compute_from_samples(target, s, x_eval)
+        x, wn = s.importance_sample(target, per_iter)            # one iteration: weights are pure functions of pm0
+        n_loc = x.shape[0]
+        assert abs(global_sum(n_loc) - per_iter) < 0.5, (name, n_loc)
+        assert abs(global_sum(wn.double().sum()) - 1.0) < 1e-4, name
+        # oracle on a row subset of THIS rank's rows
+        rs = np.random.RandomState(rank)
+        pick = rs.choice(n_loc, size=min(500, n_loc), replace=False)
+        xs = x[pick].double().cpu().numpy()
+        if cls is CMixturePMC:
+            ref_lq = O.gmm_log_prob(xs, pm0[0], pm0[1], pm0[2])
+        else:
+            ref_lq = O.iso_mixture_log_prob(xs, pm0, 0.05)
+        ref_lw = O.gmm_log_prob(xs, mu, sig, w) - ref_lq
+        got_lw = np.log(wn[pick].double().cpu().numpy())
+        ok = np.isfinite(got_lw) & np.isfinite(ref_lw)
+        shift = np.median((got_lw - ref_lw)[ok])
+        # the normaliser is global: every rank must see the same shift
+        same_on_all_ranks(torch.tensor([round(float(shift), 3)]), name + " global normaliser")
+        err = np.max(np.abs(got_lw[ok] - shift - ref_lw[ok]) / np.maximum(1.0, np.abs(ref_lw[ok])))
+        assert err < 1e-4, (name, err)
+        x, wn = s.importance_sample(target, iters * per_iter)    # more adapt iterations
+        assert abs(global_sum(x.shape[0]) - iters * per_iter) < 0.5
+        if cls is CMixturePMC:
+            same_on_all_ranks(torch.from_numpy(s._means), name + " adapted means")
+            same_on_all_ranks(torch.from_numpy(s._mix_weights), name + " adapted weights")
+        else:
+            same_on_all_ranks(s.proposal_means(), name + " adapted means")
+            assert abs(global_sum(wn.double().sum()) - 1.0) < 1e-4, name
+        ness = s.get_approx_NESS() if cls is not CMixturePMC else float("nan")
+        same_on_all_ranks(torch.tensor([ness]), name + " NESS")
+        kld1 = metric.compute_from_samples(target, s, x_eval)
+        lines.append("%-8s world %d: %d samples over %d iterations, local rows %d, weight parity %.1e, NESS %.4g, "
+                     "KLD(target || proposal) %.3f -> %.3f" % (name, world, iters * per_iter, iters, x.shape[0], err,
+                                                             ness, kld0, kld1))
+        return kld0, kld1
+
+    k0, k1 = run(CDeterministicMixtureAIS, {}, 101, 8, "DM-AIS")
+    assert k1 < k0, ("DM-AIS did not adapt", k0, k1)
+    k0, k1 = run(CLayeredAIS, {"L": 10, "mh_sigma": 0.05}, 101, 8, "LAIS")
+    assert k1 < k0, ("LAIS did not adapt", k0, k1)
+    run(CMixturePMC, {}, 50001, 3, "M-PMC")
+    if rank == 0:
+        print("\n".join(lines))
+        print("sharded samplers ok on %d ranks" % world)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

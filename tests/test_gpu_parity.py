@@ -910,3 +910,22 @@ def test_benchmark_fused_evaluation_loop(tmp_path):
     assert abs(direct - rows[True][-1]["KL"]) <= 0.1 * abs(direct) + 0.02
     assert dm.device_outputs is False  # restored
 
+
+
+def test_sharded_samplers_multi_gpu():
+    """DM-AIS / LAIS / M-PMC with `sharded: True` under torchrun (scripts/sharded_samplers_check.py): needs >= 2 GPUs
+    on the box, skipped otherwise (the host-side exchange logic is covered on CPU by tests/test_parallel_gloo.py)."""
+    import os
+    import subprocess
+    import sys
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29600 + os.getpid() % 300
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port),
+                          os.path.join(root, "scripts", "sharded_samplers_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "sharded samplers ok on 2 ranks" in res.stdout

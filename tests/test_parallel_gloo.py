@@ -88,3 +88,55 @@ def test_shard_rows_covers_everything():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ---------------------------------------------------------------------------------------------------
+# Adaptation over row-sharded samples: two-level multinomial resampling, chain-shard gather, broadcast, host all-reduce
+# ---------------------------------------------------------------------------------------------------
+def _adapt_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ais_benchmarks_b200 import parallel
+    np.random.seed(100 + rank)          # ranks deliberately disagree: rank 0 decides, the others follow
+    torch.manual_seed(200 + rank)
+    # rank r owns rows whose first coordinate is r; rank 1's rows carry 3x the mass of rank 0's
+    n_loc, D, N = 500 + 100 * rank, 3, 4000
+    rows = torch.cat([torch.full((n_loc, 1), float(rank)), torch.arange(n_loc, dtype=torch.float32).reshape(-1, 1),
+                      torch.randn(n_loc, 1)], dim=1)
+    logw = torch.full((n_loc,), float(np.log((1.0 if rank == 0 else 3.0) / n_loc)))
+    logw[0] = float("nan")              # invalid weights count as zero
+    logw[1] = -float("inf")
+    new = parallel.resample_global(rows, logw, N)
+    # degenerate weights -> uniform over the union
+    deg = parallel.resample_global(rows, torch.full((n_loc,), -float("inf")), 1000)
+    start = parallel.broadcast_array(np.random.uniform(size=(5, 2)))
+    summed = parallel.all_reduce_sum_host(np.arange(6, dtype=np.float64).reshape(2, 3) * (rank + 1))
+    counts = [3, 1]
+    gathered = parallel.all_gather_rows(torch.full((counts[rank], 2), float(rank + 1)), counts)
+    np.savez(os.path.join(out_dir, "a%d.npz" % rank), new=new.numpy(), deg=deg.numpy(), start=start, summed=summed,
+             gathered=gathered.numpy())
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_sharded_adaptation(tmp_path):
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_adapt_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(os.path.join(str(tmp_path), "a%d.npz" % k)) for k in range(world)]
+    for key in ("new", "deg", "start", "summed", "gathered"):
+        assert np.array_equal(r[0][key], r[1][key]), key            # replicated state stays identical
+    new = r[0]["new"]
+    assert new.shape == (4000, 3)
+    frac1 = (new[:, 0] == 1).mean()
+    assert abs(frac1 - 0.75) < 0.03                                  # shard masses 1 : 3
+    # chosen rows exist in their shard and never carry an invalid / zero weight
+    assert set(np.unique(new[:, 0])) <= {0.0, 1.0}
+    assert new[new[:, 0] == 0, 1].max() < 500 and new[new[:, 0] == 1, 1].max() < 600
+    assert new[:, 1].min() >= 2
+    # within a shard the draws are uniform over its (equal-weight) rows
+    assert abs(new[new[:, 0] == 1, 1].mean() - 300.5) < 20
+    deg = r[0]["deg"]
+    assert abs((deg[:, 0] == 1).mean() - 600 / 1100) < 0.06
+    assert np.array_equal(r[0]["summed"], np.arange(6).reshape(2, 3) * 3.0)
+    assert np.array_equal(r[0]["gathered"], np.array([[1, 1]] * 3 + [[2, 2]], dtype=np.float32))
