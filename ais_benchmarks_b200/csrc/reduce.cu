@@ -82,7 +82,7 @@ __global__ void normalize_weights_kernel(const float* __restrict__ logw, int64_t
 __global__ void __launch_bounds__(256) normalize_weights_dev_kernel(const float* __restrict__ logw, int64_t n,
                                                                     const double* __restrict__ rec,
                                                                     float* __restrict__ out,
-                                                                    double* __restrict__ stats) {
+                                                                    double* __restrict__ stats, int vec_ok) {
   __shared__ float shc[2];
   if (threadIdx.x == 0) {
     const double M = rec[0], S1 = rec[1], S2 = rec[2];
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) normalize_weights_dev_kernel(const float*
   __syncthreads();
   const float M = shc[0], logS = shc[1];
   const int64_t base = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
-  if (base + 3 < n) {
+  if (vec_ok && base + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(logw + base);
     float4 r;
     r.x = expf((v.x - M) - logS);
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) normalize_weights_dev_kernel(const float*
     r.w = expf((v.w - M) - logS);
     *reinterpret_cast<float4*>(out + base) = r;
   } else {
-    for (int64_t p = base; p < n; ++p) out[p] = expf((logw[p] - M) - logS);
+    for (int64_t p = base; p < n && p < base + 4; ++p) out[p] = expf((logw[p] - M) - logS);
   }
 }
 
@@ -400,14 +400,12 @@ extern "C" int aisb_normalize_weights_dev_f32(const float* d_logw, int64_t n, co
     set_error("normalize_weights_dev: null pointer or negative n");
     return AISB_ERR_INVALID;
   }
-  if ((reinterpret_cast<uintptr_t>(d_logw) | reinterpret_cast<uintptr_t>(d_out_w)) & 15) {
-    set_error("normalize_weights_dev: d_logw and d_out_w must be 16-byte aligned");
-    return AISB_ERR_INVALID;
-  }
+  // float4 accesses when both vectors are 16-byte aligned (always true for whole tensors), scalar ones for odd views
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(d_logw) | reinterpret_cast<uintptr_t>(d_out_w)) & 15) == 0;
   // n == 0 still launches one block so that the statistics are written
   const int64_t blocks = n > 0 ? (n + 1023) / 1024 : 1;
   normalize_weights_dev_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_logw, n, d_partials, d_out_w, d_out_stats);
+      d_logw, n, d_partials, d_out_w, d_out_stats, vec_ok);
   AISB_LAUNCH_CHECK("normalize_weights_dev_kernel");
   return AISB_OK;
 }

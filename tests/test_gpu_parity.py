@@ -254,6 +254,9 @@ def test_device_resident_records_and_streamed_weighting():
         assert st[0] == pytest.approx(_device.weight_logsum(ph), rel=1e-12)
         assert st[1] == pytest.approx(_device.weight_ess(ph), rel=1e-12)
         assert st[2] == n
+        # an odd (4-byte aligned) view takes the scalar branch of the same kernel
+        w_odd, _ = _device.normalize_weights_dev(logw[1:], part, out=torch.empty(n + 2, device="cuda")[3:])
+        assert np.array_equal(w_odd.cpu().numpy(), w_host[1:])
         # (2) records of row shards merged on the device = host merge rule = the one-shot record
         cuts = [0, n // 3 // 4 * 4, n // 2 // 4 * 4, n]
         recs = torch.stack([_device.logw_partials(logw[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
