@@ -4,7 +4,7 @@
 //
 // Work decomposition
 //   * a CTA of 128 threads owns a tile of 128*E points; every thread keeps its E points in
-//     registers for the whole kernel (E*DP floats),
+//     registers for the whole kernel (E*DP floats; E = 4 up to DP = 32, 2 at DP = 64),
 //   * component parameters stream through shared memory in chunks of J components, staged by
 //     1-D TMA bulk copies (cp.async.bulk -> UBLKCP) into a 2-deep mbarrier ring,
 //   * all lanes of a warp read the SAME component (LDS broadcast) and evaluate it against
@@ -34,7 +34,9 @@ namespace aisb {
 #ifndef AISB_E_SMALL
 #define AISB_E_SMALL 4  // points per thread for DP <= 8
 #endif
-__host__ __device__ constexpr int points_per_thread(int DP) { return DP <= 8 ? AISB_E_SMALL : (DP <= 16 ? 4 : 2); }
+// 4 up to DP = 32 (two point pairs per thread: twice the independent FFMA2 chains and half the LDS per FFMA2 of one
+// pair; 210-226 registers, no spills; measured at DP = 32 against 2 points per thread: DIAG K=64 +8 %, ISO K=1024 +2 %)
+__host__ __device__ constexpr int points_per_thread(int DP) { return DP <= 8 ? AISB_E_SMALL : (DP <= 32 ? 4 : 2); }
 
 #ifndef AISB_JJ_SMALL
 #define AISB_JJ_SMALL 8  // components per online-LSE step for DP <= 8 (ISO/DIAG); 8 measured 1.6 % faster than 4
