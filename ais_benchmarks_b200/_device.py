@@ -337,16 +337,20 @@ def merge_kld_records(records):
     return out
 
 
-def normalize_weights_dev(logw, record, out=None):
-    """Normalised weights from a (merged) weight record that stays in HBM (C ABI aisb_normalize_weights_dev_f32).
+def normalize_weights_dev(logw, records, out=None):
+    """Normalised weights from weight record(s) that stay in HBM (C ABI aisb_normalize_weights_dev_f32). `records`:
+    float64 CUDA [4] or [G, 4] (one per rank / streamed chunk; folded inside the kernel).
     -> (w float32 CUDA [n], stats float64 CUDA [3] = {log sum w, ESS, n_finite}); nothing is read back here."""
     lib = require_cuda()
     n = logw.shape[0]
+    records = records.reshape(-1, 4)
+    if not records.is_contiguous():
+        records = records.contiguous()
     if out is None:
         out = torch.empty(n, dtype=torch.float32, device=logw.device)
     stats = torch.empty(3, dtype=torch.float64, device=logw.device)
-    check(lib.aisb_normalize_weights_dev_f32(_ptr(logw), n, _ptr(record), _ptr(out), _ptr(stats), stream_ptr()),
-          "aisb_normalize_weights_dev_f32")
+    check(lib.aisb_normalize_weights_dev_f32(_ptr(logw), n, _ptr(records), records.shape[0], _ptr(out), _ptr(stats),
+                                             stream_ptr()), "aisb_normalize_weights_dev_f32")
     return out, stats
 
 
@@ -363,7 +367,8 @@ def _copy_stream():
 def dm_weights_streamed(x_host, target, proposals, hint=None, chunk_rows=None, x_out=None):
     """DM weights of a HOST-resident (ideally pinned) float32 sample matrix [n, D]: the rows are copied to HBM in chunks
     on a copy stream while the weight kernel works on the previous chunk, so the PCIe transfer hides the arithmetic.
-    Every chunk leaves one weight record; they are merged on the device. -> (x_dev, logw, merged record [4] CUDA f64).
+    Every chunk leaves one weight record. -> (x_dev, logw, records [chunks, 4] CUDA f64; normalize_weights_dev and
+    merge_weight_records fold them on the device).
     `hint`: int32 CUDA [n] as in dm_weights."""
     require_cuda()
     n, D = x_host.shape
@@ -392,7 +397,7 @@ def dm_weights_streamed(x_host, target, proposals, hint=None, chunk_rows=None, x
         dm_weights(xd[a:b], target, None, proposals, hint=None if hint is None else hint[a:b], out_logw=logw[a:b],
                    out_partials=records[c])
     xd.record_stream(side)
-    return xd, logw, (records[0] if nchunks == 1 else merge_weight_records(records))
+    return xd, logw, records
 
 
 def kld_partials(lp, lq):

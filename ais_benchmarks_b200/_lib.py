@@ -48,7 +48,7 @@ PROTOTYPES = {
     "aisb_normalize_weights_f32": (C.c_int, [_vp, _i64, C.POINTER(_dbl), _vp, _vp]),
     "aisb_weight_records_merge": (C.c_int, [_vp, _i64, _vp, _vp]),
     "aisb_kld_records_merge": (C.c_int, [_vp, _i64, _vp, _vp]),
-    "aisb_normalize_weights_dev_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "aisb_normalize_weights_dev_f32": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _vp, _vp]),
     "aisb_weight_partials_merge": (None, [C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_dbl)]),
     "aisb_weight_partials_ess": (_dbl, [C.POINTER(_dbl)]),
     "aisb_weight_partials_logsum": (_dbl, [C.POINTER(_dbl)]),

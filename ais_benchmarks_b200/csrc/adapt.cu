@@ -1,4 +1,6 @@
 // Adaptation-step kernels: M-PMC Rao-Blackwellised moments, raw moments, LAIS MH chains.
+#include <stdlib.h>
+
 #include "pairwise.cuh"
 
 namespace aisb {
@@ -82,9 +84,161 @@ __global__ void __launch_bounds__(kThreads)
       });
 }
 
+// ---------------------------------------------------------------------------------------------
+// Component-stationary variant for small rows (ISO / DIAG up to DP = 16, FULL up to DP = 8): thread = component, its
+// parameters and its D+1 accumulators live in registers, the points of a tile stream through shared memory (every
+// lane reads the same point: LDS broadcast). The sum over points is then thread-local -- no warp shuffles, no shared
+// atomics; a CTA adds its K x (D+1) float64 partials to global memory once. Measured at config 3 (1e6 points x 256
+// proposals, D = 8) against the point-stationary kernel above, whose per-component warp reduction of D+1 values
+// dominates its time: see DESIGN.md section 4.4.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCsThreads = 128;      // components per CTA
+constexpr int kCsSub = 128;          // points per staged sub-tile (one per thread)
+constexpr int kCsSubTiles = 16;      // sub-tiles per CTA: 2048 points
+
+template <int KIND, int DP>
+__global__ void __launch_bounds__(kCsThreads)
+    mpmc_moments_cs_kernel(const float* __restrict__ x, int64_t n, int D, int vec_ok, const float* __restrict__ rows,
+                           const float* __restrict__ offs, int64_t K, float a_iso, const float* __restrict__ logq,
+                           const float* __restrict__ logw, float log2_norm, double* __restrict__ out) {
+  constexpr int ROW = row_floats(KIND, DP);
+  constexpr int XS = DP >= 4 ? DP : 4;                      // padded point row in shared memory (float4 reads)
+  __shared__ __align__(16) float sx[kCsSub * XS];
+  __shared__ float ssh[kCsSub];
+  const int64_t k = static_cast<int64_t>(blockIdx.y) * kCsThreads + threadIdx.x;
+  const bool live = k < K;
+  float row[ROW];
+  float c = -INFINITY;
+  if (live) {
+#pragma unroll
+    for (int q = 0; q < ROW; ++q) row[q] = __ldg(rows + k * ROW + q);
+    c = __ldg(offs + k);
+  } else {
+#pragma unroll
+    for (int q = 0; q < ROW; ++q) row[q] = 0.f;
+  }
+  double acc[DP + 1];
+#pragma unroll
+  for (int d = 0; d <= DP; ++d) acc[d] = 0.0;
+
+  const int64_t tile0 = static_cast<int64_t>(blockIdx.x) * (kCsSub * kCsSubTiles);
+#pragma unroll 1
+  for (int st = 0; st < kCsSubTiles; ++st) {
+    const int64_t base = tile0 + static_cast<int64_t>(st) * kCsSub;
+    if (base >= n) break;  // uniform across the CTA
+    // ---- stage: thread t loads point base + t and its shift log2 w~_i - log2 q(x_i) ----
+    {
+      const int64_t p = base + threadIdx.x;
+      float xv[XS];
+#pragma unroll
+      for (int d = 0; d < XS; ++d) xv[d] = 0.f;
+      float sh = -INFINITY;
+      if (p < n) {
+        if (DP >= 4 && D == DP && vec_ok) {
+#pragma unroll
+          for (int q = 0; q < DP / 4; ++q) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(x + p * DP) + q);
+            xv[4 * q] = f.x;
+            xv[4 * q + 1] = f.y;
+            xv[4 * q + 2] = f.z;
+            xv[4 * q + 3] = f.w;
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < DP; ++d)
+            if (d < D) xv[d] = __ldg(x + p * D + d);
+        }
+        const float lw = __ldg(logw + p), lq = __ldg(logq + p);
+        sh = (lw - lq) * 1.4426950408889634f - log2_norm;
+        if (!(sh == sh) || sh == INFINITY) sh = -INFINITY;
+      }
+#pragma unroll
+      for (int q = 0; q < XS / 4; ++q)
+        reinterpret_cast<float4*>(sx + threadIdx.x * XS)[q] = make_float4(xv[4 * q], xv[4 * q + 1], xv[4 * q + 2], xv[4 * q + 3]);
+      ssh[threadIdx.x] = sh;
+    }
+    __syncthreads();
+    // ---- this thread's component against the staged points ----
+    const int cnt = n - base < kCsSub ? static_cast<int>(n - base) : kCsSub;
+    float v[DP + 1];
+#pragma unroll
+    for (int d = 0; d <= DP; ++d) v[d] = 0.f;
+#pragma unroll 2
+    for (int i = 0; i < cnt; ++i) {
+      float xi[XS];
+#pragma unroll
+      for (int q = 0; q < XS / 4; ++q) {
+        const float4 f = reinterpret_cast<const float4*>(sx + i * XS)[q];
+        xi[4 * q] = f.x;
+        xi[4 * q + 1] = f.y;
+        xi[4 * q + 2] = f.z;
+        xi[4 * q + 3] = f.w;
+      }
+      float t = c;
+      if constexpr (KIND == AISB_COV_ISO_SHARED) {
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+          const float dl = fmaf(xi[d], a_iso, row[d]);
+          t = fmaf(-dl, dl, t);
+        }
+      } else if constexpr (KIND == AISB_COV_DIAG) {
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+          const float dl = fmaf(xi[d], row[d], row[DP + d]);
+          t = fmaf(-dl, dl, t);
+        }
+      } else {
+        constexpr int TRI = DP * (DP + 1) / 2;
+        int idx = 0;
+#pragma unroll
+        for (int r = 0; r < DP; ++r) {
+          float z = row[TRI + r];
+#pragma unroll
+          for (int cc = 0; cc <= r; ++cc) z = fmaf(row[idx++], xi[cc], z);
+          t = fmaf(-z, z, t);
+        }
+      }
+      const float a = ex2(t + ssh[i]);
+      v[0] += a;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) v[1 + d] = fmaf(a, xi[d], v[1 + d]);
+    }
+#pragma unroll
+    for (int d = 0; d <= DP; ++d) acc[d] += static_cast<double>(v[d]);
+    __syncthreads();  // the stage is overwritten by the next sub-tile
+  }
+  if (live) {
+#pragma unroll
+    for (int d = 0; d <= DP; ++d)
+      if (d <= D && acc[d] != 0.0) atomicAdd(&out[k * (D + 1) + d], acc[d]);
+  }
+}
+
+template <int KIND, int DP>
+static int launch_mpmc_cs_t(const float* x, int64_t n, int D, int vec_ok, const aisb_packed_mixture* mix,
+                            const float* logq, const float* logw, float log2_norm, double* out, cudaStream_t st) {
+  const int64_t tiles = (n + kCsSub * kCsSubTiles - 1) / (kCsSub * kCsSubTiles);
+  const dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>((mix->K + kCsThreads - 1) / kCsThreads));
+  mpmc_moments_cs_kernel<KIND, DP><<<grid, kCsThreads, 0, st>>>(x, n, D, vec_ok, mix->d_rows, mix->d_offsets, mix->K,
+                                                               mix->iso_scale, logq, logw, log2_norm, out);
+  AISB_LAUNCH_CHECK("mpmc_moments_cs_kernel");
+  return AISB_OK;
+}
+
+__host__ __device__ constexpr bool mpmc_cs_ok(int kind, int DP) {
+  return kind == AISB_COV_FULL ? DP <= 8 : DP <= 16;
+}
+
 template <int KIND, int DP>
 static int launch_mpmc_t(const float* x, int64_t n, int D, int vec_ok, const aisb_packed_mixture* mix,
                          const float* logq, const float* logw, float log2_norm, double* out, cudaStream_t st) {
+  if constexpr (mpmc_cs_ok(KIND, DP)) {
+    static const bool ps = [] {  // AISB_MPMC_POINT_STATIONARY=1 keeps the point-stationary kernel (timing experiments)
+      const char* e = getenv("AISB_MPMC_POINT_STATIONARY");
+      return e && e[0] == '1';
+    }();
+    if (!ps) return launch_mpmc_cs_t<KIND, DP>(x, n, D, vec_ok, mix, logq, logw, log2_norm, out, st);
+  }
   constexpr int E = points_per_thread(DP);
   constexpr size_t smem = pass_smem_bytes(KIND, DP, true) + sizeof(double) * chunk_comps(KIND, DP) * (DP + 1);
   auto kern = mpmc_moments_kernel<KIND, DP>;

@@ -140,11 +140,6 @@ __global__ void __launch_bounds__(256) logw_combine_kernel(const float* __restri
   block_weight_partials<E, 256>(lw, ok, red, block_partials + 4 * static_cast<int64_t>(blockIdx.x));
 }
 
-// a tensor-core kernel that aborted (barrier time-out) poisons the partial record: n_valid = -1
-__global__ void tc_abort_to_partials_kernel(const int32_t* __restrict__ err, double* __restrict__ partials) {
-  if (*err != 0) partials[3] = -1.0;
-}
-
 // ---------------------------------------------------------------------------------------------
 // KDE pack: rows[j][d] = -a * samples[idx[j]][d], pad dims 0, pad components 1e18
 // ---------------------------------------------------------------------------------------------
@@ -491,7 +486,7 @@ extern "C" int aisb_dm_weights_f32(const float* d_x, int64_t n, const aisb_packe
     logw_combine_kernel<<<static_cast<unsigned>(nblocks), 256, 0, st>>>(lp, lq, n, d_out_logw, ws.block_partials);
     AISB_LAUNCH_CHECK("logw_combine_kernel");
   }
-  weight_partials_merge_kernel<<<1, 256, 0, st>>>(ws.block_partials, nblocks, d_out_partials);
+  weight_partials_merge_kernel<<<1, 256, 0, st>>>(ws.block_partials, nblocks, d_out_partials, nullptr);
   AISB_LAUNCH_CHECK("weight_partials_merge_kernel");
   return AISB_OK;
 }
@@ -550,10 +545,9 @@ extern "C" int aisb_dm_weights_hinted_f32(const float* d_x, int64_t n, const ais
   if (rc) return rc;
   logw_combine_kernel<<<static_cast<unsigned>(nblocks), 256, 0, st>>>(lp, lq, n, d_out_logw, ws.block_partials);
   AISB_LAUNCH_CHECK("logw_combine_kernel");
-  weight_partials_merge_kernel<<<1, 256, 0, st>>>(ws.block_partials, nblocks, d_out_partials);
+  // a tensor-core kernel that aborted (barrier time-out) poisons the record: n_valid = -1
+  weight_partials_merge_kernel<<<1, 256, 0, st>>>(ws.block_partials, nblocks, d_out_partials, d_err);
   AISB_LAUNCH_CHECK("weight_partials_merge_kernel");
-  tc_abort_to_partials_kernel<<<1, 1, 0, st>>>(d_err, d_out_partials);
-  AISB_LAUNCH_CHECK("tc_abort_to_partials_kernel");
   return AISB_OK;
 }
 

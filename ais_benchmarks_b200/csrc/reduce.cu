@@ -4,7 +4,7 @@
 namespace aisb {
 
 __global__ void weight_partials_merge_kernel(const double* __restrict__ bp, int64_t nblocks,
-                                             double* __restrict__ out4) {
+                                             double* __restrict__ out4, const int32_t* __restrict__ abort) {
   __shared__ double sh[3][8];
   __shared__ double shM;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -48,7 +48,7 @@ __global__ void weight_partials_merge_kernel(const double* __restrict__ bp, int6
     out4[0] = M;
     out4[1] = a;
     out4[2] = b2;
-    out4[3] = c < 0.0 ? -1.0 : c;
+    out4[3] = (c < 0.0 || (abort != nullptr && *abort != 0)) ? -1.0 : c;
   }
 }
 
@@ -77,22 +77,33 @@ __global__ void normalize_weights_kernel(const float* __restrict__ logw, int64_t
   out[p] = expf((logw[p] - M) - logS);
 }
 
-// Same, with the (merged) record in device memory: thread 0 derives the two constants, block 0 also writes the
-// summary statistics {log sum w, ESS, n_finite}.
+// Same, with the record(s) in device memory: thread 0 folds the nrec records (one per rank after an all-gather, or one
+// per streamed chunk; log-sum-exp rescale rule, float64) and derives the two constants; block 0 also writes the summary
+// statistics {log sum w, ESS, n_finite}.
 __global__ void __launch_bounds__(256) normalize_weights_dev_kernel(const float* __restrict__ logw, int64_t n,
-                                                                    const double* __restrict__ rec,
+                                                                    const double* __restrict__ rec, int nrec,
                                                                     float* __restrict__ out,
                                                                     double* __restrict__ stats, int vec_ok) {
   __shared__ float shc[2];
   if (threadIdx.x == 0) {
-    const double M = rec[0], S1 = rec[1], S2 = rec[2];
+    double M = rec[0];
+    for (int r = 1; r < nrec; ++r) M = fmax(M, rec[4 * r]);
+    double S1 = 0.0, S2 = 0.0, cnt = 0.0;
+    bool poisoned = false;
+    for (int r = 0; r < nrec; ++r) {
+      const double f = exp(rec[4 * r] - M);
+      S1 += rec[4 * r + 1] * f;
+      S2 += rec[4 * r + 2] * f * f;
+      poisoned |= rec[4 * r + 3] < 0.0;
+      cnt += rec[4 * r + 3];
+    }
     const float Mf = static_cast<float>(M);
     shc[0] = Mf;
     shc[1] = static_cast<float>(log(S1) + (M - static_cast<double>(Mf)));
     if (blockIdx.x == 0 && stats) {
       stats[0] = M + log(S1);
       stats[1] = S2 > 0.0 ? S1 * S1 / S2 : 0.0;
-      stats[2] = rec[3];
+      stats[2] = poisoned ? -1.0 : cnt;
     }
   }
   __syncthreads();
@@ -352,7 +363,7 @@ extern "C" int aisb_logw_partials_f32(const float* d_logw, int64_t n, double* d_
     logw_partials_kernel<<<static_cast<unsigned>(nblocks), 256, 0, st>>>(d_logw, n, bp);
     AISB_LAUNCH_CHECK("logw_partials_kernel");
   }
-  weight_partials_merge_kernel<<<1, 256, 0, st>>>(bp, nblocks, d_out_partials);
+  weight_partials_merge_kernel<<<1, 256, 0, st>>>(bp, nblocks, d_out_partials, nullptr);
   AISB_LAUNCH_CHECK("weight_partials_merge_kernel");
   return AISB_OK;
 }
@@ -378,7 +389,8 @@ extern "C" int aisb_weight_records_merge(const double* d_records, int64_t n_reco
     set_error("weight_records_merge: null pointer or n_records < 1");
     return AISB_ERR_INVALID;
   }
-  weight_partials_merge_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_records, n_records, d_out_partials);
+  weight_partials_merge_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_records, n_records, d_out_partials,
+                                                                                 nullptr);
   AISB_LAUNCH_CHECK("weight_partials_merge_kernel");
   return AISB_OK;
 }
@@ -394,10 +406,10 @@ extern "C" int aisb_kld_records_merge(const double* d_records, int64_t n_records
   return AISB_OK;
 }
 
-extern "C" int aisb_normalize_weights_dev_f32(const float* d_logw, int64_t n, const double* d_partials, float* d_out_w,
-                                              double* d_out_stats, void* stream) {
-  if (n < 0 || !d_partials || (n > 0 && (!d_logw || !d_out_w))) {
-    set_error("normalize_weights_dev: null pointer or negative n");
+extern "C" int aisb_normalize_weights_dev_f32(const float* d_logw, int64_t n, const double* d_records,
+                                              int32_t n_records, float* d_out_w, double* d_out_stats, void* stream) {
+  if (n < 0 || !d_records || n_records < 1 || n_records > 4096 || (n > 0 && (!d_logw || !d_out_w))) {
+    set_error("normalize_weights_dev: null pointer, negative n or n_records outside 1..4096");
     return AISB_ERR_INVALID;
   }
   // float4 accesses when both vectors are 16-byte aligned (always true for whole tensors), scalar ones for odd views
@@ -405,7 +417,7 @@ extern "C" int aisb_normalize_weights_dev_f32(const float* d_logw, int64_t n, co
   // n == 0 still launches one block so that the statistics are written
   const int64_t blocks = n > 0 ? (n + 1023) / 1024 : 1;
   normalize_weights_dev_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_logw, n, d_partials, d_out_w, d_out_stats, vec_ok);
+      d_logw, n, d_records, n_records, d_out_w, d_out_stats, vec_ok);
   AISB_LAUNCH_CHECK("normalize_weights_dev_kernel");
   return AISB_OK;
 }

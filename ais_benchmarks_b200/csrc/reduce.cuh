@@ -62,8 +62,9 @@ __device__ __forceinline__ void block_weight_partials(const float (&lw)[E], cons
 
 #endif
 
-// one block of 256 threads folds `nblocks` weight records into one
+// one block of 256 threads folds `nblocks` weight records into one; a non-zero *abort (nullable: the abort counter of a
+// tensor-core kernel) poisons the result (n_valid = -1)
 __global__ void weight_partials_merge_kernel(const double* __restrict__ block_partials, int64_t nblocks,
-                                             double* __restrict__ out4);
+                                             double* __restrict__ out4, const int32_t* __restrict__ abort);
 
 }  // namespace aisb

@@ -66,11 +66,11 @@ def all_gather_records_dev(record):
     return out
 
 
-def global_weight_record_dev(local_record):
-    """Device-resident counterpart of global_weight_partials: all ranks' weight records gathered over NCCL and merged
-    by a one-block kernel; the result (float64 CUDA [4]) feeds _device.normalize_weights_dev without a host round trip."""
-    recs = all_gather_records_dev(local_record)
-    return local_record if recs.shape[0] == 1 else _device.merge_weight_records(recs)
+def global_weight_record_dev(local_records):
+    """Device-resident counterpart of global_weight_partials: this rank's weight record(s) ([4] or [C, 4], float64 CUDA)
+    all-gathered over NCCL -> [ranks * C, 4], still on the device. _device.normalize_weights_dev folds them inside
+    its own kernel, so a weighting step has no host round trip and no separate merge launch."""
+    return all_gather_records_dev(local_records.reshape(-1)).reshape(-1, 4)
 
 
 def merge_weight_partials(records):

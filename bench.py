@@ -271,8 +271,8 @@ def run_cuda(args):
             dm_kernel.append((e0, e1))
         else:
             _, logw, part = _device.dm_weights_streamed(xs_pin, tmix, qmix, hint=own, x_out=xs_stage)
-        g = parallel.global_weight_record_dev(part)                     # device all-gather + merge kernel
-        wn, stats = _device.normalize_weights_dev(logw, g)              # normalised weights + statistics stay in HBM
+        g = parallel.global_weight_record_dev(part)                     # NCCL all-gather of the records (N > 1)
+        wn, stats = _device.normalize_weights_dev(logw, g)              # folds the records; weights + statistics stay in HBM
         return stats, wn
 
     def dm_result(stats):
@@ -389,9 +389,9 @@ def run_cuda(args):
                                                   "peak_pairs_per_s": ex2_peak,
                                                   "note": "peak = 16 accumulator words per clk per SM = the measured "
                                                           "MUFU.EX2 rate; achieved includes the target pass"}},
-                       # target logpdf + tc_logq + logw_combine + block-record merge + abort flag + normalise
-                       # (+ the cross-rank record merge for N > 1)
-                       "gpu_launches": (6 if world == 1 else 7) * args.steps},
+                       # target logpdf + tc_logq + logw_combine + block-record merge + normalise (our kernels; the NCCL
+                       # all-gather of the records for N > 1 is not counted)
+                       "gpu_launches": 5 * args.steps},
         }
         print_json(out)
     if world > 1:

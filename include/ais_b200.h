@@ -172,14 +172,15 @@ int aisb_normalize_weights_f32(const float* d_logw, int64_t n, const double* h_p
  *   aisb_weight_records_merge / aisb_kld_records_merge: fold n_records records that live in DEVICE memory (one per
  *       rank after an all-gather, or one per streamed chunk) into d_out_partials (device, 4 resp. 8 doubles) with the
  *       same log-sum-exp rescale rule as the host helpers below.
- *   aisb_normalize_weights_dev_f32: aisb_normalize_weights_f32 with the (merged) record read from device memory;
- *       d_out_stats (device, nullable) receives {log sum_i w_i, ESS = (sum w)^2 / sum w^2, n_finite}
+ *   aisb_normalize_weights_dev_f32: aisb_normalize_weights_f32 with the record(s) read from device memory: d_records
+ *       holds n_records (1..4096) records, folded inside the kernel (so an all-gathered [ranks, 4] buffer can be passed
+ *       as it is); d_out_stats (device, nullable) receives {log sum_i w_i, ESS = (sum w)^2 / sum w^2, n_finite}
  *       (sampling_methods/base.py:72-75 without leaving HBM).
  */
 int aisb_weight_records_merge(const double* d_records, int64_t n_records, double* d_out_partials, void* stream);
 int aisb_kld_records_merge(const double* d_records, int64_t n_records, double* d_out_partials, void* stream);
-int aisb_normalize_weights_dev_f32(const float* d_logw, int64_t n, const double* d_partials, float* d_out_w,
-                                   double* d_out_stats, void* stream);
+int aisb_normalize_weights_dev_f32(const float* d_logw, int64_t n, const double* d_records, int32_t n_records,
+                                   float* d_out_w, double* d_out_stats, void* stream);
 
 /*
  * Host-side helpers on partials (no CUDA): merge two partial records with the

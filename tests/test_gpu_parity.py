@@ -272,9 +272,11 @@ def test_device_resident_records_and_streamed_weighting():
         xs, logw_s, rec_s = _device.dm_weights_streamed(xp, tmix, q, hint=hint, chunk_rows=chunk)
         assert torch.equal(xs, xd)
         assert torch.equal(logw_s, logw)
-        rs_ = rec_s.cpu().numpy()
+        assert rec_s.shape == (3, 4)
+        rs_ = _device.merge_weight_records(rec_s).cpu().numpy()
         assert rs_[3] == n and rs_[0] + np.log(rs_[1]) == pytest.approx(ph[0] + np.log(ph[1]), abs=1e-6)
-        w_s, _ = _device.normalize_weights_dev(logw_s, rec_s)
+        w_s, st_s = _device.normalize_weights_dev(logw_s, rec_s)      # the kernel folds the chunk records itself
+        assert st_s.cpu().numpy()[2] == n and st_s.cpu().numpy()[1] == pytest.approx(_device.weight_ess(ph), rel=1e-9)
         assert np.max(np.abs(w_s.cpu().numpy() - w_host)) <= 2e-6 * w_host.max()
         # (4) float64 oracle on the same float32 samples
         x64 = x.astype(np.float64)
@@ -449,6 +451,51 @@ def test_mpmc_iteration_golden():
             live = g["new_alpha" + t] > 1e-9
             assert np.allclose(s._means[live], g["new_means" + t][live], rtol=W_TOL, atol=1e-5)
             assert np.allclose(s._covs[live], g["new_covs" + t][live], rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("D", [1, 3, 8, 16, 32])
+@pytest.mark.parametrize("kind", ["iso", "diag", "full"])
+def test_mpmc_moment_kernels_vs_oracle(kind, D):
+    """Rao-Blackwellised M-PMC moments (m_pmc.py:57-61,102-105) for every kernel variant -- the component-stationary
+    kernel (small rows) and the point-stationary one (large rows) -- against a float64 evaluation of
+    sum_i w~_i rho_di [1, x_i]; ragged sizes (n not a multiple of the tiles, K not a multiple of 128)."""
+    from ais_benchmarks_b200 import _device, _lib
+    from scipy.special import logsumexp
+    rs = np.random.RandomState(100 * D + len(kind))
+    n, K = 2048 * 2 + 517, 150
+    mu = rs.uniform(-1, 1, size=(K, D))
+    w = rs.rand(K)
+    w[5] = 0.0
+    w /= w.sum()
+    x = rs.uniform(-1.2, 1.2, size=(n, D)).astype(np.float32)
+    x64 = x.astype(np.float64)
+    if kind == "iso":
+        covs = np.stack([np.eye(D) * 0.3] * K)
+        mix = _device.DeviceMixture.from_params(mu, np.array([0.3]), w, _lib.COV_ISO_SHARED)
+    elif kind == "diag":
+        var = rs.uniform(0.1, 0.4, size=(K, D))
+        covs = np.stack([np.diag(v) for v in var])
+        mix = _device.DeviceMixture.from_params(mu, var, w, _lib.COV_DIAG)
+    else:
+        a = rs.normal(size=(K, D, D)) * 0.2
+        covs = a @ np.transpose(a, (0, 2, 1)) + 0.15 * np.eye(D)
+        mix = _device.DeviceMixture.from_params(mu, covs, w, _lib.COV_FULL)
+    with np.errstate(divide="ignore"):
+        comp = np.stack([O.mvn_log_prob(x64, mu[k], covs[k]) + np.log(w[k]) for k in range(K)])   # [K, n]
+    logq = logsumexp(comp, axis=0)
+    logw = rs.normal(size=n) * 2.0
+    logw[7] = -np.inf                     # a zero-weight sample contributes nothing
+    log_norm = logsumexp(logw)
+    a_ki = np.exp(comp - logq[None, :] + (logw - log_norm)[None, :])
+    ref = np.concatenate([a_ki.sum(1, keepdims=True), a_ki @ x64], axis=1)
+    xd = torch.from_numpy(x).cuda()
+    got = _device.mpmc_moments(xd, mix, torch.from_numpy(logq).cuda().float(), torch.from_numpy(logw).cuda().float(),
+                               float(log_norm)).cpu().numpy()
+    assert got.shape == (K, D + 1)
+    assert np.all(got[5] == 0.0)
+    scale = np.abs(ref).max(axis=1, keepdims=True) + 1e-12
+    assert np.max(np.abs(got - ref) / scale) < W_TOL
+    assert abs(got[:, 0].sum() - 1.0) < 1e-4      # sum_d alpha_d = 1
 
 
 def test_lais_chains_golden():
