@@ -96,6 +96,13 @@ def workspace(nbytes):
     return ws
 
 
+def workspace_bytes_for(n, K, D):
+    lib = require_cuda()
+    need = C.c_size_t(0)
+    check(lib.aisb_workspace_bytes(int(n), int(K), int(D), C.byref(need)), "aisb_workspace_bytes")
+    return int(need.value)
+
+
 def workspace_for(n, K, D):
     lib = require_cuda()
     need = C.c_size_t(0)
@@ -239,11 +246,13 @@ def tc_operand(mix):
 
 
 def dm_weights(x, target, logp_in, proposals, want_logp=False, want_logq=False, hint=None, out_logw=None,
-               out_partials=None):
+               out_partials=None, ws=None):
     """DM weights. Without `hint`: the fused CUDA-core kernel (C ABI aisb_dm_weights_f32). With `hint` (int32 CUDA [n],
     the proposal each sample was drawn from) and an eligible proposal mixture: proposal density on the tensor cores
     (aisb_dm_weights_hinted_f32). Returns (logw, logp|None, logq|None, partials[4] device f64). out_logw [n] float32 /
-    out_partials [4] float64 (contiguous CUDA views) receive the results in place when given (streamed weighting)."""
+    out_partials [4] float64 (contiguous CUDA views) receive the results in place when given (streamed weighting). `ws`:
+    a caller-owned workspace (uint8 CUDA tensor, see workspace_bytes_for) instead of the shared per-device one -- a
+    captured CUDA graph must own every buffer it touches."""
     lib = require_cuda()
     operand = tc_operand(proposals) if hint is not None and x.shape[0] > 0 else None
     if operand is not None:
@@ -256,7 +265,8 @@ def dm_weights(x, target, logp_in, proposals, want_logp=False, want_logq=False, 
     logq = torch.empty(n, dtype=torch.float32, device=dev) if want_logq else None
     partials = torch.empty(4, dtype=torch.float64, device=dev) if out_partials is None else out_partials
     Kmax = max(proposals.K, target.K if target is not None else 1)
-    ws = workspace_for(max(n, 1), Kmax, proposals.D)
+    if ws is None:
+        ws = workspace_for(max(n, 1), Kmax, proposals.D)
     check(lib.aisb_dm_weights_f32(_ptr(x), n, target.ref() if target is not None else None, _ptr(logp_in),
                                   proposals.ref(), _ptr(logw), _ptr(logp), _ptr(logq), _ptr(partials), _ptr(ws),
                                   ws.numel(), stream_ptr()), "aisb_dm_weights_f32")
@@ -544,6 +554,32 @@ def sample_iso(means, per, var):
     off = _next_offset(K * per * D)
     check(lib.aisb_sample_iso_f32(_ptr(means), K, D, int(per), float(var), _rng_state["seed"], off, _ptr(out),
                                   stream_ptr()), "aisb_sample_iso_f32")
+    return out
+
+
+_GRAPH_STREAM_KEY = 0x9E3779B97F4A7C15  # Philox key offset of the device-counter stream (disjoint from the host-offset stream)
+_rng_counters = {}
+
+
+def rng_counter():
+    """Device-resident position of the Philox stream used inside captured CUDA graphs (one int64 per device)."""
+    dev = torch.cuda.current_device()
+    key = (dev, _rng_state["seed"])
+    if key not in _rng_counters:
+        _rng_counters[key] = torch.zeros(1, dtype=torch.int64, device=device())
+    return _rng_counters[key]
+
+
+def sample_iso_ctr(means, per, var, out=None):
+    """sample_iso with the stream position in device memory (C ABI aisb_sample_iso_ctr_f32): safe to capture in a CUDA
+    graph -- every replay draws fresh numbers."""
+    lib = require_cuda()
+    K, D = means.shape
+    if out is None:
+        out = torch.empty((K * per, D), dtype=torch.float32, device=means.device)
+    check(lib.aisb_sample_iso_ctr_f32(_ptr(means), K, D, int(per), float(var),
+                                      (_rng_state["seed"] ^ _GRAPH_STREAM_KEY) & 0xFFFFFFFFFFFFFFFF, _ptr(rng_counter()),
+                                      _ptr(out), stream_ptr()), "aisb_sample_iso_ctr_f32")
     return out
 
 

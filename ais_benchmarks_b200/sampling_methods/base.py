@@ -331,13 +331,14 @@ mixture_component_draws = _device.mixture_component_draws
 
 def multinomial_resample(logw, n_draws):
     """n_draws indices ~ Categorical(w / sum w), w = exp(logw) (dm_ais.py:47-54). Invalid (NaN / +inf) weights
-    count as zero. Inverse-CDF on the device: cumsum + searchsorted, float64."""
+    count as zero; if no weight is left the draw is uniform. Inverse-CDF on the device: cumsum + searchsorted, float64.
+    No host synchronisation (the degenerate case is a device-side select), so the call can sit in a CUDA graph."""
     lw = logw.double()
     lw = torch.where(torch.isfinite(lw) | (lw == -math.inf), lw, torch.full_like(lw, -math.inf))
     m = torch.max(lw)
-    if not torch.isfinite(m):
-        return torch.randint(0, logw.shape[0], (n_draws,), device=logw.device)
-    cdf = torch.cumsum(torch.exp(lw - m), 0)
+    ok = torch.isfinite(m)
+    w = torch.where(ok, torch.exp(lw - torch.where(ok, m, torch.zeros_like(m))), torch.ones_like(lw))
+    cdf = torch.cumsum(w, 0)
     u = torch.rand(n_draws, dtype=torch.float64, device=logw.device) * cdf[-1]
     return torch.clamp(torch.searchsorted(cdf, u, right=True), max=logw.shape[0] - 1)
 

@@ -28,6 +28,9 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
               proposal; the proposal means stay replicated (two-level multinomial resampling + an all-gather of the N
               chosen means per iteration); returned samples are this rank's rows, their weights are normalised over
               ALL ranks and iterations
+            - cuda_graph (optional, default "auto"): capture one whole adapt iteration (draws, proposal packing, weight
+              kernel, resampling) in a CUDA graph and replay it; "auto" does so when an iteration is launch-bound
+              (at most GRAPH_MAX_BATCH draws, packed Gaussian target, not sharded); False keeps eager launches
         """
         super(CDeterministicMixtureAIS, self).__init__(params)
         self.K = params["K"]
@@ -35,6 +38,8 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
         self.J = params["J"]
         self.sigma = params["sigma"]
         self.sharded = bool(params.get("sharded", False))
+        self.cuda_graph = params.get("cuda_graph", "auto")
+        self._captured = None
         self._means = None
         self._mixture = None
         self._objects = None
@@ -168,6 +173,76 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
         rec = self._global_partials()
         return _device.weight_ess(rec) / rec[3]
 
+    # -- one adapt iteration as a replayed CUDA graph ------------------------------------------------
+    GRAPH_MAX_BATCH = 1 << 18   # draws per iteration up to which an iteration is launch-bound on a B200
+
+    def _graph_wanted(self, target_d, per):
+        if self.cuda_graph is False or self.cuda_graph == "off" or self.sharded or per < 1:
+            return False
+        if target_device_mixture(target_d) is None:
+            return False          # a foreign target runs host code inside the iteration
+        return self.cuda_graph is True or self.N * per <= self.GRAPH_MAX_BATCH
+
+    def _adapt_in_graph(self, mbuf, x, logw, target):
+        """The adaptation step of the captured iteration, in place on the proposal means `mbuf` (DM-PMC resampling,
+        dm_ais.py:47-56). Overridden by LAIS."""
+        mbuf.copy_(x[multinomial_resample(logw, self.N)])
+
+    def _iteration_ops(self, mbuf, target, per, ws):
+        """Every device operation of one iteration, on buffers the caller owns (capturable: no host synchronisation,
+        Philox position in device memory). The proposal density runs on the CUDA cores here -- the batches this path is
+        meant for are far too small for the tensor-core kernel to matter."""
+        x = _device.sample_iso_ctr(mbuf, per, float(self.sigma))
+        mix = _device.DeviceMixture.kde(mbuf, None, self.N, float(self.sigma))
+        logw, _, _, part = _device.dm_weights(x, target, None, mix, ws=ws)
+        self._adapt_in_graph(mbuf, x, logw, target)
+        return x, logw, part, mix
+
+    def _prepare_graph(self, dev):
+        """Hook: device constants an iteration needs, created eagerly BEFORE the capture (host-to-device copies from
+        pageable memory are not capturable)."""
+
+    def _captured_iteration(self, target_d, per):
+        """Build (once per target / shape) and return the captured iteration."""
+        target = target_device_mixture(target_d)
+        key = (target.rows.data_ptr(), target.K, int(self.N), int(per), float(self.sigma), int(self.ndims))
+        cap = self._captured
+        if cap is None or cap["key"] != key:
+            dev = _device.device()
+            self._prepare_graph(dev)
+            means = torch.empty((self.N, self.ndims), dtype=torch.float32, device=dev)
+            ws = torch.empty(_device.workspace_bytes_for(self.N * per, max(self.N, target.K), self.ndims) + 256,
+                             dtype=torch.uint8, device=dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):          # warm-up on a scratch copy: loads the kernels, adapts nothing
+                scratch = self.proposal_means().clone()
+                for _ in range(2):
+                    self._iteration_ops(scratch, target, per, ws)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                x, logw, part, mix = self._iteration_ops(means, target, per, ws)
+            cap = {"key": key, "graph": graph, "means": means, "x": x, "logw": logw, "part": part,
+                   "keep": (mix, ws, target)}
+            self._captured = cap
+        if self._means is not cap["means"]:          # reset() / a caller replaced the proposal means
+            cap["means"].copy_(self.proposal_means())
+            self._set_means_dev(cap["means"])
+        return cap
+
+    def _graph_iteration(self, target_d, per):
+        cap = self._captured_iteration(target_d, per)
+        cap["graph"].replay()
+        # the means changed in place: everything derived from them is stale
+        self._mixture = None
+        self._objects = None
+        self._num_q_samples += self.N * per
+        self._num_pi_evals += self.N * per
+        # the graph's outputs are overwritten by the next replay: the accumulated state gets copies
+        self._append(cap["x"].clone(), cap["logw"].clone())
+        self._n_all_ranks += self.N * int(self.K)
+
     def importance_sample(self, target_d, n_samples, timeout=60):
         elapsed_time = 0
         t_ini = time.time()
@@ -175,6 +250,10 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
         # n_samples is the total wanted over all ranks; every iteration adds N*K of them
         # (sharded: the loop is driven by the sample count alone -- a per-rank clock must not desynchronise the collectives)
         while n_samples > (self._n_all_ranks if self.sharded else self._n()) and (self.sharded or elapsed_time < timeout):
+            if self._graph_wanted(target_d, per):
+                self._graph_iteration(target_d, per)
+                elapsed_time = time.time() - t_ini
+                continue
             # K samples from each proposal, proposal-major like dm_ais.py:64-69
             new_samples = _device.sample_iso(self.proposal_means(), per, float(self.sigma))
             self._num_q_samples += self.N * per

@@ -57,6 +57,24 @@ class CLayeredAIS(CDeterministicMixtureAIS):
             means = parallel.all_gather_rows(means, counts)
         self._set_means_dev(means)
 
+    def _prepare_graph(self, dev):
+        self._graph_consts = (torch.zeros((1, self.ndims), dtype=torch.float32, device=dev),
+                              torch.from_numpy(self.space_min.astype(np.float32)).to(dev),
+                              torch.from_numpy(self.space_max.astype(np.float32)).to(dev))
+
+    def _adapt_in_graph(self, mbuf, x, logw, target):
+        """Captured-iteration counterpart of resample(): L MH steps of all N chains, in place on the means."""
+        zeros, lo, hi = self._graph_consts
+        delta = _device.sample_iso_ctr(zeros, int(self.L) * int(self.N), float(self.mhsigma))
+        u = torch.rand((int(self.L), int(self.N)), dtype=torch.float32, device=mbuf.device)
+        _device.lais_mh(mbuf, target, delta.reshape(self.L, self.N, self.ndims), u, lo, hi)
+        self._graph_mh_keep = (delta, u)
+
+    def _graph_iteration(self, target_d, per):
+        super(CLayeredAIS, self)._graph_iteration(target_d, per)
+        self._num_pi_evals += 2 * self.L * self.N
+        self._num_q_samples += self.L * self.N
+
     def resample(self, target_d):
         if self.sharded:
             from .. import parallel
@@ -73,6 +91,10 @@ class CLayeredAIS(CDeterministicMixtureAIS):
         per = self._draws_per_proposal()
         # (sharded: the loop is driven by the sample count alone -- a per-rank clock must not desynchronise the collectives)
         while n_samples > (self._n_all_ranks if self.sharded else self._n()) and (self.sharded or elapsed_time < timeout):
+            if self._graph_wanted(target_d, per):
+                self._graph_iteration(target_d, per)
+                elapsed_time = time.time() - t_ini
+                continue
             new_samples = _device.sample_iso(self.proposal_means(), per, float(self.sigma))
             self._num_q_samples += self.N * per
             new_logw, _ = self.weigh(new_samples, target_d, hint=self._own_proposal(per))

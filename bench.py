@@ -311,6 +311,23 @@ def run_cuda(args):
     assert abs(ness_e - ness) <= 1e-6 * max(1.0, abs(ness)), (ness_e, ness)
     dm_flops = float(n_local) * (N * (3 * D2 + 6) + dc["modes"] * (4 * D2 + 6))
     dm_tflops = dm_flops / (dm_kernel_ms * 1e-3) / 1e12
+    # the two kernels of a weighting step timed alone (untimed extras, after the measured loops), each against its own bound
+    def best_ms(fn, reps=3):
+        fn()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return min(ts)
+    scratch = torch.empty(n_local, dtype=torch.float32, device=dev)
+    operand = _device.tc_operand(qmix)
+    tc_ms = best_ms(lambda: _device.tc_logq(xs, operand, own, scratch)) if operand is not None else None
+    tgt_ms = best_ms(lambda: _device.mixture_logpdf(xs, tmix, scratch))
+    del scratch
 
     # ---- live FP32-FMA / MUFU.EX2 peaks on this GPU (roofline denominators for the compute-bound kernels), measured
     # after the workloads so that the clocks have ramped up exactly as they had for the timed kernels ---------------
@@ -385,10 +402,21 @@ def run_cuda(args):
                                     "kernel": "tc_logq_kernel<32> (tcgen05 TF32 screen + exact refinement) + "
                                               "logpdf_kernel<DIAG,32> for the 64-mode target",
                                     "kernel_ms": dm_kernel_ms,
-                                    "tmem_read": {"achieved_pairs_per_s": float(n_local) * N / (dm_kernel_ms * 1e-3),
-                                                  "peak_pairs_per_s": ex2_peak,
-                                                  "note": "peak = 16 accumulator words per clk per SM = the measured "
-                                                          "MUFU.EX2 rate; achieved includes the target pass"}},
+                                    # per kernel, timed alone, each against the unit that binds it
+                                    "kernels": {
+                                        "tc_logq_kernel": None if tc_ms is None else {
+                                            "ms": tc_ms, "bound": "tmem-read",
+                                            "achieved": float(n_local) * N / (tc_ms * 1e-3), "peak": ex2_peak,
+                                            "unit": "accumulator columns/s (= pairs/s)",
+                                            "frac": float(n_local) * N / (tc_ms * 1e-3) / ex2_peak,
+                                            "note": "peak = 16 32-bit TMEM columns per clk per SM (tcgen05.ld), numerically "
+                                                    "the MUFU.EX2 rate measured live in this run"},
+                                        "logpdf_kernel<DIAG,32>": {
+                                            "ms": tgt_ms, "bound": "fp32",
+                                            "achieved": float(n_local) * dc["modes"] * (4 * D2 + 6) / (tgt_ms * 1e-3) / 1e12,
+                                            "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+                                            "frac": float(n_local) * dc["modes"] * (4 * D2 + 6) / (tgt_ms * 1e-3) / 1e12
+                                                    / fp32_peak_tflops}}},
                        # target logpdf + tc_logq + logw_combine + block-record merge + normalise (our kernels; the NCCL
                        # all-gather of the records for N > 1 is not counted)
                        "gpu_launches": 5 * args.steps},
