@@ -48,6 +48,8 @@ PROTOTYPES = {
     "aisb_normalize_weights_f32": (C.c_int, [_vp, _i64, C.POINTER(_dbl), _vp, _vp]),
     "aisb_weight_records_merge": (C.c_int, [_vp, _i64, _vp, _vp]),
     "aisb_kld_records_merge": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "aisb_weight_exchange_doubles": (_i64, [_i32]),
+    "aisb_weight_records_exchange": (C.c_int, [_vp, _vp, _i32, _i32, _u64, _vp, _vp]),
     "aisb_normalize_weights_dev_f32": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _vp, _vp]),
     "aisb_weight_partials_merge": (None, [C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_dbl)]),
     "aisb_weight_partials_ess": (_dbl, [C.POINTER(_dbl)]),

@@ -122,6 +122,50 @@ __global__ void __launch_bounds__(256) normalize_weights_dev_kernel(const float*
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cross-rank exchange of the 4-double weight records over NVLink peer memory (one CTA, no NCCL launch).
+// Every rank owns a symmetric buffer laid out as
+//     double rec[2][world][4];  unsigned long long flag[2][world];        (index 0/1 = epoch parity)
+// and sees its peers' buffers through peer_bufs[r]. Thread r of the CTA stores this rank's record into slot
+// [parity][rank] of peer r, fences, and publishes the epoch number in the matching flag; then it waits for the flag
+// of slot [parity][r] in the LOCAL buffer and copies that record out. Two parities make the slots safe to re-use: a
+// peer can only reach epoch e+2 after this rank has published epoch e+1, i.e. after everything it enqueued for epoch e
+// (including the kernels that read out[]) has completed. The wait is bounded; a time-out poisons the record.
+// ---------------------------------------------------------------------------------------------
+__global__ void weight_records_exchange_kernel(const double* __restrict__ local_rec, double* const* __restrict__ peer_bufs,
+                                               int rank, int world, unsigned long long epoch,
+                                               double* __restrict__ out) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  const int par = static_cast<int>(epoch & 1ull);
+  {
+    double* pb = peer_bufs[r];
+    volatile double* slot = pb + (static_cast<size_t>(par) * world + rank) * 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) slot[q] = local_rec[q];
+    __threadfence_system();
+    volatile unsigned long long* flag =
+        reinterpret_cast<unsigned long long*>(pb + static_cast<size_t>(2) * world * 4) + par * world + rank;
+    *flag = epoch;
+  }
+  double* mine = peer_bufs[rank];
+  volatile unsigned long long* flag =
+      reinterpret_cast<unsigned long long*>(mine + static_cast<size_t>(2) * world * 4) + par * world + r;
+  const long long t0 = clock64();
+  bool ok = true;
+  while (*flag < epoch) {
+    if (clock64() - t0 > (1ll << 32)) {  // ~2 s: a peer never arrived
+      ok = false;
+      break;
+    }
+  }
+  __threadfence_system();
+  const volatile double* src = mine + (static_cast<size_t>(par) * world + r) * 4;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) out[4 * r + q] = src[q];
+  if (!ok) out[4 * r + 3] = -1.0;
+}
+
 // KLD block record (8 doubles): { m_p, S_p, A, m_q, S_q, n_inlier, n_posinf_q, n_total }
 // Inliers: lp > floor and lq > floor (floor = -inf for the KLD; the float64 underflow threshold of exp() for the
 // linear-domain JSD of the reference, divergences.py:170-173).
@@ -392,6 +436,24 @@ extern "C" int aisb_weight_records_merge(const double* d_records, int64_t n_reco
   weight_partials_merge_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_records, n_records, d_out_partials,
                                                                                  nullptr);
   AISB_LAUNCH_CHECK("weight_partials_merge_kernel");
+  return AISB_OK;
+}
+
+extern "C" int64_t aisb_weight_exchange_doubles(int32_t world) {
+  return world < 1 ? 0 : static_cast<int64_t>(2) * world * 4 + static_cast<int64_t>(2) * world;
+}
+
+extern "C" int aisb_weight_records_exchange(const double* d_local_record, void* const* d_peer_bufs, int32_t rank,
+                                            int32_t world, uint64_t epoch, double* d_out_records, void* stream) {
+  if (!d_local_record || !d_peer_bufs || !d_out_records || world < 1 || world > 256 || rank < 0 || rank >= world ||
+      epoch == 0) {
+    set_error("weight_records_exchange: null pointer, bad rank/world or epoch 0");
+    return AISB_ERR_INVALID;
+  }
+  weight_records_exchange_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_local_record, reinterpret_cast<double* const*>(d_peer_bufs), rank, world,
+      static_cast<unsigned long long>(epoch), d_out_records);
+  AISB_LAUNCH_CHECK("weight_records_exchange_kernel");
   return AISB_OK;
 }
 

@@ -66,10 +66,78 @@ def all_gather_records_dev(record):
     return out
 
 
+class PeerRecordExchange:
+    """Weight-record exchange over NVLink peer memory (C ABI aisb_weight_records_exchange): a symmetric buffer per
+    rank (torch.distributed._symmetric_memory), one 1-CTA kernel per exchange, no collective launch. Created
+    collectively on first use; if symmetric memory is not available on ANY rank, every rank falls back to the NCCL
+    all-gather (the decision is agreed with an all-reduce so that the ranks cannot diverge)."""
+    _instance = None
+    _disabled = False
+
+    def __init__(self):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        lib = _device.require_cuda()
+        self.rank, self.world = world()
+        self.lib, self.C = lib, C
+        n = int(lib.aisb_weight_exchange_doubles(self.world))
+        group = dist.group.WORLD
+        self.buf = symm.empty(n, dtype=torch.float64, device=_device.device())
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group)
+        self.peer_ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64,
+                                      device=_device.device())
+        self.epoch = 0
+        torch.cuda.synchronize()
+        dist.barrier()          # every rank's buffer is zeroed and mapped before the first flag is written
+
+    def exchange(self, local_record):
+        """local_record: float64 CUDA [4] -> [world, 4] float64 CUDA (stream-ordered, no host synchronisation)."""
+        self.epoch += 1
+        out = torch.empty((self.world, 4), dtype=torch.float64, device=local_record.device)
+        rec = local_record.reshape(-1).contiguous()
+        _device.check(self.lib.aisb_weight_records_exchange(
+            self.C.c_void_p(rec.data_ptr()), self.C.c_void_p(self.peer_ptrs.data_ptr()), self.rank, self.world,
+            self.epoch, self.C.c_void_p(out.data_ptr()), _device.stream_ptr()), "aisb_weight_records_exchange")
+        return out
+
+    @classmethod
+    def get(cls):
+        """The process-wide exchange, or None (not NCCL, single rank, switched off with AISB_P2P=0, or unavailable)."""
+        import os
+        if cls._instance is not None or cls._disabled:
+            return cls._instance
+        _, ws = world()
+        if ws == 1 or dist.get_backend() != "nccl" or os.environ.get("AISB_P2P", "1") == "0":
+            cls._disabled = True
+            return None
+        inst, ok = None, 1
+        try:
+            inst = cls()
+        except Exception as e:  # noqa: BLE001 -- any failure means "use NCCL", agreed below
+            ok = 0
+            if world()[0] == 0:
+                print("[ais_benchmarks_b200] peer-memory record exchange unavailable (%s: %s); using NCCL all-gather"
+                      % (type(e).__name__, e))
+        flag = torch.tensor([ok], dtype=torch.int32, device=_device.device())
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            cls._instance = inst
+        else:
+            cls._disabled = True
+        return cls._instance
+
+
 def global_weight_record_dev(local_records):
     """Device-resident counterpart of global_weight_partials: this rank's weight record(s) ([4] or [C, 4], float64 CUDA)
-    all-gathered over NCCL -> [ranks * C, 4], still on the device. _device.normalize_weights_dev folds them inside
-    its own kernel, so a weighting step has no host round trip and no separate merge launch."""
+    gathered from all ranks -> [ranks * C, 4], still on the device: a single record goes through the NVLink peer-memory
+    exchange kernel (PeerRecordExchange), anything else through an NCCL all-gather. _device.normalize_weights_dev folds
+    the records inside its own kernel, so a weighting step has no host round trip and no separate merge launch."""
+    _, ws = world()
+    if ws > 1 and local_records.numel() == 4 and local_records.is_cuda:
+        px = PeerRecordExchange.get()
+        if px is not None:
+            return px.exchange(local_records)
     return all_gather_records_dev(local_records.reshape(-1)).reshape(-1, 4)
 
 

@@ -178,6 +178,19 @@ int aisb_normalize_weights_f32(const float* d_logw, int64_t n, const double* h_p
  *       (sampling_methods/base.py:72-75 without leaving HBM).
  */
 int aisb_weight_records_merge(const double* d_records, int64_t n_records, double* d_out_partials, void* stream);
+
+/*
+ * Cross-rank exchange of the weight records over NVLink peer memory, as one tiny kernel instead of a collective launch
+ * (the exchange is 32 bytes per rank: latency is everything). Every rank allocates a SYMMETRIC buffer of
+ * aisb_weight_exchange_doubles(world) doubles, zero-filled once, and passes d_peer_bufs = device array of the `world`
+ * peer-mapped base pointers of those buffers (own buffer at index `rank`). All ranks call with the same `epoch`
+ * (1, 2, 3, ...: one per exchange, in lockstep). d_out_records [world, 4] receives every rank's record (rank-major,
+ * identical on all ranks; feed it to aisb_normalize_weights_dev_f32). A peer that does not show up within ~2 s
+ * poisons its record (n_finite = -1) instead of hanging the GPU.
+ */
+int64_t aisb_weight_exchange_doubles(int32_t world);
+int aisb_weight_records_exchange(const double* d_local_record, void* const* d_peer_bufs, int32_t rank, int32_t world,
+                                 uint64_t epoch, double* d_out_records, void* stream);
 int aisb_kld_records_merge(const double* d_records, int64_t n_records, double* d_out_partials, void* stream);
 int aisb_normalize_weights_dev_f32(const float* d_logw, int64_t n, const double* d_records, int32_t n_records,
                                    float* d_out_w, double* d_out_stats, void* stream);
