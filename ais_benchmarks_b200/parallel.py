@@ -114,6 +114,12 @@ class PeerRecordExchange:
         inst, ok = None, 1
         try:
             inst = cls()
+            # self-test: every rank publishes {rank, rank + 1, ...}; every rank must read all of them back
+            mine = torch.arange(4, dtype=torch.float64, device=_device.device()) + float(inst.rank)
+            got = inst.exchange(mine).cpu()
+            want = torch.arange(4, dtype=torch.float64)[None, :] + torch.arange(ws, dtype=torch.float64)[:, None]
+            if not torch.equal(got, want):
+                raise RuntimeError("self-test mismatch %s" % got.tolist())
         except Exception as e:  # noqa: BLE001 -- any failure means "use NCCL", agreed below
             ok = 0
             if world()[0] == 0:
