@@ -1,4 +1,6 @@
 // Mixture log-density and fused DM-weight kernels + their C-ABI entry points.
+#include <stdlib.h>
+
 #include "pairwise.cuh"
 #include "reduce.cuh"
 
@@ -188,6 +190,10 @@ static bool make_plan(int64_t n, int64_t K, int D, Plan* p) {
   int64_t want = p->ntiles > 0 ? (target + p->ntiles - 1) / p->ntiles : 1;
   if (want > max_split) want = max_split;
   if (want < 1) want = 1;
+  if (const char* e = getenv("AISB_NSPLIT")) {  // timing experiments
+    const int64_t v = atoll(e);
+    if (v >= 1 && v <= max_split) want = v;
+  }
   const int64_t units = p->KP / AISB_COMP_ALIGN;
   const int64_t units_per_split = (units + want - 1) / want;
   p->comps_per_split = units_per_split * AISB_COMP_ALIGN;

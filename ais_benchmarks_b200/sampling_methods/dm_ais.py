@@ -232,7 +232,16 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
         return cap
 
     def _graph_iteration(self, target_d, per):
-        cap = self._captured_iteration(target_d, per)
+        try:
+            cap = self._captured_iteration(target_d, per)
+        except RuntimeError as e:
+            # capture refused (e.g. another thread is using the device): this sampler stays on eager launches
+            import warnings
+            warnings.warn("CUDA-graph capture of the adapt iteration failed (%s); using eager launches" % e)
+            self.cuda_graph = False
+            self._captured = None
+            torch.cuda.synchronize()
+            return False
         cap["graph"].replay()
         # the means changed in place: everything derived from them is stale
         self._mixture = None
@@ -242,6 +251,7 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
         # the graph's outputs are overwritten by the next replay: the accumulated state gets copies
         self._append(cap["x"].clone(), cap["logw"].clone())
         self._n_all_ranks += self.N * int(self.K)
+        return True
 
     def importance_sample(self, target_d, n_samples, timeout=60):
         elapsed_time = 0
@@ -250,8 +260,7 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
         # n_samples is the total wanted over all ranks; every iteration adds N*K of them
         # (sharded: the loop is driven by the sample count alone -- a per-rank clock must not desynchronise the collectives)
         while n_samples > (self._n_all_ranks if self.sharded else self._n()) and (self.sharded or elapsed_time < timeout):
-            if self._graph_wanted(target_d, per):
-                self._graph_iteration(target_d, per)
+            if self._graph_wanted(target_d, per) and self._graph_iteration(target_d, per):
                 elapsed_time = time.time() - t_ini
                 continue
             # K samples from each proposal, proposal-major like dm_ais.py:64-69

@@ -71,9 +71,11 @@ class CLayeredAIS(CDeterministicMixtureAIS):
         self._graph_mh_keep = (delta, u)
 
     def _graph_iteration(self, target_d, per):
-        super(CLayeredAIS, self)._graph_iteration(target_d, per)
+        if not super(CLayeredAIS, self)._graph_iteration(target_d, per):
+            return False
         self._num_pi_evals += 2 * self.L * self.N
         self._num_q_samples += self.L * self.N
+        return True
 
     def resample(self, target_d):
         if self.sharded:
@@ -91,8 +93,7 @@ class CLayeredAIS(CDeterministicMixtureAIS):
         per = self._draws_per_proposal()
         # (sharded: the loop is driven by the sample count alone -- a per-rank clock must not desynchronise the collectives)
         while n_samples > (self._n_all_ranks if self.sharded else self._n()) and (self.sharded or elapsed_time < timeout):
-            if self._graph_wanted(target_d, per):
-                self._graph_iteration(target_d, per)
+            if self._graph_wanted(target_d, per) and self._graph_iteration(target_d, per):
                 elapsed_time = time.time() - t_ini
                 continue
             new_samples = _device.sample_iso(self.proposal_means(), per, float(self.sigma))
