@@ -364,7 +364,7 @@ def run_cuda(args):
                                    "target, bw=0.02; eval points sharded over %d GPU(s)" % (n_c, n_e, world),
                        "l2": "no flush between steps: the pairwise kernel is compute-bound (%.0f flop per byte of "
                              "input); its %.0f MB of packed centres are re-read from L2 by every CTA by design and the "
-                             "%.0f MB of points are read once" % (n_c * 30.0 / 8 / 4, n_c * D * 8 / 1e6, n_e * D * 4 / 1e6),
+                             "%.0f MB of points are read once" % (n_c * 30.0 / 8 / 4, n_c * D * 4 / 1e6, n_e * D * 4 / 1e6),
                        "kld": kld_val, "scale": scale},
             "e2e": {"value": total_pairs / (kde_e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(centres_pin.numel() * 4 + x_pin.numel() * 4), "d2h_bytes_per_step": 64,

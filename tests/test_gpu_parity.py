@@ -1032,6 +1032,65 @@ def test_cuda_graph_adapt_iteration(method):
     assert abs(le - lg) < 2.5, (le, lg)
 
 
+def test_cuda_graph_edge_cases():
+    """Captured iterations at awkward shapes: a single proposal with a single draw, tensor-core-eligible dimensions
+    (the captured iteration stays on the CUDA-core weight kernel), a change of target (re-capture), "auto" mode
+    switching between the graph (small batches) and eager launches (large batches), a foreign target (never captured)."""
+    from ais_benchmarks_b200 import _device
+    from ais_benchmarks_b200.sampling_methods import CDeterministicMixtureAIS
+    rs = np.random.RandomState(8)
+
+    def make_target(D, k):
+        return (rs.uniform(-0.5, 0.5, size=(k, D)), rs.uniform(0.05, 0.08, size=(k, D)), np.full(k, 1.0 / k))
+
+    def check_last_batch(s, tp, means_before, nk, sigma):
+        xb = s._samples_dev[-nk:].double().cpu().numpy()
+        lwb = s._logw_dev[-nk:].double().cpu().numpy()
+        ref = O.gmm_log_prob(xb, *tp) - O.iso_mixture_log_prob(xb, means_before, sigma)
+        fin = np.isfinite(ref) & np.isfinite(lwb)
+        assert fin.any() and np.max(np.abs(lwb[fin] - ref[fin]) / np.maximum(1.0, np.abs(ref[fin]))) < 5e-5
+
+    np.random.seed(2)
+    _device.seed(2)
+    for D, N, K in [(1, 1, 1), (12, 7, 3), (2, 3, 1000)]:
+        tp = make_target(D, 3)
+        tgt = gmm(*tp, support=[np.full(D, -1.0), np.full(D, 1.0)])
+        s = CDeterministicMixtureAIS({"space_min": np.full(D, -1.0), "space_max": np.full(D, 1.0), "dims": D, "K": K,
+                                      "N": N, "J": 1, "sigma": 0.1, "device_outputs": True, "cuda_graph": True})
+        for it in range(3):
+            mb = s.proposal_means().double().cpu().numpy().copy()
+            s.importance_sample(tgt, (it + 1) * N * K)
+            check_last_batch(s, tp, mb, N * K, 0.1)
+        cap = s._captured
+        assert cap is not None
+        tp2 = make_target(D, 2)                       # another target: the iteration is captured again
+        tgt2 = gmm(*tp2, support=[np.full(D, -1.0), np.full(D, 1.0)])
+        mb = s.proposal_means().double().cpu().numpy().copy()
+        s.importance_sample(tgt2, 4 * N * K)
+        assert s._captured is not cap
+        check_last_batch(s, tp2, mb, N * K, 0.1)
+    # "auto": small batches replay a graph, batches above GRAPH_MAX_BATCH launch eagerly
+    D = 2
+    tp = make_target(D, 3)
+    tgt = gmm(*tp, support=[np.full(D, -1.0), np.full(D, 1.0)])
+    small = CDeterministicMixtureAIS({"space_min": np.full(D, -1.0), "space_max": np.full(D, 1.0), "dims": D, "K": 10,
+                                      "N": 5, "J": 1, "sigma": 0.1})
+    small.importance_sample(tgt, 50)
+    assert small._captured is not None
+    big = CDeterministicMixtureAIS({"space_min": np.full(D, -1.0), "space_max": np.full(D, 1.0), "dims": D,
+                                    "K": (1 << 18) // 4 + 1, "N": 4, "J": 1, "sigma": 0.1})
+    big.importance_sample(tgt, 10)
+    assert big._captured is None and big._n() == 4 * ((1 << 18) // 4 + 1)
+
+    class Foreign:
+        def log_prob(self, v):
+            return O.gmm_log_prob(v, *tp)
+    f = CDeterministicMixtureAIS({"space_min": np.full(D, -1.0), "space_max": np.full(D, 1.0), "dims": D, "K": 10,
+                                  "N": 5, "J": 1, "sigma": 0.1, "cuda_graph": True})
+    x, w = f.importance_sample(Foreign(), 100)
+    assert f._captured is None and x.shape == (100, D) and abs(w.sum() - 1.0) < 1e-5
+
+
 def test_sharded_samplers_multi_gpu():
     """DM-AIS / LAIS / M-PMC with `sharded: True` under torchrun (scripts/sharded_samplers_check.py): needs >= 2 GPUs
     on the box, skipped otherwise (the host-side exchange logic is covered on CPU by tests/test_parallel_gloo.py)."""
