@@ -493,12 +493,16 @@ def weight_logsum(p):
     return float(lib.aisb_weight_partials_logsum((C.c_double * 4)(*[float(v) for v in p])))
 
 
-def mpmc_moments(x, proposals, logq, logw, log_norm):
-    """-> float64 CUDA [K, D+1]: column 0 = sum_i w~_i rho_di, columns 1.. = sum_i w~_i rho_di x_i."""
+def mpmc_moments(x, proposals, logq, logw, log_norm, second=False):
+    """-> float64 CUDA [K, D+1]: column 0 = sum_i w~_i rho_di, columns 1.. = sum_i w~_i rho_di x_i. With second=True
+    (D <= 8) the row continues with the lower triangle of sum_i w~_i rho_di x_i x_i^T: [K, 1 + D + D (D+1) / 2]."""
     lib = require_cuda()
-    out = torch.zeros((proposals.K, proposals.D + 1), dtype=torch.float64, device=x.device)
-    check(lib.aisb_mpmc_moments_f32(_ptr(x), x.shape[0], proposals.ref(), _ptr(logq), _ptr(logw), float(log_norm),
-                                    _ptr(out), stream_ptr()), "aisb_mpmc_moments_f32")
+    D = proposals.D
+    width = D + 1 + (D * (D + 1) // 2 if second else 0)
+    out = torch.zeros((proposals.K, width), dtype=torch.float64, device=x.device)
+    fn = lib.aisb_mpmc_moments2_f32 if second else lib.aisb_mpmc_moments_f32
+    check(fn(_ptr(x), x.shape[0], proposals.ref(), _ptr(logq), _ptr(logw), float(log_norm), _ptr(out), stream_ptr()),
+          "aisb_mpmc_moments2_f32" if second else "aisb_mpmc_moments_f32")
     return out
 
 

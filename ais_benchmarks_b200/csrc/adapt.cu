@@ -96,12 +96,16 @@ constexpr int kCsThreads = 128;      // components per CTA
 constexpr int kCsSub = 128;          // points per staged sub-tile (one per thread)
 constexpr int kCsSubTiles = 16;      // sub-tiles per CTA: 2048 points
 
-template <int KIND, int DP>
+// SECOND: also accumulate the weighted second moments sum_i a_{d,i} x_i x_i^T (lower triangle, row-major over the real
+// D: index r (r + 1) / 2 + c behind the D + 1 first-order columns) -- the sufficient statistic of the covariance update
+// of M-PMC as published (Cappe et al. 2008, eq. 14.3), which the reference replaces by the unweighted scatter (quirk Q3).
+template <int KIND, int DP, bool SECOND>
 __global__ void __launch_bounds__(kCsThreads)
     mpmc_moments_cs_kernel(const float* __restrict__ x, int64_t n, int D, int vec_ok, const float* __restrict__ rows,
                            const float* __restrict__ offs, int64_t K, float a_iso, const float* __restrict__ logq,
                            const float* __restrict__ logw, float log2_norm, double* __restrict__ out) {
   constexpr int ROW = row_floats(KIND, DP);
+  constexpr int TRI2 = SECOND ? DP * (DP + 1) / 2 : 1;
   constexpr int XS = DP >= 4 ? DP : 4;                      // padded point row in shared memory (float4 reads)
   __shared__ __align__(16) float sx[kCsSub * XS];
   __shared__ float ssh[kCsSub];
@@ -120,6 +124,9 @@ __global__ void __launch_bounds__(kCsThreads)
   double acc[DP + 1];
 #pragma unroll
   for (int d = 0; d <= DP; ++d) acc[d] = 0.0;
+  double acc2[TRI2];
+#pragma unroll
+  for (int q = 0; q < TRI2; ++q) acc2[q] = 0.0;
 
   const int64_t tile0 = static_cast<int64_t>(blockIdx.x) * (kCsSub * kCsSubTiles);
 #pragma unroll 1
@@ -163,6 +170,9 @@ __global__ void __launch_bounds__(kCsThreads)
     float v[DP + 1];
 #pragma unroll
     for (int d = 0; d <= DP; ++d) v[d] = 0.f;
+    float v2[TRI2];
+#pragma unroll
+    for (int q = 0; q < TRI2; ++q) v2[q] = 0.f;
 #pragma unroll 2
     for (int i = 0; i < cnt; ++i) {
       float xi[XS];
@@ -202,27 +212,70 @@ __global__ void __launch_bounds__(kCsThreads)
       v[0] += a;
 #pragma unroll
       for (int d = 0; d < DP; ++d) v[1 + d] = fmaf(a, xi[d], v[1 + d]);
+      if constexpr (SECOND) {
+        int q = 0;
+#pragma unroll
+        for (int r = 0; r < DP; ++r) {
+          const float ar = a * xi[r];
+#pragma unroll
+          for (int cc = 0; cc <= r; ++cc) {
+            v2[q] = fmaf(ar, xi[cc], v2[q]);
+            ++q;
+          }
+        }
+      }
     }
 #pragma unroll
     for (int d = 0; d <= DP; ++d) acc[d] += static_cast<double>(v[d]);
+    if constexpr (SECOND) {
+#pragma unroll
+      for (int q = 0; q < TRI2; ++q) acc2[q] += static_cast<double>(v2[q]);
+    }
     __syncthreads();  // the stage is overwritten by the next sub-tile
   }
   if (live) {
+    const int W = SECOND ? (D + 1) + D * (D + 1) / 2 : D + 1;
 #pragma unroll
     for (int d = 0; d <= DP; ++d)
-      if (d <= D && acc[d] != 0.0) atomicAdd(&out[k * (D + 1) + d], acc[d]);
+      if (d <= D && acc[d] != 0.0) atomicAdd(&out[k * W + d], acc[d]);
+    if constexpr (SECOND) {
+      int q = 0;
+#pragma unroll
+      for (int r = 0; r < DP; ++r) {
+#pragma unroll
+        for (int cc = 0; cc <= r; ++cc) {
+          if (r < D && acc2[q] != 0.0) atomicAdd(&out[k * W + (D + 1) + r * (r + 1) / 2 + cc], acc2[q]);
+          ++q;
+        }
+      }
+    }
   }
 }
 
-template <int KIND, int DP>
+template <int KIND, int DP, bool SECOND = false>
 static int launch_mpmc_cs_t(const float* x, int64_t n, int D, int vec_ok, const aisb_packed_mixture* mix,
                             const float* logq, const float* logw, float log2_norm, double* out, cudaStream_t st) {
   const int64_t tiles = (n + kCsSub * kCsSubTiles - 1) / (kCsSub * kCsSubTiles);
   const dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>((mix->K + kCsThreads - 1) / kCsThreads));
-  mpmc_moments_cs_kernel<KIND, DP><<<grid, kCsThreads, 0, st>>>(x, n, D, vec_ok, mix->d_rows, mix->d_offsets, mix->K,
-                                                               mix->iso_scale, logq, logw, log2_norm, out);
+  mpmc_moments_cs_kernel<KIND, DP, SECOND><<<grid, kCsThreads, 0, st>>>(
+      x, n, D, vec_ok, mix->d_rows, mix->d_offsets, mix->K, mix->iso_scale, logq, logw, log2_norm, out);
   AISB_LAUNCH_CHECK("mpmc_moments_cs_kernel");
   return AISB_OK;
+}
+
+// second-order variant: D <= 8 (1 + D + D (D + 1) / 2 <= 45 accumulators per thread)
+template <int KIND>
+static int launch_mpmc2_dp(int DP, const float* x, int64_t n, int D, int vec_ok, const aisb_packed_mixture* mix,
+                           const float* logq, const float* logw, float log2_norm, double* out, cudaStream_t st) {
+  switch (DP) {
+    case 1: return launch_mpmc_cs_t<KIND, 1, true>(x, n, D, vec_ok, mix, logq, logw, log2_norm, out, st);
+    case 2: return launch_mpmc_cs_t<KIND, 2, true>(x, n, D, vec_ok, mix, logq, logw, log2_norm, out, st);
+    case 4: return launch_mpmc_cs_t<KIND, 4, true>(x, n, D, vec_ok, mix, logq, logw, log2_norm, out, st);
+    case 8: return launch_mpmc_cs_t<KIND, 8, true>(x, n, D, vec_ok, mix, logq, logw, log2_norm, out, st);
+    default: break;
+  }
+  set_error("mpmc_moments2: second moments are limited to D <= 8 (got %d)", D);
+  return AISB_ERR_UNSUPPORTED;
 }
 
 __host__ __device__ constexpr bool mpmc_cs_ok(int kind, int DP) {
@@ -407,6 +460,35 @@ extern "C" int aisb_mpmc_moments_f32(const float* d_x, int64_t n, const aisb_pac
     default: break;
   }
   set_error("mpmc_moments: unknown cov_kind %d", proposals->cov_kind);
+  return AISB_ERR_INVALID;
+}
+
+extern "C" int aisb_mpmc_moments2_f32(const float* d_x, int64_t n, const aisb_packed_mixture* proposals,
+                                      const float* d_logq, const float* d_logw, double log_norm, double* d_out,
+                                      void* stream) {
+  int rc = check_mix_basic(proposals, "mpmc_moments2");
+  if (rc) return rc;
+  if (!proposals->d_offsets) {
+    set_error("mpmc_moments2: proposals need per-component offsets (log2 alpha_d + normaliser)");
+    return AISB_ERR_INVALID;
+  }
+  if (n < 0 || !d_out || (n > 0 && (!d_x || !d_logq || !d_logw))) {
+    set_error("mpmc_moments2: null pointer or negative n");
+    return AISB_ERR_INVALID;
+  }
+  if (n == 0) return AISB_OK;
+  const int D = proposals->D, DP = aisb_padded_dims(D);
+  int vec_ok = 0;
+  if (D == DP && DP >= 4) vec_ok = reinterpret_cast<uintptr_t>(d_x) % 16 == 0;
+  const float l2n = static_cast<float>(log_norm * kLog2e);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (proposals->cov_kind) {
+    case AISB_COV_ISO_SHARED: return launch_mpmc2_dp<AISB_COV_ISO_SHARED>(DP, d_x, n, D, vec_ok, proposals, d_logq, d_logw, l2n, d_out, st);
+    case AISB_COV_DIAG: return launch_mpmc2_dp<AISB_COV_DIAG>(DP, d_x, n, D, vec_ok, proposals, d_logq, d_logw, l2n, d_out, st);
+    case AISB_COV_FULL: return launch_mpmc2_dp<AISB_COV_FULL>(DP, d_x, n, D, vec_ok, proposals, d_logq, d_logw, l2n, d_out, st);
+    default: break;
+  }
+  set_error("mpmc_moments2: unknown cov_kind %d", proposals->cov_kind);
   return AISB_ERR_INVALID;
 }
 

@@ -9,7 +9,8 @@ The O(N D^2) parameter update runs on the host in float64, as in the reference.
 Reference quirks kept on purpose: Q3 - the covariance update multiplies the UNWEIGHTED scatter
 (X - mu_d)^T (X - mu_d) by sum_i w_i rho_di / alpha_d = 1, and falls back to 10*I when any entry is NaN or > 10
 (m_pmc.py:64-72); Q4 - returned weights are normalised per batch, not globally (m_pmc.py:108,118).
-``paper_covariance=True`` in params switches to the weighted covariance of eq. 14.3 instead (not parity mode).
+``paper_covariance=True`` in params switches to the weighted covariance of eq. 14.3 instead (not parity mode; D <= 8:
+the weighted second moments come from the same component-stationary kernel, C ABI aisb_mpmc_moments2_f32).
 """
 import time
 
@@ -32,6 +33,8 @@ class CMixturePMC(CMixtureISSamplingMethod):
         self.J = params["J"]
         self.sigma = params["sigma"]
         self.paper_covariance = bool(params.get("paper_covariance", False))
+        if self.paper_covariance and params["dims"] > 8:
+            raise NotImplementedError("paper_covariance is limited to dims <= 8 (second-moment kernel)")
         # sharded (under torch.distributed): every rank draws and weighs its share of the K samples of an iteration;
         # the sufficient statistics (weight record, alpha / mu numerators, raw moments) are summed over the ranks and
         # every rank performs the identical float64 parameter update
@@ -125,13 +128,18 @@ class CMixturePMC(CMixtureISSamplingMethod):
     def adapt(self, samples, logw, logq, partials_host):
         """alpha, mu, Sigma update (m_pmc.py:53-78) from device-side sufficient statistics."""
         log_norm = _device.weight_logsum(partials_host)  # log sum_i w_i: weights are batch-normalised (m_pmc.py:108)
-        mom = _device.mpmc_moments(samples, self.proposal_mixture(), logq, logw, log_norm).cpu().numpy()
+        D = self.ndims
+        mom = _device.mpmc_moments(samples, self.proposal_mixture(), logq, logw, log_norm,
+                                   second=self.paper_covariance).cpu().numpy()
         if self.sharded:
             from .. import parallel
             mom = parallel.all_reduce_sum_host(mom)
         alpha = mom[:, 0].copy()                           # eq. 14.1 (Rao-Blackwellised)
         with np.errstate(divide="ignore", invalid="ignore"):
-            mu = mom[:, 1:] / alpha[:, None]               # eq. 14.2
+            mu = mom[:, 1:D + 1] / alpha[:, None]          # eq. 14.2
+        if self.paper_covariance:
+            self._finish_adapt(alpha, mu, self._paper_covariances(mom, alpha, mu))
+            return
         n = samples.shape[0]
         s1_t, s2_t = _device.raw_moments(samples)
         s1, s2 = s1_t.cpu().numpy(), s2_t.cpu().numpy()
@@ -139,8 +147,6 @@ class CMixturePMC(CMixtureISSamplingMethod):
             flat = parallel.all_reduce_sum_host(np.concatenate([s1, s2.reshape(-1), [float(n)]]))
             D = self.ndims
             s1, s2, n = flat[:D], flat[D:D + D * D].reshape(D, D), int(round(flat[-1]))
-        if self.paper_covariance:
-            raise NotImplementedError("paper_covariance needs the weighted second-moment kernel (next round)")
         # quirk Q3: raw scatter about mu_d, (X - mu)^T (X - mu) = S2 - mu s1^T - s1 mu^T + n mu mu^T, for all N
         # proposals at once (the reference loops over proposals and samples, m_pmc.py:62-72)
         with np.errstate(invalid="ignore", over="ignore"):
@@ -148,6 +154,30 @@ class CMixturePMC(CMixtureISSamplingMethod):
                     + n * mu[:, :, None] * mu[:, None, :])
             bad = np.isnan(covs).any(axis=(1, 2)) | (covs > 10).any(axis=(1, 2))
         covs[bad] = np.diag(np.ones(self.ndims) * 10)
+        self._finish_adapt(alpha, mu, covs)
+
+    def _paper_covariances(self, mom, alpha, mu):
+        """Sigma_d = sum_i w~_i rho_di (x_i - mu_d)(x_i - mu_d)^T / alpha_d = S2_d / alpha_d - mu_d mu_d^T (eq. 14.3 of
+        the M-PMC paper), from the device-side weighted second moments; same failsafe as the reference (NaN or an
+        entry > 10 -> 10 I), plus: a component that received no mass keeps its old covariance."""
+        D = self.ndims
+        tri = mom[:, D + 1:]
+        r, c = np.tril_indices(D)
+        s2 = np.zeros((self.N, D, D))
+        s2[:, r, c] = tri
+        s2[:, c, r] = tri
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            covs = s2 / alpha[:, None, None] - mu[:, :, None] * mu[:, None, :]
+        dead = ~(alpha > 0)
+        covs[dead] = self._covs[dead]
+        covs += 1e-9 * np.eye(D)[None]                     # float32 partial sums: keep the factorisation well-posed
+        bad = np.isnan(covs).any(axis=(1, 2)) | (covs > 10).any(axis=(1, 2))
+        bad |= ~(np.linalg.det(np.where(np.isnan(covs), 0.0, covs)) > 0)
+        covs[bad] = np.diag(np.ones(D) * 10)
+        return covs
+
+    def _finish_adapt(self, alpha, mu, covs):
+        mu = np.where(np.isnan(mu), self._means, mu) if self.paper_covariance else mu
         # CMultivariateNormal.set_moments asserts det > 0 (CMultivariateNormal.py:55-56)
         assert np.all(np.linalg.det(covs) > 0)
         self._means, self._covs = mu, covs

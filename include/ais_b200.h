@@ -250,6 +250,12 @@ int aisb_weighted_mean_f32(const float* d_x, int64_t n, int32_t D, const float* 
  */
 int aisb_mpmc_moments_f32(const float* d_x, int64_t n, const aisb_packed_mixture* proposals, const float* d_logq,
                           const float* d_logw, double log_norm, double* d_out, void* stream);
+/* Same plus the weighted second moments sum_i w~_i rho_di x_i x_i^T (lower triangle, row-major: index r (r+1)/2 + c)
+ * behind the D + 1 first-order columns: d_out [K, 1 + D + D (D + 1) / 2], zeroed by the caller, D <= 8. This is the
+ * sufficient statistic of the covariance update of M-PMC as published (eq. 14.3 of the paper the reference cites,
+ * m_pmc.py:62-68 implements the unweighted scatter instead); used by CMixturePMC(paper_covariance=True). */
+int aisb_mpmc_moments2_f32(const float* d_x, int64_t n, const aisb_packed_mixture* proposals, const float* d_logq,
+                           const float* d_logw, double log_norm, double* d_out, void* stream);
 
 /*
  * First and second raw moments of a point set, in float64:  out = { sum_i x_i [D], sum_i x_i x_i^T [D*D] }.

@@ -496,6 +496,73 @@ def test_mpmc_moment_kernels_vs_oracle(kind, D):
     scale = np.abs(ref).max(axis=1, keepdims=True) + 1e-12
     assert np.max(np.abs(got - ref) / scale) < W_TOL
     assert abs(got[:, 0].sum() - 1.0) < 1e-4      # sum_d alpha_d = 1
+    if D <= 8:
+        # weighted second moments (C ABI aisb_mpmc_moments2_f32): lower triangle of sum_i a_di x_i x_i^T
+        got2 = _device.mpmc_moments(xd, mix, torch.from_numpy(logq).cuda().float(),
+                                    torch.from_numpy(logw).cuda().float(), float(log_norm), second=True).cpu().numpy()
+        assert got2.shape == (K, D + 1 + D * (D + 1) // 2)
+        assert np.max(np.abs(got2[:, :D + 1] - ref) / scale) < W_TOL
+        r, c = np.tril_indices(D)
+        ref2 = np.einsum("ki,ir,ic->krc", a_ki, x64, x64)[:, r, c]
+        scale2 = np.abs(ref2).max(axis=1, keepdims=True) + 1e-12
+        assert np.max(np.abs(got2[:, D + 1:] - ref2) / scale2) < W_TOL
+    else:
+        with pytest.raises(_lib.AisbError):
+            _device.mpmc_moments(xd, mix, torch.from_numpy(logq).cuda().float(), torch.from_numpy(logw).cuda().float(),
+                                 float(log_norm), second=True)
+
+
+def test_mpmc_paper_covariance_adapts():
+    """CMixturePMC(paper_covariance=True): the weighted covariance update of the M-PMC paper (eq. 14.3) instead of the
+    reference's unweighted scatter (quirk Q3, which always ends in the 10 I failsafe). One adapt step is checked against
+    a float64 evaluation of the update; over a few iterations the proposal mixture approaches the target."""
+    from ais_benchmarks_b200 import _device
+    from ais_benchmarks_b200.metrics import CKLDivergence
+    from ais_benchmarks_b200.sampling_methods import CMixturePMC
+    from scipy.special import logsumexp
+    rs = np.random.RandomState(12)
+    D, N, K = 2, 6, 20000
+    mu = np.array([[-0.5, -0.4], [0.5, 0.3], [0.0, 0.6]])
+    sig = rs.uniform(0.01, 0.03, size=(3, D))
+    w = np.array([0.3, 0.5, 0.2])
+    sup = [np.full(D, -1.0), np.full(D, 1.0)]
+    target = gmm(mu, sig, w, support=sup)
+    params = {"space_min": sup[0], "space_max": sup[1], "dims": D, "K": K, "N": N, "J": 10, "sigma": 0.05,
+              "paper_covariance": True}
+    np.random.seed(5)
+    _device.seed(5)
+    s = CMixturePMC(params)
+    # one adapt step on a fixed batch vs float64
+    x = s.sample_batch()
+    logw, logq, part = s.weigh(x, target)
+    m0, c0, a0 = s._means.copy(), s._covs.copy(), s._mix_weights.copy()
+    s.adapt(x, logw, logq, part.cpu().numpy())
+    x64 = x.double().cpu().numpy()
+    comp = np.stack([O.mvn_log_prob(x64, m0[k], c0[k]) + np.log(a0[k]) for k in range(N)])
+    lq = logsumexp(comp, axis=0)
+    lw = O.gmm_log_prob(x64, mu, sig, w) - lq
+    wt = np.exp(lw - logsumexp(lw))
+    a = wt[None, :] * np.exp(comp - lq[None, :])
+    alpha = a.sum(1)
+    mean = (a @ x64) / alpha[:, None]
+    cov = np.einsum("ki,kir,kic->krc", a, x64[None] - mean[:, None], x64[None] - mean[:, None]) / alpha[:, None, None]
+    live = alpha > 1e-6
+    assert np.allclose(s.wproposals, alpha / alpha.sum(), rtol=1e-3, atol=1e-7)
+    assert np.allclose(s._means[live], mean[live], rtol=1e-3, atol=1e-4)
+    assert np.allclose(s._covs[live], cov[live], rtol=2e-2, atol=2e-5)
+    # a few more iterations: the proposal mixture closes in on the target, covariances at the target's scale
+    xe = rs.uniform(-1, 1, size=(20000, D))
+    kld = CKLDivergence()
+    np.random.seed(6)
+    s2 = CMixturePMC(params)
+    k0 = kld.compute_from_samples(target, s2, xe)
+    s2.importance_sample(target, 6 * K)
+    k1 = kld.compute_from_samples(target, s2, xe)
+    assert k1 < 0.25 * k0 and k1 < 0.5, (k0, k1)
+    heavy = s2._mix_weights > 0.05
+    assert np.all(np.abs(s2._covs[heavy]) < 0.2)
+    with pytest.raises(NotImplementedError):
+        CMixturePMC(dict(params, dims=9, space_min=np.full(9, -1.0), space_max=np.full(9, 1.0)))
 
 
 def test_lais_chains_golden():
