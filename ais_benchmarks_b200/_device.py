@@ -110,6 +110,45 @@ def workspace_for(n, K, D):
     return workspace(need.value)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Spatial (Morton / Z-order) ordering of large point sets. The pairwise kernels skip the log-sum-exp fold of a group of
+# components when it is negligible for EVERY point of the warp (csrc/pairwise.cuh, lse_update2); that only fires when a
+# warp's points and a group's components are spatially coherent, so a large KDE packs its centres in Morton order and
+# evaluates its points in Morton order (results are scattered back: callers never see the permutation).
+# ---------------------------------------------------------------------------------------------------------------------
+MORTON_MIN_ROWS = 1 << 18     # centres: below this the sort costs more than the skipped folds can save
+MORTON_MIN_PAIRS = 5e10       # points x centres from which the evaluation is worth re-ordering the points (~0.5 ms)
+MORTON_MAX_DIMS = 16
+_morton_luts = {}
+
+
+def _morton_lut(D, bits, dev):
+    key = (D, bits, dev)
+    if key not in _morton_luts:
+        v = np.arange(1 << bits, dtype=np.int64)
+        lut = np.zeros((D, 1 << bits), dtype=np.int64)
+        for d in range(D):
+            for b in range(bits):
+                lut[d] |= ((v >> b) & 1) << (b * D + d)
+        _morton_luts[key] = torch.from_numpy(lut).to(dev)
+    return _morton_luts[key]
+
+
+def morton_order(x):
+    """Permutation (int64 CUDA [n]) that puts the rows of x (float32 CUDA [n, D]) in Z-order over their bounding box:
+    `bits` most significant bits per coordinate, interleaved through a per-dimension lookup table. No host sync."""
+    n, D = x.shape
+    bits = max(1, min(8, 32 // D))
+    lo = x.min(dim=0).values
+    span = (x.max(dim=0).values - lo).clamp_min(1e-30)
+    q = ((x - lo) / span * float(1 << bits)).clamp_(0, (1 << bits) - 1).to(torch.int64)
+    lut = _morton_lut(D, bits, x.device)
+    code = lut[0][q[:, 0]]
+    for d in range(1, D):
+        code = code + lut[d][q[:, d]]
+    return torch.argsort(code)
+
+
 class DeviceMixture:
     """A packed Gaussian mixture resident in HBM (layout: include/ais_b200.h "Packed mixture layout")."""
 
@@ -160,17 +199,25 @@ class DeviceMixture:
         return cls(torch.from_numpy(rows).to(dev), torch.from_numpy(offs).to(dev), K, D, kind, iso, 0.0)
 
     @classmethod
-    def kde(cls, samples, idx, n_c, bw):
+    def kde(cls, samples, idx, n_c, bw, spatial_order=True):
         """KDE of sampling_methods/base.py:162-179 built on device: centres samples[idx], covariance bw*I, weights 1/n_c."""
         lib = require_cuda()
         n, D = samples.shape
         DP = lib.aisb_padded_dims(D)
         KP = lib.aisb_padded_components(n_c)
+        ordered = n_c >= MORTON_MIN_ROWS and D <= MORTON_MAX_DIMS and spatial_order
+        if ordered:
+            # a mixture does not care about the order of its components: pack them along a Z-order curve
+            chosen = samples[:n_c] if idx is None else samples[idx]
+            perm = morton_order(chosen)
+            idx = perm if idx is None else idx[perm]
         rows = torch.empty((KP, DP), dtype=torch.float32, device=samples.device)
         check(lib.aisb_kde_pack_f32(_ptr(samples), n, D, _ptr(idx), int(n_c), float(bw), _ptr(rows), stream_ptr()),
               "aisb_kde_pack_f32")
         uo = -math.log(n_c) - 0.5 * D * (LOG_2PI + math.log(bw))
-        return cls(rows, None, n_c, D, COV_ISO_SHARED, lib.aisb_iso_scale(float(bw)), uo)
+        mix = cls(rows, None, n_c, D, COV_ISO_SHARED, lib.aisb_iso_scale(float(bw)), uo)
+        mix.spatially_ordered = bool(ordered)
+        return mix
 
 
 def mixture_logpdf(x, mix, out=None):
@@ -182,6 +229,15 @@ def mixture_logpdf(x, mix, out=None):
     if n == 0:
         return out
     ws = workspace_for(n, mix.K, mix.D)
+    if getattr(mix, "spatially_ordered", False) and n >= (1 << 16) and float(n) * mix.K >= MORTON_MIN_PAIRS:
+        # components are packed in Z-order: evaluate the points in Z-order too (warp-coherent fold skipping), scatter back
+        perm = morton_order(x)
+        xs = x[perm]
+        tmp = torch.empty(n, dtype=torch.float32, device=x.device)
+        check(lib.aisb_mixture_logpdf_ordered_f32(_ptr(xs), n, mix.ref(), _ptr(tmp), _ptr(ws), ws.numel(),
+                                                  stream_ptr()), "aisb_mixture_logpdf_ordered_f32")
+        out[perm] = tmp
+        return out
     check(lib.aisb_mixture_logpdf_f32(_ptr(x), n, mix.ref(), _ptr(out), _ptr(ws), ws.numel(), stream_ptr()),
           "aisb_mixture_logpdf_f32")
     return out

@@ -16,6 +16,7 @@ struct PassArgs {
   int64_t KP;
   float a_iso;
   float uniform_offset;
+  float skip_margin;  // 28 + log2(KP): groups this far (log2) below a warp's running maxima are not folded (pairwise.cuh)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -24,8 +25,11 @@ struct PassArgs {
 // split (b / ntiles). With nsplit > 1 the (m, S) partials go to the workspace and
 // lse_merge_kernel finishes.
 // ---------------------------------------------------------------------------------------------
-template <int KIND, int DP, bool HAS_C>
-__global__ void __launch_bounds__(kThreads, (KIND != AISB_COV_FULL && DP <= 8) ? AISB_MIN_CTAS_SMALL : 1)
+// SKIP: the warp-uniform fold skip of pairwise.cuh (points and components spatially ordered by the caller); that
+// variant needs ~120 registers at DP <= 8, hence 4 resident CTAs instead of 5.
+template <int KIND, int DP, bool HAS_C, bool SKIP = false>
+__global__ void __launch_bounds__(kThreads,
+                                  (KIND != AISB_COV_FULL && DP <= 8) ? (SKIP ? 4 : AISB_MIN_CTAS_SMALL) : 1)
     logpdf_kernel(const float* __restrict__ x, int64_t n, int D, int vec_ok, PassArgs mix, int nsplit,
                   int64_t comps_per_split, int64_t ntiles, float* __restrict__ out, float* __restrict__ ws_m,
                   float* __restrict__ ws_S) {
@@ -46,7 +50,8 @@ __global__ void __launch_bounds__(kThreads, (KIND != AISB_COV_FULL && DP <= 8) ?
   const int64_t k_begin = split * comps_per_split;
   const int64_t k_end = k_begin + comps_per_split < mix.KP ? k_begin + comps_per_split : mix.KP;
   uint32_t it = 0;
-  mixture_pass<KIND, DP, E, HAS_C>(mix.rows, mix.offs, k_begin, k_end, mix.a_iso, smem, bars, outer, it, xr, m, S);
+  mixture_pass<KIND, DP, E, HAS_C, SKIP>(mix.rows, mix.offs, k_begin, k_end, mix.a_iso, smem, bars, outer, it, xr, m, S,
+                                         mix.skip_margin);
 
   if (nsplit == 1) {
 #pragma unroll
@@ -234,12 +239,12 @@ using LogpdfFn = void (*)(const float*, int64_t, int, int, PassArgs, int, int64_
 using DmFn = void (*)(const float*, int64_t, int, int, PassArgs, const float*, PassArgs, float*, float*, float*,
                       double*);
 
-template <int KIND, int DP, bool HAS_C>
+template <int KIND, int DP, bool HAS_C, bool SKIP = false>
 static int launch_logpdf_t(const float* x, int64_t n, int D, int vec_ok, const PassArgs& mix, const Plan& plan,
                            float* out, const Workspace& ws, cudaStream_t st) {
   constexpr size_t smem = pass_smem_bytes(KIND, DP, HAS_C);
   const int64_t grid = plan.ntiles * plan.nsplit;
-  logpdf_kernel<KIND, DP, HAS_C><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(
+  logpdf_kernel<KIND, DP, HAS_C, SKIP><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(
       x, n, D, vec_ok, mix, plan.nsplit, plan.comps_per_split, plan.ntiles, out, ws.ws_m, ws.ws_S);
   AISB_LAUNCH_CHECK("logpdf_kernel");
   if (plan.nsplit > 1) {
@@ -300,6 +305,7 @@ static PassArgs pass_args(const aisb_packed_mixture* mix) {
   a.KP = aisb_padded_components(mix->K);
   a.a_iso = mix->iso_scale;
   a.uniform_offset = mix->uniform_offset;
+  a.skip_margin = 28.f + log2f(static_cast<float>(a.KP));
   return a;
 }
 
@@ -312,9 +318,20 @@ static int vec_ok_for(const float* x, int D) {
 }
 
 static int run_logpdf(const float* x, int64_t n, const aisb_packed_mixture* mix, float* out, const Plan& plan,
-                      const Workspace& ws, cudaStream_t st) {
+                      const Workspace& ws, cudaStream_t st, bool ordered = false) {
   const PassArgs a = pass_args(mix);
   const int vec_ok = vec_ok_for(x, mix->D);
+  if (ordered && mix->cov_kind == AISB_COV_ISO_SHARED && !mix->d_offsets) {
+    // spatially ordered points against a spatially ordered KDE: the fold-skipping variants
+    switch (plan.DP) {
+      case 1: return launch_logpdf_t<AISB_COV_ISO_SHARED, 1, false, true>(x, n, mix->D, vec_ok, a, plan, out, ws, st);
+      case 2: return launch_logpdf_t<AISB_COV_ISO_SHARED, 2, false, true>(x, n, mix->D, vec_ok, a, plan, out, ws, st);
+      case 4: return launch_logpdf_t<AISB_COV_ISO_SHARED, 4, false, true>(x, n, mix->D, vec_ok, a, plan, out, ws, st);
+      case 8: return launch_logpdf_t<AISB_COV_ISO_SHARED, 8, false, true>(x, n, mix->D, vec_ok, a, plan, out, ws, st);
+      case 16: return launch_logpdf_t<AISB_COV_ISO_SHARED, 16, false, true>(x, n, mix->D, vec_ok, a, plan, out, ws, st);
+      default: break;  // larger D: Z-order says little, the ordinary kernel below
+    }
+  }
   switch (mix->cov_kind) {
     case AISB_COV_ISO_SHARED:
       if (mix->d_offsets) return launch_logpdf_dp<AISB_COV_ISO_SHARED, true>(plan.DP, x, n, mix->D, vec_ok, a, plan, out, ws, st);
@@ -393,8 +410,8 @@ static int carve_checked(void* d_ws, size_t ws_bytes, int64_t n, const Plan& pla
   return AISB_OK;
 }
 
-extern "C" int aisb_mixture_logpdf_f32(const float* d_x, int64_t n, const aisb_packed_mixture* mix, float* d_out_logp,
-                                       void* d_workspace, size_t workspace_bytes, void* stream) {
+static int mixture_logpdf_impl(const float* d_x, int64_t n, const aisb_packed_mixture* mix, float* d_out_logp,
+                               void* d_workspace, size_t workspace_bytes, void* stream, bool ordered) {
   int rc = check_mixture(mix, "mixture_logpdf");
   if (rc) return rc;
   if (n == 0) return AISB_OK;
@@ -412,7 +429,18 @@ extern "C" int aisb_mixture_logpdf_f32(const float* d_x, int64_t n, const aisb_p
     rc = carve_checked(d_workspace, workspace_bytes, n, plan, &ws, "mixture_logpdf");
     if (rc) return rc;
   }
-  return run_logpdf(d_x, n, mix, d_out_logp, plan, ws, static_cast<cudaStream_t>(stream));
+  return run_logpdf(d_x, n, mix, d_out_logp, plan, ws, static_cast<cudaStream_t>(stream), ordered);
+}
+
+extern "C" int aisb_mixture_logpdf_f32(const float* d_x, int64_t n, const aisb_packed_mixture* mix, float* d_out_logp,
+                                       void* d_workspace, size_t workspace_bytes, void* stream) {
+  return mixture_logpdf_impl(d_x, n, mix, d_out_logp, d_workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int aisb_mixture_logpdf_ordered_f32(const float* d_x, int64_t n, const aisb_packed_mixture* mix,
+                                               float* d_out_logp, void* d_workspace, size_t workspace_bytes,
+                                               void* stream) {
+  return mixture_logpdf_impl(d_x, n, mix, d_out_logp, d_workspace, workspace_bytes, stream, true);
 }
 
 extern "C" int aisb_dm_weights_f32(const float* d_x, int64_t n, const aisb_packed_mixture* target,

@@ -255,8 +255,17 @@ __device__ __forceinline__ void eval_group2(const float* __restrict__ srows, con
 
 // fold one evaluated group into the running (m, S) of each point pair. Every FP32 operation here is PACKED
 // (FADD2 / FMUL2): a scalar FADD between FFMA2s leaves half of the FMA datapath idle for its two cycles.
-template <int EP, int JJ>
-__device__ __forceinline__ void lse_update2(const float2 (&t)[JJ][EP], float2 (&m2)[EP], float2 (&S2)[EP]) {
+//
+// Warp-uniform skip. A group whose largest term is 2^-margin below the running maximum of EVERY point of the warp
+// cannot change a float32 sum (margin = 28 + log2 K: at most K such terms, together below 2^-28 of the sum, i.e. 1/16
+// ulp), so its fold -- 2 MUFU, 2 FADD2 per pair, the whole LSE overhead -- is skipped after the FMNMX group maximum
+// (ALU pipe) and one vote. The running maximum is a lower bound of the final one, so the test is conservative. It fires
+// when the points of a warp and the components of a group are spatially coherent: large KDEs are evaluated in Morton
+// order on both sides for exactly this reason (_device.py). On incoherent data the vote and its register pressure cost
+// 2-5 %, so the test is a template flag (SKIP) that only the "ordered" entry point of the library switches on.
+template <int EP, int JJ, bool SKIP = false>
+__device__ __forceinline__ void lse_update2(const float2 (&t)[JJ][EP], float2 (&m2)[EP], float2 (&S2)[EP],
+                                            float margin = INFINITY) {
 #pragma unroll
   for (int pp = 0; pp < EP; ++pp) {
     float g0 = t[0][pp].x, g1 = t[0][pp].y;
@@ -264,6 +273,11 @@ __device__ __forceinline__ void lse_update2(const float2 (&t)[JJ][EP], float2 (&
     for (int jj = 1; jj < JJ; ++jj) {
       g0 = fmaxf(g0, t[jj][pp].x);
       g1 = fmaxf(g1, t[jj][pp].y);
+    }
+    if constexpr (SKIP) {
+      // NaN maxima compare false and therefore take the full path
+      const bool negligible = (g0 <= m2[pp].x - margin) && (g1 <= m2[pp].y - margin);
+      if (__all_sync(0xffffffffu, negligible)) continue;
     }
     const float2 mn = make_float2(fmaxf(m2[pp].x, g0), fmaxf(m2[pp].y, g1));
     const float2 nmn = neg2(mn);
@@ -281,10 +295,11 @@ __device__ __forceinline__ void lse_update2(const float2 (&t)[JJ][EP], float2 (&
 
 // Software-pipelined chunk: on entry tP holds the previously evaluated, not yet folded group (all -inf at the very
 // start: folding it is a no-op); on exit it holds this chunk's last group. cnt / JJ is even (cnt is a multiple of 32).
-template <int KIND, int DP, int EP, int JJ, bool HAS_C>
+template <int KIND, int DP, int EP, int JJ, bool HAS_C, bool SKIP = false>
 __device__ __forceinline__ void accumulate_chunk2(const float* __restrict__ srows, const float* __restrict__ soffs,
                                                   int cnt, float a_iso, const float2 (&x2)[EP][DP],
-                                                  float2 (&tP)[JJ][EP], float2 (&m)[EP], float2 (&S)[EP]) {
+                                                  float2 (&tP)[JJ][EP], float2 (&m)[EP], float2 (&S)[EP],
+                                                  float margin) {
   float2 zero[EP];
 #pragma unroll
   for (int pp = 0; pp < EP; ++pp) zero[pp] = make_float2(0.f, 0.f);
@@ -292,9 +307,9 @@ __device__ __forceinline__ void accumulate_chunk2(const float* __restrict__ srow
   for (int j0 = 0; j0 < cnt; j0 += 2 * JJ) {
     float2 tQ[JJ][EP];
     eval_group2<KIND, DP, EP, JJ, HAS_C>(srows, soffs, j0, a_iso, x2, zero, tQ);
-    lse_update2<EP, JJ>(tP, m, S);
+    lse_update2<EP, JJ, SKIP>(tP, m, S, margin);
     eval_group2<KIND, DP, EP, JJ, HAS_C>(srows, soffs, j0 + JJ, a_iso, x2, zero, tP);
-    lse_update2<EP, JJ>(tQ, m, S);
+    lse_update2<EP, JJ, SKIP>(tQ, m, S, margin);
   }
 }
 
@@ -396,11 +411,11 @@ __device__ __forceinline__ void outer_finish(const OuterAcc& o, float (&m)[E], f
 }
 
 // Fold components [k_begin, k_end) into (m, S) of the E register-resident points (results replace m, S).
-template <int KIND, int DP, int E, bool HAS_C>
+template <int KIND, int DP, int E, bool HAS_C, bool SKIP = false>
 __device__ __forceinline__ void mixture_pass(const float* __restrict__ g_rows, const float* __restrict__ g_offs,
                                              int64_t k_begin, int64_t k_end, float a_iso, float* smem, uint64_t* bars,
                                              OuterAcc& outer, uint32_t& it, const float (&x)[E][DP], float (&m)[E],
-                                             float (&S)[E]) {
+                                             float (&S)[E], float margin = INFINITY) {
   constexpr int JJ = comps_per_step(KIND, DP);
   // the inner float32 sum spans at most kFoldEvery chunks (~1024 components: random-walk error sqrt(1024) 2^-24 = 2e-6)
   constexpr int kFoldEvery = chunk_comps(KIND, DP) >= 256 ? 4 : (chunk_comps(KIND, DP) >= 64 ? 16 : 32);
@@ -450,10 +465,10 @@ __device__ __forceinline__ void mixture_pass(const float* __restrict__ g_rows, c
     }
     stream_components<KIND, DP, HAS_C>(
         g_rows, g_offs, k_begin, k_end, smem, bars, it, [&](const float* srows, const float* soffs, int cnt, int64_t) {
-          accumulate_chunk2<KIND, DP, EP, JJ, HAS_C>(srows, soffs, cnt, a_iso, x2, tP, m2, S2);
+          accumulate_chunk2<KIND, DP, EP, JJ, HAS_C, SKIP>(srows, soffs, cnt, a_iso, x2, tP, m2, S2, margin);
           if ((++nchunk % kFoldEvery) == 0) fold();
         });
-    lse_update2<EP, JJ>(tP, m2, S2);
+    lse_update2<EP, JJ, SKIP>(tP, m2, S2, margin);
     fold();
   }
   outer_finish<E>(outer, m, S);

@@ -376,7 +376,9 @@ def run_cuda(args):
                          # dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch (ncu --set full capture,
                          # profiles/r1_ncu_kde_kernel_fullsize_v5.txt); algorithmic bytes: 68 MB
                          "traffic": 100072192 if (world == 1 and scale == 1.0) else None,
-                         "kernel": "logpdf_kernel<ISO_SHARED, 8, no offsets>", "kernel_ms": pair_kernel_ms,
+                         # kernel_ms brackets kde.log_prob: the Z-order sort of the evaluation points, the pairwise
+                         # kernel (fold-skipping variant, > 99.7 % of the bracket), the split merge and the scatter back
+                         "kernel": "logpdf_kernel<ISO_SHARED, 8, no offsets, ordered>", "kernel_ms": pair_kernel_ms,
                          "flop_per_pair": flop_per_pair,
                          "peak_source": "live FFMA micro-benchmark in this run (aisb_peak_fma_f32); nominal 74.5",
                          "mufu": {"achieved_gops": local_pairs / (pair_kernel_ms * 1e-3) / 1e9,

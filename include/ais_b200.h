@@ -135,6 +135,15 @@ int aisb_workspace_bytes(int64_t n, int64_t K, int32_t D, size_t* bytes);
  */
 int aisb_mixture_logpdf_f32(const float* d_x, int64_t n, const aisb_packed_mixture* mix, float* d_out_logp,
                             void* d_workspace, size_t workspace_bytes, void* stream);
+/*
+ * Same result, for callers that have put BOTH the points and the components of an ISO_SHARED mixture without offsets
+ * (a KDE) in a spatially coherent order (e.g. along a Z-order curve): selects kernel variants that skip the
+ * log-sum-exp bookkeeping of a group of components when it is negligible (2^-(28 + log2 K) of the running maximum) for
+ * every point of a warp. Purely a performance hint: on unordered data the result is the same and the vote costs 2-5 %;
+ * other mixture kinds take the ordinary kernels.
+ */
+int aisb_mixture_logpdf_ordered_f32(const float* d_x, int64_t n, const aisb_packed_mixture* mix, float* d_out_logp,
+                                    void* d_workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Deterministic-mixture importance weights in one pass over the samples:

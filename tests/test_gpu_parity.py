@@ -806,6 +806,48 @@ def test_large_kde_properties_and_row_subset():
     assert rel_err(p.cpu().numpy(), full.cpu().numpy()) < 2e-6, rel_err.last
 
 
+@pytest.mark.parametrize("D", [1, 2, 8, 16])
+def test_spatially_ordered_kde_path(D, monkeypatch):
+    """Large KDEs pack their centres in Z-order and evaluate the points in Z-order (fold-skipping kernel variants behind
+    aisb_mixture_logpdf_ordered_f32, results scattered back). Same values as the ordinary path and as the float64
+    oracle; row order of the output is the caller's; clustered data far from the origin included."""
+    from ais_benchmarks_b200 import _device
+    monkeypatch.setattr(_device, "MORTON_MIN_ROWS", 1 << 16)
+    monkeypatch.setattr(_device, "MORTON_MIN_PAIRS", 1 << 32)
+    rs = np.random.RandomState(40 + D)
+    n = K = _device.MORTON_MIN_ROWS + 777
+    modes = rs.uniform(-3, 5, size=(6, D))
+    c = (modes[rs.randint(0, 6, size=K)] + 0.15 * rs.standard_normal((K, D))).astype(np.float32)
+    x = np.concatenate([(modes[rs.randint(0, 6, size=n // 2)] + 0.3 * rs.standard_normal((n // 2, D))),
+                        rs.uniform(-4, 6, size=(n - n // 2, D))]).astype(np.float32)
+    rs.shuffle(x)
+    cd, xd = torch.from_numpy(c).cuda(), torch.from_numpy(x).cuda()
+    bw = 0.02
+    plain = _device.DeviceMixture.kde(cd, None, K, bw, spatial_order=False)
+    ordered = _device.DeviceMixture.kde(cd, None, K, bw)
+    assert ordered.spatially_ordered and not getattr(plain, "spatially_ordered", False)
+    a = _device.mixture_logpdf(xd, plain).double().cpu().numpy()
+    b = _device.mixture_logpdf(xd, ordered).double().cpu().numpy()
+    fin = np.isfinite(a)
+    assert np.array_equal(np.isfinite(b), fin)
+    assert np.max(np.abs(a[fin] - b[fin]) / np.maximum(1.0, np.abs(a[fin]))) < 5e-6  # summation order differs between the two packings
+    rows = rs.choice(n, size=300, replace=False)
+    ref = O.iso_mixture_log_prob(x[rows].astype(np.float64), c.astype(np.float64), bw)
+    ok = np.isfinite(ref)
+    assert np.max(np.abs(b[rows][ok] - ref[ok]) / np.maximum(1.0, np.abs(ref[ok]))) < LOGP_TOL
+    # fewer points than the threshold: the ordered mixture is evaluated by the ordinary kernel, same values
+    few = _device.mixture_logpdf(xd[:5000], ordered).double().cpu().numpy()
+    assert np.max(np.abs(few[fin[:5000]] - a[:5000][fin[:5000]]) / np.maximum(1.0, np.abs(a[:5000][fin[:5000]]))) < 5e-6  # summation order differs between the two packings
+    # centres chosen by index (with repetitions), as CMixtureSamplingMethod._update_model does
+    idx = torch.from_numpy(rs.randint(0, K, size=K)).cuda()
+    oi = _device.DeviceMixture.kde(cd, idx, K, bw)
+    pi = _device.DeviceMixture.kde(cd, idx, K, bw, spatial_order=False)
+    ai = _device.mixture_logpdf(xd, pi).double().cpu().numpy()
+    bi = _device.mixture_logpdf(xd, oi).double().cpu().numpy()
+    f2 = np.isfinite(ai)
+    assert np.max(np.abs(ai[f2] - bi[f2]) / np.maximum(1.0, np.abs(ai[f2]))) < 5e-6  # summation order differs between the two packings
+
+
 @pytest.mark.parametrize("case", range(3))
 def test_tpais_replay_on_device(case):
     """TP-AIS with the reference's captured draws, target densities from the CUDA kernels: same tree and samples,
