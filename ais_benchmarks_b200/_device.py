@@ -595,9 +595,15 @@ _rng_state = {"seed": 0x5EED_B200, "offset": 0}
 
 
 def seed(s):
-    """Seed the device sampling kernels (Philox). Streams are not comparable with numpy's."""
+    """Seed the device sampling kernels (Philox, host-offset and device-resident streams) and torch's CUDA generator
+    (resampling uniforms). Streams are not comparable with numpy's."""
     _rng_state["seed"] = int(s) & 0xFFFFFFFFFFFFFFFF
     _rng_state["offset"] = 0
+    for dev, st in _rng_states.items():       # device-resident streams restart too (in place: captured graphs keep their pointer)
+        st.copy_(torch.tensor([0, _graph_key()], dtype=torch.int64), non_blocking=False)
+    if torch.cuda.is_available():
+        # resampling / MH acceptance draw their uniforms from torch's CUDA generator: one seed reproduces a whole run
+        torch.cuda.manual_seed(_rng_state["seed"] & 0x7FFFFFFFFFFFFFFF)
 
 
 def _next_offset(n_values):
@@ -617,29 +623,33 @@ def sample_iso(means, per, var):
     return out
 
 
-_GRAPH_STREAM_KEY = 0x9E3779B97F4A7C15  # Philox key offset of the device-counter stream (disjoint from the host-offset stream)
-_rng_counters = {}
+_GRAPH_STREAM_KEY = 0x9E3779B97F4A7C15  # key offset of the device-resident stream (disjoint from the host-offset stream)
+_rng_states = {}
 
 
-def rng_counter():
-    """Device-resident position of the Philox stream used inside captured CUDA graphs (one int64 per device)."""
+def _graph_key():
+    k = (_rng_state["seed"] ^ _GRAPH_STREAM_KEY) & 0xFFFFFFFFFFFFFFFF
+    return k - (1 << 64) if k >= (1 << 63) else k       # as a two's-complement int64
+
+
+def rng_state():
+    """Device-resident Philox state {position, key} used inside captured CUDA graphs (one int64[2] per device). seed()
+    rewrites it IN PLACE, so graphs captured earlier follow a re-seed."""
     dev = torch.cuda.current_device()
-    key = (dev, _rng_state["seed"])
-    if key not in _rng_counters:
-        _rng_counters[key] = torch.zeros(1, dtype=torch.int64, device=device())
-    return _rng_counters[key]
+    if dev not in _rng_states:
+        _rng_states[dev] = torch.tensor([0, _graph_key()], dtype=torch.int64, device=device())
+    return _rng_states[dev]
 
 
 def sample_iso_ctr(means, per, var, out=None):
-    """sample_iso with the stream position in device memory (C ABI aisb_sample_iso_ctr_f32): safe to capture in a CUDA
+    """sample_iso with the Philox state in device memory (C ABI aisb_sample_iso_ctr_f32): safe to capture in a CUDA
     graph -- every replay draws fresh numbers."""
     lib = require_cuda()
     K, D = means.shape
     if out is None:
         out = torch.empty((K * per, D), dtype=torch.float32, device=means.device)
-    check(lib.aisb_sample_iso_ctr_f32(_ptr(means), K, D, int(per), float(var),
-                                      (_rng_state["seed"] ^ _GRAPH_STREAM_KEY) & 0xFFFFFFFFFFFFFFFF, _ptr(rng_counter()),
-                                      _ptr(out), stream_ptr()), "aisb_sample_iso_ctr_f32")
+    check(lib.aisb_sample_iso_ctr_f32(_ptr(means), K, D, int(per), float(var), _ptr(rng_state()), _ptr(out),
+                                      stream_ptr()), "aisb_sample_iso_ctr_f32")
     return out
 
 

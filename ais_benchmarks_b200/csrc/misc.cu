@@ -86,15 +86,19 @@ __device__ __forceinline__ void normal4(uint64_t counter, uint64_t seed, float (
   z[3] = r1 * s1;
 }
 
-// out[(k*per + j)*D + d] = means[k*D + d] + sd * z. The Philox counter of group q is q + offset (+ *d_offset when the
-// stream position lives in device memory: CUDA-graph replays must not re-use the offsets baked in at capture).
+// out[(k*per + j)*D + d] = means[k*D + d] + sd * z. The Philox counter of group q is q + offset. With d_state (two
+// words in device memory: {stream position, key}) both come from there instead: a CUDA-graph replay must neither re-use
+// the offsets nor keep the seed that were baked in at capture.
 __global__ void sample_iso_kernel(const float* __restrict__ means, int64_t K, int D, int64_t per, float sd,
-                                  uint64_t seed, uint64_t offset, const unsigned long long* __restrict__ d_offset,
+                                  uint64_t seed, uint64_t offset, const unsigned long long* __restrict__ d_state,
                                   float* __restrict__ out) {
   const int64_t total = K * per * D;
   const int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;  // group of 4 outputs
   if (q * 4 >= total) return;
-  if (d_offset != nullptr) offset += *d_offset;
+  if (d_state != nullptr) {
+    offset = d_state[0];
+    seed = d_state[1];
+  }
   float z[4];
   normal4(static_cast<uint64_t>(q) + offset, seed, z);
 #pragma unroll
@@ -260,8 +264,9 @@ extern "C" int aisb_sample_iso_f32(const float* d_means, int64_t K, int32_t D, i
 }
 
 extern "C" int aisb_sample_iso_ctr_f32(const float* d_means, int64_t K, int32_t D, int64_t per, double var,
-                                       uint64_t seed, uint64_t* d_counter, float* d_out, void* stream) {
-  if (!d_means || !d_out || !d_counter || K < 1 || per < 0 || D < 1 || D > AISB_MAX_DIMS || !(var >= 0.0)) {
+                                       uint64_t* d_state, float* d_out, void* stream) {
+  uint64_t* d_counter = d_state;
+  if (!d_means || !d_out || !d_state || K < 1 || per < 0 || D < 1 || D > AISB_MAX_DIMS || !(var >= 0.0)) {
     set_error("sample_iso_ctr: invalid argument");
     return AISB_ERR_INVALID;
   }
@@ -270,8 +275,7 @@ extern "C" int aisb_sample_iso_ctr_f32(const float* d_means, int64_t K, int32_t 
   const int64_t groups = (total + 3) / 4;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   sample_iso_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, st>>>(
-      d_means, K, D, per, static_cast<float>(sqrt(var)), seed, 0, reinterpret_cast<unsigned long long*>(d_counter),
-      d_out);
+      d_means, K, D, per, static_cast<float>(sqrt(var)), 0, 0, reinterpret_cast<unsigned long long*>(d_state), d_out);
   AISB_LAUNCH_CHECK("sample_iso_kernel");
   counter_add_kernel<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long*>(d_counter),
                                       static_cast<unsigned long long>(groups + 1));

@@ -213,6 +213,10 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
             means = torch.empty((self.N, self.ndims), dtype=torch.float32, device=dev)
             ws = torch.empty(_device.workspace_bytes_for(self.N * per, max(self.N, target.K), self.ndims) + 256,
                              dtype=torch.uint8, device=dev)
+            # warm-up and capture must not consume random numbers: a sampler that captures now and one that captured
+            # earlier draw the same streams after the same seed
+            saved_philox = _device.rng_state().clone()
+            saved_torch = torch.cuda.get_rng_state(dev)
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):          # warm-up on a scratch copy: loads the kernels, adapts nothing
@@ -223,6 +227,8 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 x, logw, part, mix = self._iteration_ops(means, target, per, ws)
+            _device.rng_state().copy_(saved_philox)
+            torch.cuda.set_rng_state(saved_torch, dev)
             cap = {"key": key, "graph": graph, "means": means, "x": x, "logw": logw, "part": part,
                    "keep": (mix, ws, target)}
             self._captured = cap

@@ -305,11 +305,12 @@ int aisb_box_mixture_logpdf_f32(const float* d_x, int64_t n, int32_t D, const fl
  *      (CMultivariateNormal.py:64-65) once the component indices have been drawn (m_pmc.py:86). */
 int aisb_sample_mixture_f32(const float* d_means, const float* d_chol, int64_t K, int32_t D, const int64_t* d_idx,
                             int64_t n, uint64_t seed, uint64_t offset, float* d_out, void* stream);
-/*  aisb_sample_iso_ctr_f32: aisb_sample_iso_f32 with the position in the Philox stream kept in DEVICE memory
- *      (*d_counter is read by the kernel and advanced by a one-thread kernel behind it), so that a captured CUDA graph
- *      of a sampler iteration draws fresh numbers on every replay. */
-int aisb_sample_iso_ctr_f32(const float* d_means, int64_t K, int32_t D, int64_t per, double var, uint64_t seed,
-                            uint64_t* d_counter, float* d_out, void* stream);
+/*  aisb_sample_iso_ctr_f32: aisb_sample_iso_f32 with the Philox state kept in DEVICE memory: d_state[2] =
+ *      {position in the stream, key}. The kernel reads both; a one-thread kernel behind it advances the position. A
+ *      captured CUDA graph of a sampler iteration therefore draws fresh numbers on every replay and follows a re-seed
+ *      (the owner rewrites d_state) without being captured again. */
+int aisb_sample_iso_ctr_f32(const float* d_means, int64_t K, int32_t D, int64_t per, double var, uint64_t* d_state,
+                            float* d_out, void* stream);
 int aisb_sample_iso_f32(const float* d_means, int64_t K, int32_t D, int64_t per, double var, uint64_t seed,
                         uint64_t offset, float* d_out, void* stream);
 int aisb_uniform_box_f32(const float* d_lo, const float* d_hi, int32_t D, int64_t n, uint64_t seed, uint64_t offset,

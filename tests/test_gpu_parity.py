@@ -1127,6 +1127,21 @@ def test_cuda_graph_adapt_iteration(method):
     assert s._captured is cap
     d = (x.double().cpu().numpy().reshape(N, K, D) - m0[:, None, :]) / np.sqrt(0.02)
     assert abs(d.std() - 1.0) < 0.1
+    # one seed reproduces a run, also through the captured graph (device-resident Philox state, torch generator)
+    runs = []
+    for _ in range(2):
+        np.random.seed(1)
+        _device.seed(11)
+        r = cls(params)
+        xr, wr = r.importance_sample(target, 3 * N * K)
+        runs.append((xr.clone(), wr.clone()))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+    s.reset()
+    np.random.seed(1)
+    _device.seed(11)
+    s.reset()
+    xs_, _ = s.importance_sample(target, 3 * N * K)      # the EARLIER capture follows the re-seed as well
+    assert torch.equal(xs_, runs[0][0])
     # eager path (cuda_graph False): same adaptation quality
     np.random.seed(1)
     e = cls(dict(params, cuda_graph=False))
