@@ -220,8 +220,10 @@ class DeviceMixture:
         return mix
 
 
-def mixture_logpdf(x, mix, out=None):
-    """x: float32 CUDA [n, D]; returns float32 CUDA [n] natural-log densities (C ABI: aisb_mixture_logpdf_f32)."""
+def mixture_logpdf(x, mix, out=None, points_ordered=False):
+    """x: float32 CUDA [n, D]; returns float32 CUDA [n] natural-log densities (C ABI: aisb_mixture_logpdf_f32).
+    points_ordered: the caller has already put the rows of x in Z-order (parallel.spatial_shard): with a spatially
+    ordered mixture the fold-skipping kernels are used directly, without the internal sort / scatter."""
     lib = require_cuda()
     n = x.shape[0]
     if out is None:
@@ -229,6 +231,10 @@ def mixture_logpdf(x, mix, out=None):
     if n == 0:
         return out
     ws = workspace_for(n, mix.K, mix.D)
+    if points_ordered and getattr(mix, "spatially_ordered", False):
+        check(lib.aisb_mixture_logpdf_ordered_f32(_ptr(x), n, mix.ref(), _ptr(out), _ptr(ws), ws.numel(),
+                                                  stream_ptr()), "aisb_mixture_logpdf_ordered_f32")
+        return out
     if getattr(mix, "spatially_ordered", False) and n >= (1 << 16) and float(n) * mix.K >= MORTON_MIN_PAIRS:
         # components are packed in Z-order: evaluate the points in Z-order too (warp-coherent fold skipping), scatter back
         perm = morton_order(x)

@@ -35,6 +35,20 @@ def shard_rows(n, rank=None, world_size=None):
     return start, start + base + (1 if rank < rem else 0)
 
 
+def spatial_shard(x, rank=None, world_size=None):
+    """This rank's share of the point set x (float32 CUDA [n, D], the SAME on every rank) as a contiguous piece of the
+    Z-order curve through all n points: -> (rows [m, D] in Z-order, their indices into x). Sharding along the curve
+    instead of by row number keeps every rank's points as dense in space as the whole set, which is what lets the
+    pairwise kernel skip negligible folds (csrc/pairwise.cuh); any partition gives the same KLD. The permutation is
+    recomputed identically on every rank (no communication)."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    perm = _device.morton_order(x)
+    a, b = shard_rows(x.shape[0], rank, world_size)
+    mine = perm[a:b]
+    return x[mine], mine
+
+
 def _comm_device():
     if dist.get_backend() == "nccl":
         return _device.device()

@@ -838,6 +838,19 @@ def test_spatially_ordered_kde_path(D, monkeypatch):
     # fewer points than the threshold: the ordered mixture is evaluated by the ordinary kernel, same values
     few = _device.mixture_logpdf(xd[:5000], ordered).double().cpu().numpy()
     assert np.max(np.abs(few[fin[:5000]] - a[:5000][fin[:5000]]) / np.maximum(1.0, np.abs(a[:5000][fin[:5000]]))) < 5e-6  # summation order differs between the two packings
+    # spatial sharding (parallel.spatial_shard): the pieces of the Z-order curve partition the points, are evaluated
+    # without the internal sort (points_ordered) and give the ordinary path's values
+    from ais_benchmarks_b200 import parallel
+    seen = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for r in range(3):
+        rows_r, idx_r = parallel.spatial_shard(xd, r, 3)
+        seen[idx_r] += 1
+        assert torch.equal(rows_r, xd[idx_r])
+        vals = _device.mixture_logpdf(rows_r, ordered, points_ordered=True).double().cpu().numpy()
+        av = a[idx_r.cpu().numpy()]
+        fr = np.isfinite(av)
+        assert np.max(np.abs(vals[fr] - av[fr]) / np.maximum(1.0, np.abs(av[fr]))) < 5e-6
+    assert bool((seen == 1).all())
     # centres chosen by index (with repetitions), as CMixtureSamplingMethod._update_model does
     idx = torch.from_numpy(rs.randint(0, K, size=K)).cuda()
     oi = _device.DeviceMixture.kde(cd, idx, K, bw)
