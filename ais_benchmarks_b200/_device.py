@@ -134,11 +134,15 @@ def _morton_lut(D, bits, dev):
     return _morton_luts[key]
 
 
-def morton_order(x):
-    """Permutation (int64 CUDA [n]) that puts the rows of x (float32 CUDA [n, D]) in Z-order over their bounding box:
-    `bits` most significant bits per coordinate, interleaved through a per-dimension lookup table. No host sync."""
+def morton_bits(D):
+    return max(1, min(8, 32 // D))
+
+
+def morton_order_torch(x):
+    """Reference implementation of morton_order with torch element-wise operations only (any device; the test oracle
+    of the key kernel, and the path taken with AISB_MORTON_TORCH=1)."""
     n, D = x.shape
-    bits = max(1, min(8, 32 // D))
+    bits = morton_bits(D)
     lo = x.min(dim=0).values
     span = (x.max(dim=0).values - lo).clamp_min(1e-30)
     q = ((x - lo) / span * float(1 << bits)).clamp_(0, (1 << bits) - 1).to(torch.int64)
@@ -147,6 +151,29 @@ def morton_order(x):
     for d in range(1, D):
         code = code + lut[d][q[:, d]]
     return torch.argsort(code)
+
+
+def morton_keys(x):
+    """Signed 32-bit Z-order keys of the rows of x (float32 CUDA [n, D]) over their bounding box (C ABI
+    aisb_morton_keys_f32): one kernel instead of the element-wise chain of morton_order_torch."""
+    lib = require_cuda()
+    n, D = x.shape
+    x = x.contiguous()
+    lo = x.min(dim=0).values
+    span = (x.max(dim=0).values - lo).contiguous()
+    keys = torch.empty(n, dtype=torch.int32, device=x.device)
+    check(lib.aisb_morton_keys_f32(_ptr(x), n, D, morton_bits(D), _ptr(lo.contiguous()), _ptr(span), _ptr(keys),
+                                   stream_ptr()), "aisb_morton_keys_f32")
+    return keys
+
+
+def morton_order(x):
+    """Permutation (int64 CUDA [n]) that puts the rows of x (float32 CUDA [n, D]) in Z-order over their bounding box:
+    morton_bits(D) most significant bits per coordinate, interleaved; key kernel + one 32-bit sort. No host sync."""
+    import os
+    if os.environ.get("AISB_MORTON_TORCH") == "1" or not x.is_cuda:
+        return morton_order_torch(x)
+    return torch.sort(morton_keys(x)).indices
 
 
 class DeviceMixture:

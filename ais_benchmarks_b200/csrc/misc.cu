@@ -155,6 +155,27 @@ static int launch_sample_mixture(const float* means, const float* chol, int64_t 
   return AISB_OK;
 }
 
+// Z-order (Morton) keys of a point set: `bits` most significant bits of every coordinate's position inside the
+// bounding box [lo, lo + span], interleaved (bit b of coordinate d -> key bit b * D + d; bits * D <= 32). The key is
+// stored with its top bit flipped so that SIGNED 32-bit order equals the unsigned order of the code (a 32-bit radix
+// sort then gives the curve order). One read of the rows; replaces ~25 element-wise launches.
+__global__ void __launch_bounds__(256) morton_keys_kernel(const float* __restrict__ x, int64_t n, int D, int bits,
+                                                          const float* __restrict__ lo, const float* __restrict__ span,
+                                                          int32_t* __restrict__ keys) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float scale = static_cast<float>(1 << bits);
+  const float top = static_cast<float>((1 << bits) - 1);
+  uint32_t code = 0;
+  for (int d = 0; d < D; ++d) {
+    float v = __fmul_rn(__fdiv_rn(__fsub_rn(x[i * D + d], lo[d]), fmaxf(span[d], 1e-30f)), scale);
+    v = fminf(fmaxf(v, 0.f), top);   // NaN -> 0
+    const uint32_t q = static_cast<uint32_t>(static_cast<int>(v));
+    for (int b = 0; b < bits; ++b) code |= ((q >> b) & 1u) << (b * D + d);
+  }
+  keys[i] = static_cast<int32_t>(code ^ 0x80000000u);
+}
+
 __global__ void counter_add_kernel(unsigned long long* ctr, unsigned long long inc) { *ctr += inc; }
 
 __global__ void uniform_box_kernel(const float* __restrict__ lo, const float* __restrict__ hi, int D, int64_t n,
@@ -260,6 +281,21 @@ extern "C" int aisb_sample_iso_f32(const float* d_means, int64_t K, int32_t D, i
   sample_iso_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_means, K, D, per, static_cast<float>(sqrt(var)), seed, offset, nullptr, d_out);
   AISB_LAUNCH_CHECK("sample_iso_kernel");
+  return AISB_OK;
+}
+
+extern "C" int aisb_morton_keys_f32(const float* d_x, int64_t n, int32_t D, int32_t bits, const float* d_lo,
+                                    const float* d_span, int32_t* d_keys, void* stream) {
+  if (n < 0 || D < 1 || D > AISB_MAX_DIMS || bits < 1 || bits * D > 32 || !d_lo || !d_span ||
+      (n > 0 && (!d_x || !d_keys))) {
+    set_error("morton_keys: invalid argument (n=%lld D=%d bits=%d; bits * D must not exceed 32)",
+              static_cast<long long>(n), D, bits);
+    return AISB_ERR_INVALID;
+  }
+  if (n == 0) return AISB_OK;
+  morton_keys_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_x, n, D, bits, d_lo, d_span, d_keys);
+  AISB_LAUNCH_CHECK("morton_keys_kernel");
   return AISB_OK;
 }
 

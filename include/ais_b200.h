@@ -299,6 +299,12 @@ int aisb_box_mixture_logpdf_f32(const float* d_x, int64_t n, int32_t D, const fl
  *      (DM-AIS / LAIS: K samples from each of N proposals, dm_ais.py:64-69).
  *  aisb_uniform_box_f32: out[i, d] ~ U(lo_d, hi_d)  (CDivergence.compute eval points, divergences.py:84-85).
  */
+/*  aisb_morton_keys_f32: Z-order keys of the rows of d_x [n, D] inside the box [d_lo, d_lo + d_span] (device vectors
+ *      [D]): `bits` bits per coordinate interleaved, bits * D <= 32, stored so that a SIGNED 32-bit sort of d_keys [n]
+ *      yields the curve order. Used to put large KDEs and their evaluation points in a spatially coherent order (see
+ *      aisb_mixture_logpdf_ordered_f32); no reference counterpart. */
+int aisb_morton_keys_f32(const float* d_x, int64_t n, int32_t D, int32_t bits, const float* d_lo, const float* d_span,
+                         int32_t* d_keys, void* stream);
 /*  aisb_sample_mixture_f32: ancestral draws from a full-covariance Gaussian mixture, given the component of every draw:
  *      out[i, :] = means[idx[i], :] + chol[idx[i]] z_i,  z_i ~ N(0, I)   (chol: lower-triangular factors, row-major
  *      [K, D, D]). Replaces CMixtureModel.sample (CMixtureModel.py:79-89) over CMultivariateNormal.sample

@@ -806,6 +806,36 @@ def test_large_kde_properties_and_row_subset():
     assert rel_err(p.cpu().numpy(), full.cpu().numpy()) < 2e-6, rel_err.last
 
 
+@pytest.mark.parametrize("D", [1, 2, 3, 8, 16, 32])
+def test_morton_key_kernel(D):
+    """aisb_morton_keys_f32 against the torch element-wise reference: same codes, a valid permutation, codes
+    non-decreasing along it; degenerate columns (zero span) and duplicated rows included."""
+    from ais_benchmarks_b200 import _device
+    rs = np.random.RandomState(D)
+    n = 100003
+    x = rs.uniform(-3, 7, size=(n, D)).astype(np.float32)
+    x[1000:2000] = x[0]                      # duplicates
+    if D > 1:
+        x[:, D - 1] = 2.5                    # a coordinate without extent
+    xd = torch.from_numpy(x).cuda()
+    bits = _device.morton_bits(D)
+    assert bits * D <= 32
+    keys = _device.morton_keys(xd)
+    code = (keys.to(torch.int64) & 0xFFFFFFFF) ^ 0x80000000
+    lo = xd.min(dim=0).values
+    span = (xd.max(dim=0).values - lo).clamp_min(1e-30)
+    q = ((xd - lo) / span * float(1 << bits)).clamp_(0, (1 << bits) - 1).to(torch.int64)
+    lut = _device._morton_lut(D, bits, xd.device)
+    ref = sum(lut[d][q[:, d]] for d in range(D))
+    assert float((code == ref).double().mean()) > 0.9999
+    perm = _device.morton_order(xd)
+    assert torch.equal(torch.sort(perm).values, torch.arange(n, device="cuda"))
+    along = code[perm]
+    assert bool((along[1:] >= along[:-1]).all())
+    perm_t = _device.morton_order_torch(xd)
+    assert bool((ref[perm_t][1:] >= ref[perm_t][:-1]).all())
+
+
 @pytest.mark.parametrize("D", [1, 2, 8, 16])
 def test_spatially_ordered_kde_path(D, monkeypatch):
     """Large KDEs pack their centres in Z-order and evaluate the points in Z-order (fold-skipping kernel variants behind
