@@ -270,3 +270,71 @@ def test_benchmark_methods_and_no_cpu_fallback(tmp_path):
     with pytest.raises(AisbError):  # no CPU fallback: the evaluation loop fails loudly without CUDA
         CBenchmark.evaluate_method(1, b.targets[2], b.methods[3], max_samples=50, sampling_eval_samples=100,
                                    metrics=["KLD"], n_reps=1, batch_size=2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Host-side logic added around the kernels: Z-order permutation, sync-free resampling, spatial sharding
+# (device-agnostic torch code paths, exercised here on CPU tensors)
+# ---------------------------------------------------------------------------------------------------
+def test_morton_order_reference_path_cpu():
+    import torch
+    from ais_benchmarks_b200 import _device
+    rs = np.random.RandomState(0)
+    for D in (1, 2, 3, 8, 16, 33):
+        x = torch.from_numpy(rs.uniform(-2, 5, size=(4000, D)).astype(np.float32))
+        x[100:200] = x[0]
+        perm = _device.morton_order(x)                       # CPU tensors take the torch reference path
+        assert sorted(perm.tolist()) == list(range(4000))
+        assert _device.morton_bits(D) * D <= max(32, D)      # D > 32: one bit per coordinate (keys only used for D <= 16)
+    # locality: consecutive rows along the curve are much closer than consecutive rows in random order
+    x = torch.from_numpy(rs.uniform(0, 1, size=(20000, 2)).astype(np.float32))
+    p = _device.morton_order(x)
+    step_sorted = (x[p][1:] - x[p][:-1]).norm(dim=1).mean()
+    step_random = (x[1:] - x[:-1]).norm(dim=1).mean()
+    assert step_sorted < 0.1 * step_random
+
+
+def test_multinomial_resample_is_sync_free_and_handles_degenerate_weights():
+    import torch
+    from ais_benchmarks_b200.sampling_methods.base import multinomial_resample
+    torch.manual_seed(0)
+    logw = torch.log(torch.tensor([0.1, 0.0, 0.6, 0.3]))
+    logw[1] = float("nan")                                   # invalid weights count as zero
+    idx = multinomial_resample(logw, 40000)
+    freq = torch.bincount(idx, minlength=4).double() / 40000
+    assert freq[1] == 0 and torch.allclose(freq, torch.tensor([0.1, 0.0, 0.6, 0.3], dtype=torch.float64), atol=0.01)
+    # +inf weights are invalid too; a single valid entry takes every draw
+    idx = multinomial_resample(torch.tensor([float("inf"), -3.0, float("-inf")]), 100)
+    assert bool((idx == 1).all())
+    # nothing valid: uniform over all rows (the reference would divide by zero)
+    idx = multinomial_resample(torch.full((5,), float("-inf")), 50000)
+    freq = torch.bincount(idx, minlength=5).double() / 50000
+    assert torch.allclose(freq, torch.full((5,), 0.2, dtype=torch.float64), atol=0.01)
+    assert multinomial_resample(torch.zeros(3), 0).shape == (0,)
+
+
+def test_spatial_shard_partitions_the_point_set_cpu():
+    import torch
+    from ais_benchmarks_b200 import parallel
+    rs = np.random.RandomState(3)
+    x = torch.from_numpy(rs.normal(size=(1001, 3)).astype(np.float32))
+    seen = torch.zeros(1001, dtype=torch.int64)
+    sizes = []
+    for r in range(4):
+        rows, idx = parallel.spatial_shard(x, r, 4)
+        assert torch.equal(rows, x[idx])
+        seen[idx] += 1
+        sizes.append(len(idx))
+    assert bool((seen == 1).all()) and max(sizes) - min(sizes) <= 1
+    # every shard is spatially compact: its bounding box is much smaller than the whole set's
+    whole = (x.max(0).values - x.min(0).values).prod()
+    rows, _ = parallel.spatial_shard(x, 1, 4)
+    assert (rows.max(0).values - rows.min(0).values).prod() < 0.8 * whole
+
+
+def test_peer_exchange_is_off_without_nccl():
+    from ais_benchmarks_b200 import parallel
+    parallel.PeerRecordExchange._instance = None
+    parallel.PeerRecordExchange._disabled = False
+    assert parallel.PeerRecordExchange.get() is None        # single process, no process group: NCCL path / no exchange
+    parallel.PeerRecordExchange._disabled = False
