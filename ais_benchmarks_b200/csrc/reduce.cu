@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) normalize_weights_dev_kernel(const float*
 // [parity][rank] of peer r, fences, and publishes the epoch number in the matching flag; then it waits for the flag
 // of slot [parity][r] in the LOCAL buffer and copies that record out. Two parities make the slots safe to re-use: a
 // peer can only reach epoch e+2 after this rank has published epoch e+1, i.e. after everything it enqueued for epoch e
-// (including the kernels that read out[]) has completed. The wait is bounded; a time-out poisons the record.
+// (including the kernels that read out[]) has completed. The wait is bounded (~17 s); a time-out poisons the record.
 // ---------------------------------------------------------------------------------------------
 __global__ void weight_records_exchange_kernel(const double* __restrict__ local_rec, double* const* __restrict__ peer_bufs,
                                                int rank, int world, unsigned long long epoch,
@@ -154,7 +154,7 @@ __global__ void weight_records_exchange_kernel(const double* __restrict__ local_
   const long long t0 = clock64();
   bool ok = true;
   while (*flag < epoch) {
-    if (clock64() - t0 > (1ll << 32)) {  // ~2 s: a peer never arrived
+    if (clock64() - t0 > (1ll << 35)) {  // ~17 s at 2 GHz: a peer never arrived (generous: ranks may be skewed)
       ok = false;
       break;
     }

@@ -194,7 +194,7 @@ int aisb_weight_records_merge(const double* d_records, int64_t n_records, double
  * aisb_weight_exchange_doubles(world) doubles, zero-filled once, and passes d_peer_bufs = device array of the `world`
  * peer-mapped base pointers of those buffers (own buffer at index `rank`). All ranks call with the same `epoch`
  * (1, 2, 3, ...: one per exchange, in lockstep). d_out_records [world, 4] receives every rank's record (rank-major,
- * identical on all ranks; feed it to aisb_normalize_weights_dev_f32). A peer that does not show up within ~2 s
+ * identical on all ranks; feed it to aisb_normalize_weights_dev_f32). A peer that does not show up within ~17 s
  * poisons its record (n_finite = -1) instead of hanging the GPU.
  */
 int64_t aisb_weight_exchange_doubles(int32_t world);
