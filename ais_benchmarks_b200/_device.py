@@ -247,10 +247,37 @@ class DeviceMixture:
         return mix
 
 
-def mixture_logpdf(x, mix, out=None, points_ordered=False):
+def kde_screen(mix):
+    """The screen vector of a spatially ordered KDE (C ABI aisb_kde_screen_pack_f32), built once per mixture; None when
+    the screen-and-refine kernel does not apply (D not in {2, 4, 8, 16}, or switched off with AISB_KDE_SCREEN=0)."""
+    import os
+    if mix.D not in (2, 4, 8, 16) or mix.kind != COV_ISO_SHARED or mix.offsets is not None:
+        return None
+    if os.environ.get("AISB_KDE_SCREEN", "1") == "0":
+        return None
+    if getattr(mix, "_screen", None) is None:
+        lib = require_cuda()
+        mix._screen = torch.empty(lib.aisb_kde_screen_floats(mix.K), dtype=torch.float32, device=mix.rows.device)
+        check(lib.aisb_kde_screen_pack_f32(mix.ref(), _ptr(mix._screen), stream_ptr()), "aisb_kde_screen_pack_f32")
+    return mix._screen
+
+
+def _logpdf_ordered(lib, x, n, mix, out, ws, stats=None):
+    """Both sides spatially ordered: the screen-and-refine kernel where it applies, else the fold-skipping kernel."""
+    screen = kde_screen(mix) if x.data_ptr() % 16 == 0 else None
+    if screen is not None:
+        check(lib.aisb_mixture_logpdf_screened_f32(_ptr(x), n, mix.ref(), _ptr(screen), _ptr(out), _ptr(ws), ws.numel(),
+                                                   _ptr(stats), stream_ptr()), "aisb_mixture_logpdf_screened_f32")
+    else:
+        check(lib.aisb_mixture_logpdf_ordered_f32(_ptr(x), n, mix.ref(), _ptr(out), _ptr(ws), ws.numel(),
+                                                  stream_ptr()), "aisb_mixture_logpdf_ordered_f32")
+
+
+def mixture_logpdf(x, mix, out=None, points_ordered=False, stats=None):
     """x: float32 CUDA [n, D]; returns float32 CUDA [n] natural-log densities (C ABI: aisb_mixture_logpdf_f32).
     points_ordered: the caller has already put the rows of x in Z-order (parallel.spatial_shard): with a spatially
-    ordered mixture the fold-skipping kernels are used directly, without the internal sort / scatter."""
+    ordered mixture the screen-and-refine / fold-skipping kernels are used directly, without the internal sort / scatter.
+    stats: optional zeroed int64 CUDA [2] that receives the screened kernel's {refined, screened} unit counters."""
     lib = require_cuda()
     n = x.shape[0]
     if out is None:
@@ -259,16 +286,14 @@ def mixture_logpdf(x, mix, out=None, points_ordered=False):
         return out
     ws = workspace_for(n, mix.K, mix.D)
     if points_ordered and getattr(mix, "spatially_ordered", False):
-        check(lib.aisb_mixture_logpdf_ordered_f32(_ptr(x), n, mix.ref(), _ptr(out), _ptr(ws), ws.numel(),
-                                                  stream_ptr()), "aisb_mixture_logpdf_ordered_f32")
+        _logpdf_ordered(lib, x, n, mix, out, ws, stats)
         return out
     if getattr(mix, "spatially_ordered", False) and n >= (1 << 16) and float(n) * mix.K >= MORTON_MIN_PAIRS:
         # components are packed in Z-order: evaluate the points in Z-order too (warp-coherent fold skipping), scatter back
         perm = morton_order(x)
         xs = x[perm]
         tmp = torch.empty(n, dtype=torch.float32, device=x.device)
-        check(lib.aisb_mixture_logpdf_ordered_f32(_ptr(xs), n, mix.ref(), _ptr(tmp), _ptr(ws), ws.numel(),
-                                                  stream_ptr()), "aisb_mixture_logpdf_ordered_f32")
+        _logpdf_ordered(lib, xs, n, mix, tmp, ws, stats)
         out[perm] = tmp
         return out
     check(lib.aisb_mixture_logpdf_f32(_ptr(x), n, mix.ref(), _ptr(out), _ptr(ws), ws.numel(), stream_ptr()),
@@ -380,9 +405,16 @@ def _dm_weights_hinted(lib, x, target, logp_in, proposals, operand, want_logp, w
 
 
 def check_partials(p):
-    """Raise if a tensor-core kernel reported an abort through the partial record (n_valid = -1)."""
-    if p[3] < 0:
-        raise AisbError("tensor-core kernel aborted: barrier protocol time-out")
+    """Raise if a kernel reported an abort through a weight record (n_valid = -1: a tensor-core CTA that timed out on
+    its barrier protocol left log q unwritten; a peer-memory exchange that timed out poisons its record the same way).
+    p: one record [4] or a stack of records [G, 4], host array or tensor (a tensor is read back here: call this where
+    the host reads results anyway, it synchronises the stream)."""
+    if is_tensor(p):
+        p = p.detach().cpu().numpy()
+    p = np.asarray(p, dtype=np.float64).reshape(-1, 4)
+    if (p[:, 3] < 0).any():
+        raise AisbError("weight record poisoned (n_valid < 0): a tensor-core kernel or a peer exchange aborted on a "
+                        "barrier time-out; the log weights of that batch are not valid")
     return p
 
 
@@ -624,19 +656,48 @@ def box_mixture_logpdf(x, lo, hi, logw_over_vol, open_upper):
     return out
 
 
-_rng_state = {"seed": 0x5EED_B200, "offset": 0}
+_rng_state = {"seed": 0x5EED_B200, "offset": 0, "rank": None}
+_RANK_MIX = 0xD1B54A32D192ED03  # odd 64-bit constant: rank r draws from the Philox key  seed ^ (r * _RANK_MIX)
+
+
+def _rank():
+    """Rank of this process under torch.distributed (0 when not initialised)."""
+    import torch.distributed as dist
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def _key():
+    """Philox key of THIS process. Under torch.distributed every rank folds its rank into the user's seed, so that
+    sharded samplers, which draw each rank's share with the same (seed, offset) bookkeeping, never produce identical
+    rows on two ranks (that would count every sample world_size times in the merged weights, ESS and moments). Host
+    draws that must agree across ranks (initial centres, shard counts) come from numpy on rank 0 + a broadcast."""
+    _sync_rank()
+    return (_rng_state["seed"] ^ ((_rng_state["rank"] * _RANK_MIX) & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF
+
+
+def _sync_rank():
+    """(Re-)derive the per-rank streams when the rank becomes known or changes (seed() may run before
+    init_process_group): torch's CUDA generator and the device-resident Philox state follow the rank-folded key."""
+    r = _rank()
+    if _rng_state["rank"] == r:
+        return
+    _rng_state["rank"] = r
+    key = (_rng_state["seed"] ^ ((r * _RANK_MIX) & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF
+    if torch.cuda.is_available():
+        # resampling / MH acceptance draw their uniforms from torch's CUDA generator: one seed reproduces a whole run
+        torch.cuda.manual_seed(key & 0x7FFFFFFFFFFFFFFF)
+        for dev, st in _rng_states.items():   # in place: captured graphs keep their pointer
+            st.copy_(torch.tensor([0, _graph_key(key)], dtype=torch.int64), non_blocking=False)
 
 
 def seed(s):
     """Seed the device sampling kernels (Philox, host-offset and device-resident streams) and torch's CUDA generator
-    (resampling uniforms). Streams are not comparable with numpy's."""
+    (resampling uniforms). Streams are not comparable with numpy's. Under torch.distributed the rank is folded into
+    every stream (see _key): one seed still reproduces a whole multi-rank run."""
     _rng_state["seed"] = int(s) & 0xFFFFFFFFFFFFFFFF
     _rng_state["offset"] = 0
-    for dev, st in _rng_states.items():       # device-resident streams restart too (in place: captured graphs keep their pointer)
-        st.copy_(torch.tensor([0, _graph_key()], dtype=torch.int64), non_blocking=False)
-    if torch.cuda.is_available():
-        # resampling / MH acceptance draw their uniforms from torch's CUDA generator: one seed reproduces a whole run
-        torch.cuda.manual_seed(_rng_state["seed"] & 0x7FFFFFFFFFFFFFFF)
+    _rng_state["rank"] = None                 # force _sync_rank to re-derive torch's generator and the device streams
+    _sync_rank()
 
 
 def _next_offset(n_values):
@@ -651,7 +712,7 @@ def sample_iso(means, per, var):
     K, D = means.shape
     out = torch.empty((K * per, D), dtype=torch.float32, device=means.device)
     off = _next_offset(K * per * D)
-    check(lib.aisb_sample_iso_f32(_ptr(means), K, D, int(per), float(var), _rng_state["seed"], off, _ptr(out),
+    check(lib.aisb_sample_iso_f32(_ptr(means), K, D, int(per), float(var), _key(), off, _ptr(out),
                                   stream_ptr()), "aisb_sample_iso_f32")
     return out
 
@@ -660,8 +721,8 @@ _GRAPH_STREAM_KEY = 0x9E3779B97F4A7C15  # key offset of the device-resident stre
 _rng_states = {}
 
 
-def _graph_key():
-    k = (_rng_state["seed"] ^ _GRAPH_STREAM_KEY) & 0xFFFFFFFFFFFFFFFF
+def _graph_key(key=None):
+    k = ((_key() if key is None else key) ^ _GRAPH_STREAM_KEY) & 0xFFFFFFFFFFFFFFFF
     return k - (1 << 64) if k >= (1 << 63) else k       # as a two's-complement int64
 
 
@@ -669,6 +730,7 @@ def rng_state():
     """Device-resident Philox state {position, key} used inside captured CUDA graphs (one int64[2] per device). seed()
     rewrites it IN PLACE, so graphs captured earlier follow a re-seed."""
     dev = torch.cuda.current_device()
+    _sync_rank()
     if dev not in _rng_states:
         _rng_states[dev] = torch.tensor([0, _graph_key()], dtype=torch.int64, device=device())
     return _rng_states[dev]
@@ -693,8 +755,11 @@ def sample_mixture(means, chol, idx):
     K, D = means.shape
     n = idx.shape[0]
     out = torch.empty((n, D), dtype=torch.float32, device=means.device)
-    off = _next_offset(n * ((D + 3) // 4) * 4)
-    check(lib.aisb_sample_mixture_f32(_ptr(means), _ptr(chol), K, D, _ptr(idx), n, _rng_state["seed"], off, _ptr(out),
+    # the kernel consumes ceil(DP / 4) Philox counters per draw, DP = D padded to a power of two (csrc/misc.cu,
+    # sample_mixture_kernel): advance the stream by exactly that, or consecutive calls would share normal deviates
+    counters_per_draw = (int(lib.aisb_padded_dims(D)) + 3) // 4
+    off = _next_offset(n * counters_per_draw * 4)
+    check(lib.aisb_sample_mixture_f32(_ptr(means), _ptr(chol), K, D, _ptr(idx), n, _key(), off, _ptr(out),
                                       stream_ptr()), "aisb_sample_mixture_f32")
     return out
 
@@ -705,6 +770,6 @@ def uniform_box(lo, hi, n):
     D = lo.shape[0]
     out = torch.empty((n, D), dtype=torch.float32, device=lo.device)
     off = _next_offset(n * D)
-    check(lib.aisb_uniform_box_f32(_ptr(lo), _ptr(hi), D, int(n), _rng_state["seed"], off, _ptr(out), stream_ptr()),
+    check(lib.aisb_uniform_box_f32(_ptr(lo), _ptr(hi), D, int(n), _key(), off, _ptr(out), stream_ptr()),
           "aisb_uniform_box_f32")
     return out

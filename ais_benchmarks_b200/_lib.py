@@ -44,6 +44,9 @@ PROTOTYPES = {
     "aisb_workspace_bytes": (C.c_int, [_i64, _i64, _i32, C.POINTER(_sz)]),
     "aisb_mixture_logpdf_f32": (C.c_int, [_vp, _i64, _pm, _vp, _vp, _sz, _vp]),
     "aisb_mixture_logpdf_ordered_f32": (C.c_int, [_vp, _i64, _pm, _vp, _vp, _sz, _vp]),
+    "aisb_kde_screen_floats": (_i64, [_i64]),
+    "aisb_kde_screen_pack_f32": (C.c_int, [_pm, _vp, _vp]),
+    "aisb_mixture_logpdf_screened_f32": (C.c_int, [_vp, _i64, _pm, _vp, _vp, _vp, _sz, _vp, _vp]),
     "aisb_dm_weights_f32": (C.c_int, [_vp, _i64, _pm, _vp, _pm, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "aisb_logw_partials_f32": (C.c_int, [_vp, _i64, _vp, _vp, _sz, _vp]),
     "aisb_normalize_weights_f32": (C.c_int, [_vp, _i64, C.POINTER(_dbl), _vp, _vp]),

@@ -67,6 +67,73 @@ __global__ void __launch_bounds__(kThreads,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Screen-and-refine variant for a spatially ordered KDE (pairwise.cuh, mixture_pass_screen): grid.x = ntiles * nsplit,
+// CTA b sweeps every nsplit-th chunk of the components, starting at chunk b / ntiles (interleaved split), for point tile
+// b % ntiles; warps own 32*E consecutive points. COUNT adds the (refined, screened) unit counters to stats[0..1].
+// ---------------------------------------------------------------------------------------------
+template <int DP, bool COUNT>
+__global__ void __launch_bounds__(kThreads, DP <= 8 ? 4 : 1)
+    logpdf_screen_kernel(const float* __restrict__ x, int64_t n, PassArgs mix, const float* __restrict__ hs, float marg,
+                         int nsplit, int64_t ntiles, float* __restrict__ out, float* __restrict__ ws_m,
+                         float* __restrict__ ws_S, unsigned long long* __restrict__ stats) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bars[kStages];
+  __shared__ OuterAcc outer;
+  constexpr int E = points_per_thread(DP);
+  constexpr int J = chunk_comps(AISB_COV_ISO_SHARED, DP);
+
+  const int64_t tile = blockIdx.x % ntiles;
+  const int64_t split = blockIdx.x / ntiles;
+  ring_init(bars);
+
+  float xr[E][DP];
+  int64_t pidx[E];
+  load_points_warp<DP, E>(x, n, tile * (kThreads * E), xr, pidx);
+
+  float m[E], S[E];
+  uint32_t it = 0;
+  unsigned nscr = 0, nref = 0;
+  mixture_pass_screen<DP, E, COUNT>(mix.rows, hs, mix.KP, split * J, nsplit, mix.a_iso, marg, smem, bars, outer, it, xr,
+                                    m, S, &nscr, &nref);
+  if constexpr (COUNT) {
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(stats + 0, static_cast<unsigned long long>(nref));
+      atomicAdd(stats + 1, static_cast<unsigned long long>(nscr));
+    }
+  }
+  if (nsplit == 1) {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (pidx[e] < n) out[pidx[e]] = lse_finish(m[e], S[e]) + mix.uniform_offset;
+  } else {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (pidx[e] < n) {
+        ws_m[split * n + pidx[e]] = m[e];
+        ws_S[split * n + pidx[e]] = S[e];
+      }
+  }
+}
+
+// h_j = ||b_j||^2 / (2 a) per packed component (padding rows included) and, behind the vector, max_{j < K} ||b_j||^2
+__global__ void kde_screen_pack_kernel(const float* __restrict__ rows, int64_t K, int64_t KP, int DP, float inv2a,
+                                       float* __restrict__ hs) {
+  const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  float b2 = 0.f;
+  if (j < KP) {
+    for (int d = 0; d < DP; ++d) {
+      const float v = rows[j * DP + d];
+      b2 = fmaf(v, v, b2);
+    }
+    hs[j] = b2 * inv2a;
+  }
+  float mx = (j < K) ? b2 : 0.f;
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(hs + KP), __float_as_int(mx));  // non-negative floats
+}
+
 __global__ void lse_merge_kernel(const float* __restrict__ ws_m, const float* __restrict__ ws_S, int nsplit, int64_t n,
                                  float add, float* __restrict__ out) {
   const int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -250,6 +317,28 @@ static int launch_logpdf_t(const float* x, int64_t n, int D, int vec_ok, const P
   if (plan.nsplit > 1) {
     lse_merge_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ws.ws_m, ws.ws_S, plan.nsplit, n,
                                                                              HAS_C ? 0.f : mix.uniform_offset, out);
+    AISB_LAUNCH_CHECK("lse_merge_kernel");
+  }
+  return AISB_OK;
+}
+
+
+template <int DP>
+static int launch_screen_t(const float* x, int64_t n, const PassArgs& mix, const float* hs, const Plan& plan, float* out,
+                           const Workspace& ws, unsigned long long* stats, cudaStream_t st) {
+  constexpr size_t smem = pass_smem_bytes(AISB_COV_ISO_SHARED, DP, true);
+  const int64_t grid = plan.ntiles * plan.nsplit;
+  const float marg = 21.f + log2f(static_cast<float>(mix.KP));
+  if (stats)
+    logpdf_screen_kernel<DP, true><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(
+        x, n, mix, hs, marg, plan.nsplit, plan.ntiles, out, ws.ws_m, ws.ws_S, stats);
+  else
+    logpdf_screen_kernel<DP, false><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(
+        x, n, mix, hs, marg, plan.nsplit, plan.ntiles, out, ws.ws_m, ws.ws_S, nullptr);
+  AISB_LAUNCH_CHECK("logpdf_screen_kernel");
+  if (plan.nsplit > 1) {
+    lse_merge_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ws.ws_m, ws.ws_S, plan.nsplit, n,
+                                                                             mix.uniform_offset, out);
     AISB_LAUNCH_CHECK("lse_merge_kernel");
   }
   return AISB_OK;
@@ -441,6 +530,69 @@ extern "C" int aisb_mixture_logpdf_ordered_f32(const float* d_x, int64_t n, cons
                                                float* d_out_logp, void* d_workspace, size_t workspace_bytes,
                                                void* stream) {
   return mixture_logpdf_impl(d_x, n, mix, d_out_logp, d_workspace, workspace_bytes, stream, true);
+}
+
+
+extern "C" int64_t aisb_kde_screen_floats(int64_t K) { return K < 1 ? 0 : aisb_padded_components(K) + 8; }
+
+extern "C" int aisb_kde_screen_pack_f32(const aisb_packed_mixture* mix, float* d_screen, void* stream) {
+  int rc = check_mixture(mix, "kde_screen_pack");
+  if (rc) return rc;
+  if (mix->cov_kind != AISB_COV_ISO_SHARED || mix->d_offsets || !d_screen ||
+      reinterpret_cast<uintptr_t>(d_screen) % 16) {
+    set_error("kde_screen_pack: needs an ISO_SHARED mixture without offsets and a 16-byte aligned output");
+    return AISB_ERR_INVALID;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int DP = aisb_padded_dims(mix->D);
+  const int64_t KP = aisb_padded_components(mix->K);
+  AISB_CUDA_CHECK(cudaMemsetAsync(d_screen + KP, 0, 8 * sizeof(float), st));
+  kde_screen_pack_kernel<<<static_cast<unsigned>((KP + 255) / 256), 256, 0, st>>>(mix->d_rows, mix->K, KP, DP,
+                                                                                0.5f / mix->iso_scale, d_screen);
+  AISB_LAUNCH_CHECK("kde_screen_pack_kernel");
+  return AISB_OK;
+}
+
+extern "C" int aisb_mixture_logpdf_screened_f32(const float* d_x, int64_t n, const aisb_packed_mixture* mix,
+                                                const float* d_screen, float* d_out_logp, void* d_workspace,
+                                                size_t workspace_bytes, unsigned long long* d_stats, void* stream) {
+  int rc = check_mixture(mix, "mixture_logpdf_screened");
+  if (rc) return rc;
+  if (n == 0) return AISB_OK;
+  if (!d_x || !d_out_logp || n < 0 || !d_screen || reinterpret_cast<uintptr_t>(d_screen) % 16) {
+    set_error("mixture_logpdf_screened: null / misaligned pointer or negative n");
+    return AISB_ERR_INVALID;
+  }
+  const int DP = aisb_padded_dims(mix->D);
+  if (mix->cov_kind != AISB_COV_ISO_SHARED || mix->d_offsets || mix->D != DP || DP < 2 || DP > 16 ||
+      !vec_ok_for(d_x, mix->D)) {
+    set_error("mixture_logpdf_screened: needs an ISO_SHARED mixture without offsets, D in {2, 4, 8, 16} and 16-byte "
+              "aligned points (got cov_kind=%d D=%d)", mix->cov_kind, mix->D);
+    return AISB_ERR_UNSUPPORTED;
+  }
+  Plan plan;
+  if (!make_plan(n, mix->K, mix->D, &plan)) {
+    set_error("mixture_logpdf_screened: unsupported D=%d", mix->D);
+    return AISB_ERR_UNSUPPORTED;
+  }
+  // interleaved split: every CTA must get at least one chunk
+  const int64_t nchunks = (plan.KP + chunk_comps(AISB_COV_ISO_SHARED, DP) - 1) / chunk_comps(AISB_COV_ISO_SHARED, DP);
+  if (plan.nsplit > nchunks) plan.nsplit = static_cast<int>(nchunks);
+  Workspace ws{};
+  if (plan.nsplit > 1) {
+    rc = carve_checked(d_workspace, workspace_bytes, n, plan, &ws, "mixture_logpdf_screened");
+    if (rc) return rc;
+  }
+  const PassArgs a = pass_args(mix);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (DP) {
+    case 2: return launch_screen_t<2>(d_x, n, a, d_screen, plan, d_out_logp, ws, d_stats, st);
+    case 4: return launch_screen_t<4>(d_x, n, a, d_screen, plan, d_out_logp, ws, d_stats, st);
+    case 8: return launch_screen_t<8>(d_x, n, a, d_screen, plan, d_out_logp, ws, d_stats, st);
+    case 16: return launch_screen_t<16>(d_x, n, a, d_screen, plan, d_out_logp, ws, d_stats, st);
+    default: break;
+  }
+  return AISB_ERR_UNSUPPORTED;
 }
 
 extern "C" int aisb_dm_weights_f32(const float* d_x, int64_t n, const aisb_packed_mixture* target,

@@ -319,18 +319,22 @@ __device__ __forceinline__ void accumulate_chunk2(const float* __restrict__ srow
 // `it` counts chunks consumed so far by this CTA (carries the mbarrier phase across passes).
 // k_begin/k_end are multiples of AISB_COMP_ALIGN. All threads of the CTA must call this.
 // ---------------------------------------------------------------------------------------------
+// `stride` > 1 visits every stride-th chunk only (chunk c of this CTA starts at k_begin + c * stride * J): an
+// INTERLEAVED split of the component range over CTAs, so that each of them sees a uniform sample of a spatially ordered
+// mixture (its running maximum then approaches the global one as fast as an unsplit sweep's would).
 template <int KIND, int DP, bool HAS_C, typename Fn>
 __device__ __forceinline__ void stream_components(const float* __restrict__ g_rows, const float* __restrict__ g_offs,
                                                   int64_t k_begin, int64_t k_end, float* smem, uint64_t* bars,
-                                                  uint32_t& it, Fn&& fn) {
+                                                  uint32_t& it, Fn&& fn, int stride = 1) {
   constexpr int ROW = row_floats(KIND, DP);
   constexpr int J = chunk_comps(KIND, DP);
   constexpr int STAGE = stage_floats(KIND, DP, HAS_C);
-  const int nchunks = static_cast<int>((k_end - k_begin + J - 1) / J);
+  const int64_t step = static_cast<int64_t>(J) * stride;
+  const int nchunks = k_end > k_begin ? static_cast<int>((k_end - k_begin + step - 1) / step) : 0;
   const uint32_t it0 = it;
 
   auto issue = [&](int c) {
-    const int64_t k0 = k_begin + static_cast<int64_t>(c) * J;
+    const int64_t k0 = k_begin + static_cast<int64_t>(c) * step;
     const int64_t rem = k_end - k0;
     const int cnt = rem < J ? static_cast<int>(rem) : J;
     const uint32_t stage = (it0 + c) % kStages;
@@ -352,7 +356,7 @@ __device__ __forceinline__ void stream_components(const float* __restrict__ g_ro
     const uint32_t stage = (it0 + c) % kStages;
     const uint32_t parity = ((it0 + c) / kStages) & 1u;
     mbar_wait(&bars[stage], parity);
-    const int64_t k0 = k_begin + static_cast<int64_t>(c) * J;
+    const int64_t k0 = k_begin + static_cast<int64_t>(c) * step;
     const int64_t rem = k_end - k0;
     const int cnt = rem < J ? static_cast<int>(rem) : J;
     const float* s = smem + stage * STAGE;
@@ -474,6 +478,158 @@ __device__ __forceinline__ void mixture_pass(const float* __restrict__ g_rows, c
   outer_finish<E>(outer, m, S);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Screen-and-refine pass for a spatially ordered ISO_SHARED mixture without offsets (a large KDE evaluated in Z-order).
+//
+// The exact exponent of a pair, t = -||a x + b_j||^2, costs 2 DP FMA-lane-cycles (centred form: float32-safe). Its
+// expanded form  ||a x + b_j||^2 = ||a x||^2 + 2 a (h_j + x . b_j),  h_j = ||b_j||^2 / (2 a),  costs DP: one FFMA2 chain
+// seeded with h_j. The expanded value is NOT accurate enough to be summed (cancellation), but it is far more than
+// accurate enough to decide that a pair cannot matter: a component whose exponent lies `marg` = 21 + log2 KP below the
+// running maximum of a point contributes, together with all others like it, less than 2^-21 of the sum. So every pair
+// is SCREENED with the cheap chain; a group of JJ components is evaluated exactly (and folded into the online
+// log-sum-exp) only if it is not negligible for at least one of the 64 points a warp holds in one packed register set.
+// The test per point is  s_ij = h_j + x_i . b_j >= thr_i,  thr_i = (marg + E_i - m_i - ||a x_i||^2) / (2 a), where m_i is
+// the running maximum (a lower bound of the final one: conservative) and E_i = 2^-19 (||a x_i||^2 + max_j ||b_j||^2)
+// bounds the rounding error of the float32 chain in exponent units -- data far from the origin costs time (the screen
+// stops discriminating), never accuracy.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 min2(float2 a, float2 b) { return make_float2(fminf(a.x, b.x), fminf(a.y, b.y)); }
+
+template <int DP, int EP, int JJ, bool COUNT>
+__device__ __forceinline__ void accumulate_chunk_screen(const float* __restrict__ srows, const float* __restrict__ shs,
+                                                        int cnt, float a_iso, float ninv2a,
+                                                        const float2 (&x2)[EP][DP], const float2 (&cthr)[EP],
+                                                        float2 (&thr)[EP], float2 (&m2)[EP], float2 (&S2)[EP],
+                                                        unsigned (&nrefined)) {
+#pragma unroll 1
+  for (int j0 = 0; j0 < cnt; j0 += JJ) {
+    float h[JJ];
+    lds_vec<JJ>(shs + j0, h);
+    float2 smin[EP];
+#pragma unroll
+    for (int pp = 0; pp < EP; ++pp) smin[pp] = make_float2(INFINITY, INFINITY);
+#pragma unroll
+    for (int jj = 0; jj < JJ; ++jj) {
+      float b[DP];
+      lds_vec<DP>(srows + (j0 + jj) * DP, b);
+#pragma unroll
+      for (int pp = 0; pp < EP; ++pp) {
+        float2 acc = bc2(h[jj]);
+#pragma unroll
+        for (int d = 0; d < DP; ++d) acc = __ffma2_rn(x2[pp][d], bc2(b[d]), acc);
+        smin[pp] = min2(smin[pp], acc);
+      }
+    }
+#pragma unroll
+    for (int pp = 0; pp < EP; ++pp) {
+      // NaN compares false: a NaN screen value takes the exact path
+      const bool negligible = (smin[pp].x >= thr[pp].x) && (smin[pp].y >= thr[pp].y);
+      if (__all_sync(0xffffffffu, negligible)) continue;
+      if constexpr (COUNT) ++nrefined;
+      // re-read the rows from shared memory here: keeping the group's JJ*DP parameters live across the branch (what
+      // the compiler does on its own) costs more registers than the kernel can afford at 4 CTAs per SM
+      asm volatile("" ::: "memory");
+      float2 t[JJ];
+#pragma unroll
+      for (int jj = 0; jj < JJ; ++jj) {
+        float b[DP];
+        lds_vec<DP>(srows + (j0 + jj) * DP, b);
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+          const float2 dl = __ffma2_rn(x2[pp][d], bc2(a_iso), bc2(b[d]));
+          acc = __ffma2_rn(neg2(dl), dl, acc);
+        }
+        t[jj] = acc;
+      }
+      float g0 = t[0].x, g1 = t[0].y;
+#pragma unroll
+      for (int jj = 1; jj < JJ; ++jj) {
+        g0 = fmaxf(g0, t[jj].x);
+        g1 = fmaxf(g1, t[jj].y);
+      }
+      const float2 mn = make_float2(fmaxf(m2[pp].x, g0), fmaxf(m2[pp].y, g1));
+      const float2 nmn = neg2(mn);
+      const float2 dm = __fadd2_rn(m2[pp], nmn);
+      float2 acc = __fmul2_rn(S2[pp], make_float2(ex2(dm.x), ex2(dm.y)));
+#pragma unroll
+      for (int jj = 0; jj < JJ; ++jj) {
+        const float2 a = __fadd2_rn(t[jj], nmn);
+        acc = __fadd2_rn(acc, make_float2(ex2(a.x), ex2(a.y)));
+      }
+      S2[pp] = acc;
+      m2[pp] = mn;
+      thr[pp] = make_float2(fmaf(mn.x, ninv2a, cthr[pp].x), fmaf(mn.y, ninv2a, cthr[pp].y));
+    }
+  }
+}
+
+// Fold the components {k_begin + c * stride * J .. } (every stride-th chunk from k_begin on, below k_end) into (m, S).
+// g_hs: the screen vector h_j [KP] followed by its trailer (trailer[0] = max_j ||b_j||^2), see aisb_kde_screen_pack_f32.
+// COUNT: nscreened / nrefined count this thread's (point-pair, group) units (identical for all lanes of a warp).
+template <int DP, int E, bool COUNT = false>
+__device__ __forceinline__ void mixture_pass_screen(const float* __restrict__ g_rows, const float* __restrict__ g_hs,
+                                                    int64_t KP, int64_t k_begin, int stride, float a_iso, float marg,
+                                                    float* smem, uint64_t* bars, OuterAcc& outer, uint32_t& it,
+                                                    const float (&x)[E][DP], float (&m)[E], float (&S)[E],
+                                                    unsigned* nscreened = nullptr, unsigned* nrefined_out = nullptr) {
+  constexpr int KIND = AISB_COV_ISO_SHARED;
+  constexpr int JJ = comps_per_step(KIND, DP);
+  constexpr int kFoldEvery = chunk_comps(KIND, DP) >= 256 ? 4 : (chunk_comps(KIND, DP) >= 64 ? 16 : 32);
+  static_assert(E % 2 == 0, "packed path needs an even number of points per thread");
+  constexpr int EP = E / 2;
+  int nchunk = 0;
+  unsigned nrefined = 0, nunits = 0;
+  outer_init<E>(outer);
+  const float bmax2 = __ldg(g_hs + KP);
+  const float inv2a = 0.5f / a_iso;
+  float2 x2[EP][DP], cthr[EP], thr[EP], m2[EP], S2[EP];
+#pragma unroll
+  for (int pp = 0; pp < EP; ++pp) {
+    float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      x2[pp][d] = make_float2(x[2 * pp][d], x[2 * pp + 1][d]);
+      u0 = fmaf(x[2 * pp][d], x[2 * pp][d], u0);
+      u1 = fmaf(x[2 * pp + 1][d], x[2 * pp + 1][d], u1);
+    }
+    u0 *= a_iso * a_iso;
+    u1 *= a_iso * a_iso;
+    const float e0 = 1.9073486e-6f * (u0 + bmax2), e1 = 1.9073486e-6f * (u1 + bmax2);  // 2^-19 (...)
+    cthr[pp] = make_float2((marg + e0 - u0) * inv2a, (marg + e1 - u1) * inv2a);
+    m2[pp] = make_float2(kNegBig, kNegBig);
+    S2[pp] = make_float2(0.f, 0.f);
+    thr[pp] = make_float2(fmaf(kNegBig, -inv2a, cthr[pp].x), fmaf(kNegBig, -inv2a, cthr[pp].y));
+  }
+  auto fold = [&]() {
+#pragma unroll
+    for (int pp = 0; pp < EP; ++pp) {
+      m[2 * pp] = m2[pp].x;
+      m[2 * pp + 1] = m2[pp].y;
+      S[2 * pp] = S2[pp].x;
+      S[2 * pp + 1] = S2[pp].y;
+    }
+    outer_fold<E>(outer, m, S);
+#pragma unroll
+    for (int pp = 0; pp < EP; ++pp) S2[pp] = make_float2(0.f, 0.f);
+  };
+  stream_components<KIND, DP, true>(
+      g_rows, g_hs, k_begin, KP, smem, bars, it,
+      [&](const float* srows, const float* shs, int cnt, int64_t) {
+        accumulate_chunk_screen<DP, EP, JJ, COUNT>(srows, shs, cnt, a_iso, -inv2a, x2, cthr, thr, m2, S2, nrefined);
+        if constexpr (COUNT) nunits += static_cast<unsigned>(cnt / JJ) * EP;
+        if ((++nchunk % kFoldEvery) == 0) fold();
+      },
+      stride);
+  fold();
+  outer_finish<E>(outer, m, S);
+  if constexpr (COUNT) {
+    *nscreened = nunits;
+    *nrefined_out = nrefined;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Point tile load: thread t owns points tile_base + e*128 + t (coalesced across the warp).
 // Out-of-range points are clamped to n-1 (computed, never stored).
@@ -512,6 +668,36 @@ __device__ __forceinline__ void load_points(const float* __restrict__ x, int64_t
       const float* r = x + pc * D;
 #pragma unroll
       for (int d = 0; d < DP; ++d) xr[e][d] = d < D ? __ldg(r + d) : 0.f;
+    }
+  }
+}
+
+// Warp-contiguous variant for spatially ordered points: warp w owns the 32*E consecutive points
+// tile_base + w*32*E + e*32 + lane, so a packed register set (two values of e) spans 64 neighbours of the ordering.
+template <int DP, int E>
+__device__ __forceinline__ void load_points_warp(const float* __restrict__ x, int64_t n, int64_t tile_base,
+                                                 float (&xr)[E][DP], int64_t (&pidx)[E]) {
+  static_assert(DP >= 4 || DP == 2, "vector loads");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int64_t p = tile_base + warp * (32 * E) + e * 32 + lane;
+    pidx[e] = p;
+    const int64_t pc = p < n ? p : n - 1;
+    if constexpr (DP >= 4) {
+      const float4* r = reinterpret_cast<const float4*>(x + pc * DP);
+#pragma unroll
+      for (int q = 0; q < DP / 4; ++q) {
+        const float4 f = __ldg(r + q);
+        xr[e][4 * q + 0] = f.x;
+        xr[e][4 * q + 1] = f.y;
+        xr[e][4 * q + 2] = f.z;
+        xr[e][4 * q + 3] = f.w;
+      }
+    } else {
+      const float2 f = __ldg(reinterpret_cast<const float2*>(x + pc * 2));
+      xr[e][0] = f.x;
+      xr[e][1] = f.y;
     }
   }
 }

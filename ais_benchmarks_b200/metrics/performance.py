@@ -90,6 +90,8 @@ class CMemoryUsage(CMetric):
         return self.value
 
     def reset(self, **kwargs):
-        # as in the reference (performance.py:77-80) the accumulated value survives a reset
+        # performance.py:77-81: all three counters restart (the reported `value` is only refreshed by the next post())
         self.mem_ini = 0
         self.mem_end = 0
+        self.mem_cum = 0
+        gc.collect()

@@ -126,23 +126,25 @@ class CSamplingMethod(metaclass=ABCMeta):
         return self._n() / self._num_q_samples
 
     def get_NESS(self):
-        """Autocorrelation-based ESS of base.py:41-70 (host statistic over the sample chain; not on the hot path)."""
-        x = self.samples
+        """Autocorrelation ESS / n of the sample chain (role of base.py:41-70; used by the sequential samplers, the
+        importance samplers override it with get_approx_NESS). Lag-t autocorrelation from the variogram,
+        rho_t = 1 - V_t / (2 W) with V_t the mean squared lag-t increment and W the sample variance (both summed over
+        all coordinates), accumulated until the first even lag at which rho_{t-1} + rho_t turns negative (Geyer's
+        initial positive sequence); ESS = n / (1 + 2 sum_t rho_t). Host statistic, not on the hot path."""
+        x = np.asarray(self.samples, dtype=np.float64)
         n = len(x)
-        variogram = lambda t: np.array([((x[t:] - x[:(n - t)]) ** 2).sum() / (n - t)])
-        mean = x.mean()
-        dist = x - mean
-        W = (dist ** 2).sum() / (n - 1)
-        t = 1
-        rho = np.ones(n)
-        negative_autocorr = False
-        while not negative_autocorr and (t < n):
-            rho[t] = (1. - variogram(t) / (2. * W))[0]
-            if not t % 2:
-                negative_autocorr = sum(rho[t - 1:t + 1]) < 0
-            t += 1
-        ess = n / (1 + 2 * rho[1:t].sum())
-        return ess / len(self.samples)
+        if n < 2:
+            return 1.0
+        two_w = 2.0 * np.sum((x - x.mean()) ** 2) / (n - 1)
+        tail, prev = 0.0, 1.0
+        for lag in range(1, n):
+            step = x[lag:] - x[:n - lag]
+            rho = 1.0 - (np.sum(step * step) / (n - lag)) / two_w
+            tail += rho
+            if lag % 2 == 0 and prev + rho < 0:
+                break
+            prev = rho
+        return 1.0 / (1.0 + 2.0 * tail)
 
     def get_approx_NESS(self):
         """ESS / n with ESS = 1 / sum w~^2 (base.py:72-75), from the device-side partial sums
@@ -341,32 +343,3 @@ def multinomial_resample(logw, n_draws):
     cdf = torch.cumsum(w, 0)
     u = torch.rand(n_draws, dtype=torch.float64, device=logw.device) * cdf[-1]
     return torch.clamp(torch.searchsorted(cdf, u, right=True), max=logw.shape[0] - 1)
-
-
-def make_grid(space_min, space_max, resolution):
-    """base.py:249-264."""
-    dim_range = space_max - space_min
-    num_samples = (dim_range / resolution).tolist()
-    for i in range(len(num_samples)):
-        num_samples[i] = int(num_samples[i])
-        if num_samples[i] < 1:
-            num_samples[i] = 1
-    dimensions = []
-    shape = np.array([0] * len(num_samples))
-    for i in range(len(num_samples)):
-        dimensions.append(np.linspace(space_min[i], space_max[i], num_samples[i]))
-        shape[i] = len(dimensions[i])
-    samples = np.array(np.meshgrid(*dimensions)).T.reshape(-1, len(space_min))
-    return samples, dimensions, shape
-
-
-def grid_sample_distribution(dist, space_min, space_max, resolution):
-    grid, dims, shape = make_grid(space_min, space_max, resolution)
-    log_prob = dist.log_prob(np.array(grid))
-    return grid, log_prob, dims, shape
-
-
-def uniform_sample_distribution(dist, space_min, space_max, nsamples):
-    samples = np.random.uniform(space_min, space_max, size=(nsamples, len(space_max)))
-    log_prob = dist.log_prob(samples.reshape(nsamples, len(space_max)))
-    return samples.reshape(nsamples, len(space_max)), log_prob

@@ -43,12 +43,14 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
         self._means = None
         self._mixture = None
         self._objects = None
+        self._pending_records = []
         self.reset()
 
     # -- proposal state ----------------------------------------------------------------------------
     def reset(self):
         super(CDeterministicMixtureAIS, self).reset()
         # proposal centres ~ U(space_min, space_max) from the host RNG, as dm_ais.py:36-37
+        self._pending_records = []
         centres = np.random.uniform(self.space_min, self.space_max, size=(self.N, self.ndims))
         if self.sharded:
             from .. import parallel
@@ -132,7 +134,18 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
         target = target_device_mixture(target_d)
         logp_in = None if target is not None else foreign_target_logp(target_d, new_samples)
         logw, _, _, partials = _device.dm_weights(new_samples, target, logp_in, self.proposal_mixture(), hint=hint)
+        if hint is not None:
+            # the hinted path may run the tensor-core kernel, which reports a barrier time-out only through the record
+            # (n_valid = -1) and leaves log q unwritten: remember the record, importance_sample() checks it where it
+            # reads results back anyway (stream-ordered, one small D2H per call)
+            self._pending_records.append(partials)
         return logw, partials
+
+    def _check_pending_records(self):
+        """Raise AisbError if any weighting since the last check aborted (see weigh)."""
+        if self._pending_records:
+            recs, self._pending_records = torch.stack(self._pending_records), []
+            _device.check_partials(recs)
 
     def _own_proposal(self, per=None):
         """Proposal index of every row of a proposal-major batch of N*per draws."""
@@ -278,6 +291,7 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
             self._append(new_samples, new_logw)
             self._n_all_ranks += self.N * int(self.K)
             elapsed_time = time.time() - t_ini
+        self._check_pending_records()
         # weights / weights.sum() over ALL iterations (dm_ais.py:86) -- and all ranks
         norm_w = _device.normalize_weights(self._logw_dev, self._global_partials())
         return self._out(self._samples_dev), (norm_w if self.device_outputs else norm_w.double().cpu().numpy())

@@ -104,5 +104,6 @@ class CLayeredAIS(CDeterministicMixtureAIS):
             self._append(new_samples, new_logw)
             self._n_all_ranks += self.N * int(self.K)
             elapsed_time = time.time() - t_ini
+        self._check_pending_records()
         norm_w = _device.normalize_weights(self._logw_dev, self._global_partials())
         return self._out(self._samples_dev), (norm_w if self.device_outputs else norm_w.double().cpu().numpy())

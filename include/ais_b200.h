@@ -146,6 +146,28 @@ int aisb_mixture_logpdf_ordered_f32(const float* d_x, int64_t n, const aisb_pack
                                     void* d_workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Screen-and-refine evaluation of a spatially ordered KDE (same contract and same result as
+ * aisb_mixture_logpdf_ordered_f32 to float32 accuracy; replaces the same reference code, CMixtureModel.py:43-57 reached
+ * through sampling_methods/base.py:156-179). Every (point, component) pair is first evaluated in the expanded form
+ * ||a x||^2 + 2 a (h_j + x . b_j), h_j = ||b_j||^2 / (2 a), which costs half the FMAs of the float32-safe centred form
+ * but is only good enough to DECIDE whether the pair can matter; the exact centred evaluation and the log-sum-exp fold
+ * run only for groups of components that are not negligible (2^-(21 + log2 KP) of the running maximum, minus a
+ * rounding-error allowance that grows with the distance of the data from the origin) for at least one of the 64
+ * consecutive points that share a packed register set. Needs: ISO_SHARED without offsets, D in {2, 4, 8, 16}, d_x
+ * 16-byte aligned, points and components in a spatially coherent order (else it is correct but slow).
+ *   aisb_kde_screen_floats(K)   floats of the screen vector: h_j for the KP packed components + an 8-float trailer
+ *                               (trailer[0] = max_j ||b_j||^2)
+ *   aisb_kde_screen_pack_f32    builds it from the packed mixture (once per KDE)
+ *   d_stats                     NULL, or 2 zero-initialised uint64 counters that receive {refined, screened} units
+ *                               (unit = 64 points x one group of components); selects an instrumented kernel
+ */
+int64_t aisb_kde_screen_floats(int64_t K);
+int aisb_kde_screen_pack_f32(const aisb_packed_mixture* mix, float* d_screen, void* stream);
+int aisb_mixture_logpdf_screened_f32(const float* d_x, int64_t n, const aisb_packed_mixture* mix, const float* d_screen,
+                                     float* d_out_logp, void* d_workspace, size_t workspace_bytes,
+                                     unsigned long long* d_stats, void* stream);
+
+/*
  * Deterministic-mixture importance weights in one pass over the samples:
  *   logp_i = log pi(x_i) (target mixture, or read from d_logp_in when target == NULL),
  *   logq_i = log q(x_i)  (proposal mixture),  logw_i = logp_i - logq_i.

@@ -1,0 +1,209 @@
+"""Runs the UNMODIFIED reference's own test files and its CBenchmark.evaluate_method on top of THIS repo's classes.
+
+Executed as a subprocess by tests/test_reference_dropin.py (it rewires sys.modules, so it must not share an interpreter
+with the rest of the suite). The reference is imported from oracle/_ref (oracle/build_ref.py); this repo's classes are
+aliased into the reference's namespaces exactly as INTEGRATION.md section A describes; then
+
+  unittest   oracle/_ref/tests/distributions/test_multivariate_normal_unittest.py   (scipy known answers)
+             oracle/_ref/tests/distributions/test_multivariate_uniform_unittest.py
+             oracle/_ref/tests/metrics/test_metric_kldivergence.py                   (closed-form KLDs at 1 %)
+  caller     the reference's CBenchmark.load_benchmark / load_methods / evaluate_method / write_results
+             (benchmark/CBenchmark.py:58-137, 318-326, 328-569) on the default targets and the DM-AIS / M-PMC / LAIS /
+             TP-AIS entries of def_methods.yaml.
+
+`--impl reference` runs the same with the reference's own classes (no aliasing; works without a GPU): the CPU leg of the
+test and the proof that the harness itself is sound. Prints one JSON line with the outcome.
+"""
+import argparse
+import io
+import json
+import os
+import sys
+import tempfile
+import unittest
+import warnings
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+BENCH_YAML = """
+targets:
+    - name: gmm
+      type: CGaussianMixtureModel
+      params: {means: [[1.5], [-4.2], [0.01], [7.5]],
+               sigmas: [[0.4], [0.05], [0.003], [0.003]],
+               weights:[0.4, 0.4, 0.1, 0.1],
+               support:[[-10], [10]]}
+      batch_size: 2
+      nsamples: 200
+      nsamples_eval: 2000
+      tags: []
+    - name: gmm
+      type: CGaussianMixtureModel
+      params: {means: [[0.0, 0.0], [-0.3, 0.5]],
+               sigmas: [[0.01, 0.1], [0.01, 0.03]],
+               weights:[0.5, 0.5],
+               support:[[-1, -1], [1, 1]]}
+      batch_size: 2
+      nsamples: 300
+      nsamples_eval: 2000
+      tags: []
+    - name: normal
+      type: CMultivariateNormal
+      params: {mean: [0.0], sigma: [[0.2]], support:[-5, 5]}
+      batch_size: 2
+      nsamples: 200
+      nsamples_eval: 2000
+      tags: []
+"""
+# def_methods.yaml:3-10, 29-38, 50-68 verbatim (the four samplers north_star names)
+METHODS_YAML = """
+methods:
+    - name: m_pmc
+      type: CMixturePMC
+      debug: true
+      params:
+        K: 50
+        N: 10
+        J: 1000
+        sigma: 0.01
+    - name: TP_AISr_ESS90
+      type: CTreePyramidSampling
+      debug: true
+      params:
+        method: "'simple'"
+        resampling: "'leaf'"
+        kernel: "'haar'"
+        ess_target: 0.90
+        n_min: 5
+        parallel_samples: 32
+    - name: lais
+      type: CLayeredAIS
+      debug: true
+      params:
+        K: 3
+        N: 5
+        J: 1000
+        L: 10
+        sigma: 0.5
+        mh_sigma: 0.5
+    - name: dm_ais
+      type: CDeterministicMixtureAIS
+      debug: true
+      params:
+        K: 10
+        N: 5
+        J: 1000
+        sigma: 0.5
+"""
+
+
+def alias_b200_classes():
+    """INTEGRATION.md section A, second recipe, verbatim."""
+    import ais_benchmarks_b200.distributions as d
+    import ais_benchmarks_b200.sampling_methods as s
+    import ais_benchmarks_b200.metrics as m
+    import ais_benchmarks.distributions as rd
+    import ais_benchmarks.sampling_methods as rs
+    import ais_benchmarks.metrics.divergences as rm
+    for name in d.__all__:
+        setattr(rd, name, getattr(d, name))
+    for name in s.__all__:
+        setattr(rs, name, getattr(s, name))
+    rm.CKLDivergence, rm.CJSDivergence = m.CKLDivergence, m.CJSDivergence
+
+
+def run_unittests(build_ref):
+    build_ref.seed_tests_namespace()
+    names = ["tests.distributions.test_multivariate_normal_unittest",
+             "tests.distributions.test_multivariate_uniform_unittest",
+             "tests.metrics.test_metric_kldivergence"]
+    import importlib
+    suite = unittest.TestSuite()
+    for n in names:
+        suite.addTests(unittest.defaultTestLoader.loadTestsFromModule(importlib.import_module(n)))
+    stream = io.StringIO()
+    sink = io.StringIO()
+    old = sys.stdout
+    sys.stdout = sink                       # the reference's tests print every probability they check
+    try:
+        res = unittest.TextTestRunner(stream=stream, verbosity=0).run(suite)
+    finally:
+        sys.stdout = old
+    return {"run": res.testsRun, "failures": [str(t[0]) + ": " + t[1][-400:] for t in res.failures],
+            "errors": [str(t[0]) + ": " + t[1][-400:] for t in res.errors]}
+
+
+def run_benchmark(expect_module_prefix):
+    """The reference's CBenchmark drives targets / samplers / metrics built by ITS OWN eval() factories."""
+    import numpy as np
+    from ais_benchmarks.benchmark.CBenchmark import CBenchmark
+    tmp = tempfile.mkdtemp(prefix="aisb_dropin_")
+    bfile, mfile, out = (os.path.join(tmp, f) for f in ("bench.yaml", "methods.yaml", "results.txt"))
+    with open(bfile, "w") as f:
+        f.write(BENCH_YAML)
+    with open(mfile, "w") as f:
+        f.write(METHODS_YAML)
+    bench = CBenchmark()
+    bench.load_benchmark(bfile)
+    cols = "dims output_samples KLD JSD NESS method target_d accept_rate proposal_samples proposal_evals target_evals\n"
+    with open(out, "w") as f:
+        f.write(cols)
+    rows_expected = 0
+    classes = set()
+    sink = io.StringIO()
+    for target, ndims, nsamples, neval, bsize in zip(bench.targets, bench.ndims, bench.nsamples, bench.eval_sampl,
+                                                     bench.batch_sizes):
+        classes.add(type(target).__module__)
+        bench.load_methods(mfile, target.support()[0], target.support()[1], ndims)
+        for method in bench.methods:
+            classes.add(type(method).__module__)
+            method.reset()
+            old = sys.stdout
+            sys.stdout = sink
+            try:
+                CBenchmark.evaluate_method(ndims=ndims, target_dist=target, sampling_method=method, max_samples=nsamples,
+                                           max_sampling_time=600, batch_size=bsize, debug=False, metrics=["KLD", "JSD"],
+                                           rseed=0, n_reps=1, sampling_eval_samples=neval, filename=out)
+            finally:
+                sys.stdout = old
+            rows_expected += 1
+    bad = [c for c in classes if not c.startswith(expect_module_prefix)]
+    assert not bad, "objects were built from %s, expected %s.*" % (bad, expect_module_prefix)
+    with open(out) as f:
+        lines = f.read().splitlines()
+    assert lines[0] + "\n" == cols
+    table = [ln.split() for ln in lines[1:]]
+    assert all(len(r) == 11 for r in table), "results.txt row format (CBenchmark.py:318-326)"
+    final = {}
+    for r in table:                          # last row per (method, target, dims) = the finished experiment
+        final[(r[5], r[6], r[0])] = r
+    summary = {}
+    for (meth, tgt, dims), r in sorted(final.items()):
+        kld, jsd, ness = float(r[2]), float(r[3]), float(r[4])
+        assert np.isfinite(kld) and np.isfinite(jsd) and 0.0 < ness <= 1.0 + 1e-9, r
+        assert int(r[1]) >= 200 and int(r[8]) >= int(r[1]) and int(r[10]) > 0, r
+        summary["%s/%s%sD" % (meth, tgt, dims)] = {"n": int(r[1]), "KLD": kld, "JSD": jsd, "NESS": ness}
+    assert len(final) == rows_expected, (len(final), rows_expected)
+    return {"experiments": len(final), "rows": len(table), "final": summary}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skip-benchmark", action="store_true")
+    args = ap.parse_args()
+    from oracle import build_ref
+    build_ref.load()
+    if args.impl == "b200":
+        alias_b200_classes()
+    out = {"impl": args.impl, "ref_verified": build_ref.verify()}
+    out["unittest"] = run_unittests(build_ref)
+    if not args.skip_benchmark:
+        out["benchmark"] = run_benchmark("ais_benchmarks_b200" if args.impl == "b200" else "ais_benchmarks.")
+    print("DROPIN_JSON " + json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

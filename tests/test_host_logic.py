@@ -23,7 +23,10 @@ def test_mvn_constructor_contract():
     assert np.allclose(d.support(), [[-6 * np.sqrt(2), 1 - 6], [6 * np.sqrt(2), 1 + 6]])   # CMultivariateNormal.py:37-40
     v0 = d._version
     d.set_moments(np.zeros(2), np.eye(2))
-    assert d._version == v0 + 1 and d.is_diagonal()
+    assert d._version > v0 and d.is_diagonal()           # every parameter change invalidates packed copies
+    v1 = d._version
+    d.loc = np.ones(2)                                         # the public attribute setters invalidate them too
+    assert d._version > v1 and d._packed is None
     with pytest.raises(AssertionError):
         d.set_moments(np.zeros(2), np.zeros((2, 2)))           # det > 0 (CMultivariateNormal.py:55-56)
     with pytest.raises(AssertionError):
