@@ -120,7 +120,9 @@ class CKLDivergence(CDivergence):
             from .. import parallel
             self.partials = parallel.merge_kld_partials(parallel.all_gather_records(self.partials))
         self._warn(self.partials)
-        self.value = _device.kld_finalize(self.partials)
+        # np.float64 like the reference's np.sum(res) (divergences.py:105): callers divide by expected values that may
+        # be 0 (the reference's own test_equal) and rely on numpy's inf / nan instead of a ZeroDivisionError
+        self.value = np.float64(_device.kld_finalize(self.partials))
         return self.value
 
     @staticmethod
@@ -203,11 +205,11 @@ class CJSDivergence(CDivergence):
         if part[7] > 0 and part[5] / part[7] < .1:
             print("WARNING. JSD compute. Only %6.3f%% inliers" % (part[5] / part[7] * 100))
         if part[5] <= 0:
-            self.value = 0.0  # empty sums (:188-195)
+            self.value = np.float64(0.0)  # empty sums (:188-195)
             return self.value
         log_norm_p, log_norm_q = _device.pair_log_norms(part)
         terms = _device.jsd_terms(lp, lq, floor, log_norm_p, log_norm_q)
         terms = parallel.all_gather_records(terms).sum(axis=0) if self.sharded else terms.cpu().numpy()
         self.dropped = int(terms[1])
-        self.value = float(terms[0] / self.log2)
+        self.value = np.float64(terms[0] / self.log2)
         return self.value

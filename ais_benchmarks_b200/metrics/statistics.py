@@ -54,5 +54,5 @@ class CExpectedValueMSE(CMetric):
         self.ev_p = self._expectation(x, lp)
         self.ev_q = self._expectation(x, lq)
         d = self.ev_p - self.ev_q
-        self.value = float(d @ d)
+        self.value = np.float64(d @ d)
         return self.value

@@ -438,49 +438,149 @@ def run_cuda(args):
 
 
 # ----------------------------------------------------------------------------------------------------
-# CPU arms: the reference algorithm as restated by the oracle (per-component loop + logsumexp, float64)
+# CPU arms. "reference": the UNMODIFIED reference's own classes, imported from oracle/_ref (oracle/build_ref.py copies
+# them verbatim from /root/reference; the directory travels to the GPU box like a built .so):
+#     KDE of sampling_methods/base.py:162-179  ->  CMixtureModel.log_prob (mixture/CMixtureModel.py:43-57)
+#     ->  CKLDivergence.compute_from_samples (metrics/divergences.py:101-153).
+# "port": the numpy oracle's restatement of the same loop, used only if oracle/_ref is absent.
 # ----------------------------------------------------------------------------------------------------
-def _cpu_kde_chunk(task):
+def _reference():
+    """-> (kind, module-or-None)."""
+    try:
+        from oracle import build_ref
+        if build_ref.available():
+            import warnings
+            warnings.filterwarnings("ignore")
+            build_ref.load()
+            return "reference"
+    except Exception as e:  # noqa: BLE001
+        print("[bench] oracle/_ref unusable (%s: %s); falling back to the oracle port" % (type(e).__name__, e),
+              file=sys.stderr)
+    return "port"
+
+
+def _single_thread_blas():
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:  # noqa: BLE001
+        pass
+
+
+_REF_STATE = {}
+
+
+def _ref_eval_chunk(x):
+    """Worker (forked after the KDE was built): the reference's q.log_prob and p.log_prob on a slice of the points."""
+    _single_thread_blas()
+    q, p = _REF_STATE["q"], _REF_STATE["p"]
+    return p.log_prob(x), q.log_prob(x)
+
+
+def _port_eval_chunk(x):
     from oracle import ais_oracle as O
-    x, centres, bw, mu, sig, w = task
+    _single_thread_blas()
+    centres, bw, mu, sig, w = _REF_STATE["port"]
     covs = np.stack([np.eye(centres.shape[1]) * bw] * len(centres))
     lq = O.mixture_log_prob(x, centres, covs, np.full(len(centres), 1.0 / len(centres)))   # reference hot loop #3
-    lp = O.gmm_log_prob(x, mu, sig, w)
-    return lp, lq
+    return O.gmm_log_prob(x, mu, sig, w), lq
 
 
-def cpu_kde_once(n_eval, n_centres, cores, seed=0):
-    from oracle import ais_oracle as O
+def cpu_kde_once(n_eval, n_centres, cores, seed=0, kind=None):
+    """One KDE-KLD metric evaluation on the host: KDE build + q and p log-densities + KLD. -> (seconds, kld, kind)."""
+    kind = kind or _reference()
     c = KDE_CFG
     mu, sig, w, sup = random_gmm(seed, c["D"], c["modes"])
     rs = np.random.RandomState(seed + 1)
     centres = gmm_samples(rs, mu, sig, w, n_centres).astype(np.float64)
     x = rs.uniform(sup[0], sup[1], size=(n_eval, c["D"]))
-    chunks = np.array_split(x, cores)
-    tasks = [(ch, centres, c["bw"], mu, sig, w) for ch in chunks]
     t0 = time.perf_counter()
+    if kind == "reference":
+        from ais_benchmarks.distributions import CGaussianMixtureModel
+        from ais_benchmarks.metrics.divergences import CKLDivergence
+        from ais_benchmarks.sampling_methods.base import CMixtureSamplingMethod
+
+        class _KdeHolder(CMixtureSamplingMethod):
+            """The smallest concrete CMixtureSamplingMethod: everything numeric is inherited reference code."""
+            def importance_sample(self, target_d, n_samples, timeout):
+                raise NotImplementedError
+
+            def draw(self, ax):
+                return []
+
+        np.random.seed(seed)
+        q = _KdeHolder({"space_min": sup[0], "space_max": sup[1], "dims": c["D"], "n_samples_kde": n_centres})
+        q.bw = c["bw"]
+        q.samples = centres
+        q._update_model()                                  # base.py:162-179: n_centres CMultivariateNormal objects
+        p = CGaussianMixtureModel({"means": mu, "sigmas": sig, "weights": w, "support": sup})
+        _REF_STATE.update(q=q, p=p)
+        worker = _ref_eval_chunk
+    else:
+        _REF_STATE["port"] = (centres, c["bw"], mu, sig, w)
+        worker = _port_eval_chunk
     if cores == 1:
-        res = [_cpu_kde_chunk(tasks[0])]
+        res = [worker(x)]
     else:
         import multiprocessing as mp
         with mp.get_context("fork").Pool(cores) as pool:
-            res = pool.map(_cpu_kde_chunk, tasks)
+            res = pool.map(worker, np.array_split(x, cores))
     lp = np.concatenate([r[0] for r in res])
     lq = np.concatenate([r[1] for r in res])
-    kld = O.kld_from_log_probs(lp, lq)
-    return time.perf_counter() - t0, kld
+    if kind == "reference":
+        kld = float(CKLDivergence().compute_from_log_probs(lp, lq).sum())       # divergences.py:136-153
+    else:
+        from oracle import ais_oracle as O
+        kld = O.kld_from_log_probs(lp, lq)
+    return time.perf_counter() - t0, kld, kind
+
+
+def _cpu_sample_text(kind, cores, n_eval, n_centres, dt):
+    what = ("the reference's own classes from oracle/_ref (KDE build base.py:162-179 + CMixtureModel.log_prob "
+            "CMixtureModel.py:43-57 + CKLDivergence divergences.py:136-153)" if kind == "reference" else
+            "oracle port of the reference algorithm (per-component float64 loop + logsumexp)")
+    return "%s, %d process(es), %d eval points x %d centres, D=8, %.1f s" % (what, cores, n_eval, n_centres, dt)
 
 
 def cpu_baseline_kde(cores, budget_s):
-    n_eval, n_centres = 2048 * cores, 2000
-    dt, _ = cpu_kde_once(n_eval, n_centres, cores)
+    n_eval, n_centres = 2048 * cores, 1000
+    dt, _, kind = cpu_kde_once(n_eval, n_centres, cores)
     rate = n_eval * n_centres / dt
-    n_centres = int(max(2000, min(40000, rate * budget_s / n_eval)))
-    dt, kld = cpu_kde_once(n_eval, n_centres, cores)
-    return {"value": n_eval * n_centres / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "oracle port of the reference algorithm (per-component float64 loop + logsumexp, "
-                      "CMixtureModel.py:43-57 + divergences.py:136-153) on %d eval points x %d centres, D=8, %.1f s"
-                      % (n_eval, n_centres, dt)}
+    n_centres = int(max(1000, min(40000, rate * budget_s / n_eval)))
+    dt, kld, kind = cpu_kde_once(n_eval, n_centres, cores)
+    return {"value": n_eval * n_centres / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": _cpu_sample_text(kind, cores, n_eval, n_centres, dt)}
+
+
+def cpu_baseline_dm(budget_s=10.0):
+    """DM-AIS on the host at the configs[4] shape (D=32, 64-mode target, 1024 proposals), both ways SURVEY 8(d) asks:
+    (A) the reference AS SHIPPED -- CDeterministicMixtureAIS.importance_sample, a per-sample Python loop
+    (dm_ais.py:58-86), one iteration with K=1 (1024 samples); (B) the reference's BATCHED API -- target.log_prob(X) and
+    method.log_prob(X) on the same samples. Returns None without oracle/_ref."""
+    if _reference() != "reference":
+        return None
+    from ais_benchmarks.distributions import CGaussianMixtureModel
+    from ais_benchmarks.sampling_methods import CDeterministicMixtureAIS
+    c = DM_CFG
+    mu, sig, w, sup, pmeans, per = dm_workload()
+    N = c["n_proposals"]
+    tgt = CGaussianMixtureModel({"means": mu, "sigmas": sig, "weights": w, "support": sup})
+    np.random.seed(0)
+    m = CDeterministicMixtureAIS({"space_min": sup[0], "space_max": sup[1], "dims": c["D"], "K": 1, "N": N, "J": 1000,
+                                  "sigma": c["sigma"]})
+    t0 = time.perf_counter()
+    x, _ = m.importance_sample(tgt, N, timeout=budget_s)          # one iteration: N draws, N weights, N resamplings
+    dt_a = time.perf_counter() - t0
+    m.reset()
+    t0 = time.perf_counter()
+    lw = tgt.log_prob(x) - m.log_prob(x)                           # batched: 64 + 1024 component passes over all rows
+    dt_b = time.perf_counter() - t0
+    return {"value": len(x) / dt_a, "unit": "samples/s", "cores": 1, "kind": "reference",
+            "sample": "reference as shipped: CDeterministicMixtureAIS.importance_sample (dm_ais.py:58-86), one iteration, "
+                      "K=1, N=%d proposals, D=%d, %d samples in %.1f s" % (N, c["D"], len(x), dt_a),
+            "batched": {"value": len(x) / dt_b, "unit": "samples/s",
+                        "sample": "reference batched API: target.log_prob(X) - method.log_prob(X) on the same %d samples "
+                                  "(CMixtureModel.py:43-57), %.2f s" % (len(x), dt_b)}}
 
 
 def run_reference(args):
@@ -491,21 +591,28 @@ def run_reference(args):
     per_step = []
     n_eval, n_centres = 1024 * cores, 4000
     for _ in range(args.warmup):
-        cpu_kde_once(256 * cores, 500, cores)
+        cpu_kde_once(64 * cores, 250, cores)
     for _ in range(args.steps):
-        dt, kld = cpu_kde_once(n_eval, n_centres, cores)
+        dt, kld, kind = cpu_kde_once(n_eval, n_centres, cores)
         per_step.append(dt)
     ms = float(np.mean(per_step)) * 1e3
     val = n_eval * n_centres / (ms * 1e-3)
-    sample = ("oracle port of the reference CPU algorithm, %d processes, each step = %d eval points x %d centres "
-              "(bounded sample of the 1e6 x 1e6 workload; the rate is size-independent)" % (cores, n_eval, n_centres))
+    sample = _cpu_sample_text(kind, cores, n_eval, n_centres, ms * 1e-3) + \
+        " per step (bounded sample of the 1e6 x 1e6 workload: the reference materialises a (K, N) float64 matrix, " \
+        "CMixtureModel.py:49, 8 TB at full size; the rate is size-independent)"
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "BASELINE configs[3]: KDE-KLD, D=8, 16-mode GMM target, bw=0.02 (bounded sample)"},
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "config": {"workload": "BASELINE configs[3]: KDE-KLD, D=8, 16-mode GMM target, bw=0.02 (bounded sample)",
+                      "kld": kld},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
+    if not args.no_cpu:
+        out["dm_ais"] = {"metric": "DM-AIS weighted samples/sec", "cpu_baseline": cpu_baseline_dm()}
+        if out["dm_ais"]["cpu_baseline"] is not None:
+            out["dm_ais"]["value"] = out["dm_ais"]["cpu_baseline"]["value"]
+            out["dm_ais"]["unit"] = "samples/s"
     print_json(out)
 
 

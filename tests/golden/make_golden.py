@@ -294,6 +294,116 @@ def make_mpmc():
     save("mpmc", **out)
 
 
+def _f32(a):
+    """Round captured draws to float32-representable float64: the reference then computes from exactly the numbers the
+    float32 device path receives, and the fixture stores them in half the space (draws are inputs, not results)."""
+    return np.asarray(a, dtype=np.float32).astype(np.float64)
+
+
+def make_config3():
+    """BASELINE configs[2] SHAPE (8-D 16-mode GMM target, 256 proposals) driven through the reference's own adapt loops:
+
+    * M-PMC (sampling_methods/m_pmc.py:53-118), two consecutive iterations, in two geometries:
+        "std"  support [-1, 1]^8, sigma 0.05, K = 10 000 draws per iteration. The raw scatter of quirk Q3 exceeds 10 in
+               both iterations, so both updates end in the 10*I failsafe (m_pmc.py:71-72).
+        "tiny" support [-0.01, 0.01]^8, sigma 1e-6, K = 4 000. Iteration 1 keeps the raw scatter below 10: a genuine
+               FULL covariance for all 256 proposals (no failsafe); iteration 2 draws from those full-covariance
+               proposals and weighs against them, and its update hits the failsafe.
+      The mixture draws are captured (rounded to float32) by wrapping self.sample; everything else is reference code.
+    * LAIS (sampling_methods/layered_ais.py:54-104): DM weights of one 256 x 39 batch against the 256 proposals
+      (:90-94) and the 256-chain x 10-step MH layer with captured noise (:54-74).
+    """
+    out = {}
+    dims, N = 8, 256
+    geoms = [("std", 1.0, 0.05, 10000, (0.04, 0.05), 80), ("tiny", 0.01, 1e-6, 4000, (4e-6, 5e-6), 81)]
+    for name, half, sigma, K, (smin, smax), seed in geoms:
+        np.random.seed(seed)
+        target = generateRandomGMM(np.full(dims, -half), np.full(dims, half), 16,
+                                   sigma_min=np.full(dims, smin), sigma_max=np.full(dims, smax))
+        out["tmeans_" + name], out["tsigmas_" + name], out["tweights_" + name] = gmm_arrays(target)
+        np.random.seed(seed + 100)
+        s = CMixturePMC({"space_min": np.full(dims, -half), "space_max": np.full(dims, half), "dims": dims,
+                         "K": K, "N": N, "J": 1000, "sigma": sigma})
+        real_sample = s.sample
+        s.sample = lambda n, _f=real_sample: _f32(_f(n))
+        for it in range(2):
+            tag = "_%s_%d" % (name, it)
+            out["means" + tag] = np.array([p.loc for p in s.proposals])
+            out["covs" + tag] = np.array([p.scale for p in s.proposals])
+            out["alpha" + tag] = np.array(s.wproposals)
+            out["mixw" + tag] = np.array(s.model.weights)
+            n_before = len(s.samples)
+            s.importance_sample(target, n_before + K, timeout=3600)
+            x = np.array(s.samples[n_before:])
+            assert len(x) == K and np.array_equal(x, _f32(x))
+            out["x" + tag] = x.astype(np.float32)
+            out["w" + tag] = np.array(s.weights[n_before:])
+            out["new_means" + tag] = np.array([p.loc for p in s.proposals])
+            out["new_covs" + tag] = np.array([p.scale for p in s.proposals])
+            out["new_alpha" + tag] = np.array(s.wproposals)
+            failsafe = np.all(out["new_covs" + tag] == np.diag(np.ones(dims) * 10)[None], axis=(1, 2))
+            out["failsafe" + tag] = failsafe
+            print("  m-pmc %-4s it %d: failsafe on %d / %d proposals, sum w = %.6f" % (name, it, failsafe.sum(), N,
+                                                                                     out["w" + tag].sum()))
+        out["sigma_" + name], out["half_" + name] = np.array(sigma), np.array(half)
+    # ---- LAIS at the same shape ----
+    seed = 90
+    target = random_gmm(seed, dims, 16)
+    sup = target.support()
+    K, L, sigma, mh_sigma = 39, 10, 0.05, 0.5
+    np.random.seed(seed + 100)
+    s = CLayeredAIS({"space_min": sup[0], "space_max": sup[1], "dims": dims, "K": K, "N": N, "J": 1000, "L": L,
+                     "sigma": sigma, "mh_sigma": mh_sigma})
+    out["l_tmeans"], out["l_tsigmas"], out["l_tweights"] = gmm_arrays(target)
+    out["l_before"] = np.array([p.loc for p in s.proposals])
+    for p in s.proposals:                                    # capture the proposal draws (dm-style sampling, :82-88)
+        p.sample = (lambda n_samples=1, _f=p.sample: _f32(_f(n_samples)))
+    rs = np.random.RandomState(seed + 200)
+    delta = _f32(rs.normal(size=(L, N, dims)) * np.sqrt(mh_sigma))
+    u = _f32(rs.uniform(size=(L, N)))
+    d_iter = iter([delta[l, n] for n in range(N) for l in range(L)])
+    u_iter = iter([u[l, n] for n in range(N) for l in range(L)])
+    s.mhproposal.sample = lambda n_samples=1: np.array([next(d_iter)])
+    real_rand = np.random.rand
+    np.random.rand = lambda *a: next(u_iter)
+    try:
+        x, w = s.importance_sample(target, N * K, timeout=3600)          # exactly one iteration
+    finally:
+        np.random.rand = real_rand
+    assert len(x) == N * K and np.array_equal(x, _f32(x))
+    out["l_x"], out["l_w"] = np.asarray(x, dtype=np.float32), np.asarray(w)
+    out["l_ness"] = np.array(s.get_NESS())
+    out["l_after"] = np.array([p.loc for p in s.proposals])
+    out["l_delta"], out["l_u"] = delta.astype(np.float32), u.astype(np.float32)
+    out["l_lo"], out["l_hi"] = sup[0], sup[1]
+    out["l_cfg"] = np.array([K, L, sigma, mh_sigma])
+    out["l_pi_evals"] = np.array(s.num_target_evals)
+    _config3_logs(out)
+    save("config3", **out)
+
+
+def _config3_logs(out, rows=1000):
+    """Reference log densities behind every M-PMC batch of make_config3, for the first `rows` draws: log pi(x) and
+    log q(x) under the PRE-update proposal mixture (CMixtureModel.log_prob over CMultivariateNormal components with the
+    stored means / covariances / sanitised weights). They stay finite where the linear-domain weights of the reference
+    underflow to 0 / NaN ("tiny" iteration 1: proposals ~3e4 times wider than the target), so they are what pins the
+    full-covariance 256-component density at this shape."""
+    for name in ("std", "tiny"):
+        half = float(out["half_" + name])
+        sup = [np.full(8, -half), np.full(8, half)]
+        target = CGaussianMixtureModel({"means": out["tmeans_" + name], "sigmas": out["tsigmas_" + name],
+                                        "weights": out["tweights_" + name], "support": sup})
+        for it in range(2):
+            tag = "_%s_%d" % (name, it)
+            x = np.asarray(out["x" + tag][:rows], dtype=np.float64)
+            models = [CMultivariateNormal({"mean": m.copy(), "sigma": c.copy()})
+                      for m, c in zip(out["means" + tag], out["covs" + tag])]
+            q = CMixtureModel({"models": models, "weights": np.array(out["mixw" + tag], dtype=np.float64),
+                               "dims": 8, "support": sup})
+            out["lp" + tag] = target.log_prob(x)
+            out["lq" + tag] = q.log_prob(x)
+
+
 def make_lais():
     """LAIS upper layer (sampling_methods/layered_ais.py:54-74) with the random draws captured."""
     out = {}
@@ -406,6 +516,16 @@ def make_tpais():
 
 if __name__ == "__main__":
     np.seterr(all="ignore")
+    if sys.argv[1:] == ["config3_logs"]:       # re-derive the log-density arrays of an existing config3.npz
+        with np.load(os.path.join(OUT, "config3.npz")) as f:
+            out = {k: f[k] for k in f.files}
+        _config3_logs(out)
+        save("config3", **out)
+        sys.exit(0)
+    if len(sys.argv) > 1:                      # regenerate selected fixtures only: make_golden.py config3 mpmc ...
+        for name in sys.argv[1:]:
+            globals()["make_" + name]()
+        sys.exit(0)
     make_mvn()
     make_gmm()
     make_mixture()
@@ -413,6 +533,7 @@ if __name__ == "__main__":
     make_kde_kld()
     make_metrics()
     make_mpmc()
+    make_config3()
     make_lais()
     make_uniform()
     make_tpais()
