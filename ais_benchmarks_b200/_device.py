@@ -247,14 +247,21 @@ class DeviceMixture:
         return mix
 
 
-def kde_screen(mix):
-    """The screen vector of a spatially ordered KDE (C ABI aisb_kde_screen_pack_f32), built once per mixture; None when
-    the screen-and-refine kernel does not apply (D not in {2, 4, 8, 16}, or switched off with AISB_KDE_SCREEN=0)."""
+def kde_mode():
+    """Kernel family for a spatially ordered KDE evaluated on spatially ordered points (AISB_KDE_MODE):
+    "fast" (default)  recentred expanded form + exact re-evaluation of the points whose error estimate is too large
+    "screen"          expanded-form screen + exact centred refinement of every group that matters
+    "ordered"         centred form for every pair, fold skipping only (the round-1 kernel)"""
     import os
-    if mix.D not in (2, 4, 8, 16) or mix.kind != COV_ISO_SHARED or mix.offsets is not None:
-        return None
-    if os.environ.get("AISB_KDE_SCREEN", "1") == "0":
-        return None
+    return os.environ.get("AISB_KDE_MODE", "fast")
+
+
+def _kde_kernel_applies(mix, x):
+    return (mix.D in (2, 4, 8, 16) and mix.kind == COV_ISO_SHARED and mix.offsets is None and x.data_ptr() % 16 == 0)
+
+
+def kde_screen(mix):
+    """The screen vector of a spatially ordered KDE (C ABI aisb_kde_screen_pack_f32), built once per mixture."""
     if getattr(mix, "_screen", None) is None:
         lib = require_cuda()
         mix._screen = torch.empty(lib.aisb_kde_screen_floats(mix.K), dtype=torch.float32, device=mix.rows.device)
@@ -262,12 +269,31 @@ def kde_screen(mix):
     return mix._screen
 
 
+_fast_scratch = {}
+
+
+def _kde_fast_scratch(n):
+    lib = require_cuda()
+    dev = torch.cuda.current_device()
+    need = int(lib.aisb_kde_fast_scratch_bytes(int(n)))
+    buf = _fast_scratch.get(dev)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(need, dtype=torch.uint8, device=device())
+        _fast_scratch[dev] = buf
+    return buf
+
+
 def _logpdf_ordered(lib, x, n, mix, out, ws, stats=None):
-    """Both sides spatially ordered: the screen-and-refine kernel where it applies, else the fold-skipping kernel."""
-    screen = kde_screen(mix) if x.data_ptr() % 16 == 0 else None
-    if screen is not None:
-        check(lib.aisb_mixture_logpdf_screened_f32(_ptr(x), n, mix.ref(), _ptr(screen), _ptr(out), _ptr(ws), ws.numel(),
-                                                   _ptr(stats), stream_ptr()), "aisb_mixture_logpdf_screened_f32")
+    """Both sides spatially ordered: the fast / screened kernels where they apply, else the fold-skipping kernel."""
+    mode = kde_mode() if _kde_kernel_applies(mix, x) else "ordered"
+    if mode == "fast":
+        sc = _kde_fast_scratch(n)
+        check(lib.aisb_mixture_logpdf_fast_f32(_ptr(x), n, mix.ref(), _ptr(out), _ptr(ws), ws.numel(), _ptr(sc),
+                                               sc.numel(), _ptr(stats), stream_ptr()), "aisb_mixture_logpdf_fast_f32")
+    elif mode == "screen":
+        check(lib.aisb_mixture_logpdf_screened_f32(_ptr(x), n, mix.ref(), _ptr(kde_screen(mix)), _ptr(out), _ptr(ws),
+                                                   ws.numel(), _ptr(stats), stream_ptr()),
+              "aisb_mixture_logpdf_screened_f32")
     else:
         check(lib.aisb_mixture_logpdf_ordered_f32(_ptr(x), n, mix.ref(), _ptr(out), _ptr(ws), ws.numel(),
                                                   stream_ptr()), "aisb_mixture_logpdf_ordered_f32")
@@ -277,7 +303,7 @@ def mixture_logpdf(x, mix, out=None, points_ordered=False, stats=None):
     """x: float32 CUDA [n, D]; returns float32 CUDA [n] natural-log densities (C ABI: aisb_mixture_logpdf_f32).
     points_ordered: the caller has already put the rows of x in Z-order (parallel.spatial_shard): with a spatially
     ordered mixture the screen-and-refine / fold-skipping kernels are used directly, without the internal sort / scatter.
-    stats: optional zeroed int64 CUDA [2] that receives the screened kernel's {refined, screened} unit counters."""
+    stats: optional zeroed int64 CUDA [3] that receives the fast / screened kernel's unit counters."""
     lib = require_cuda()
     n = x.shape[0]
     if out is None:

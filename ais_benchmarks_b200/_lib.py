@@ -47,6 +47,8 @@ PROTOTYPES = {
     "aisb_kde_screen_floats": (_i64, [_i64]),
     "aisb_kde_screen_pack_f32": (C.c_int, [_pm, _vp, _vp]),
     "aisb_mixture_logpdf_screened_f32": (C.c_int, [_vp, _i64, _pm, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "aisb_kde_fast_scratch_bytes": (_sz, [_i64]),
+    "aisb_mixture_logpdf_fast_f32": (C.c_int, [_vp, _i64, _pm, _vp, _vp, _sz, _vp, _sz, _vp, _vp]),
     "aisb_dm_weights_f32": (C.c_int, [_vp, _i64, _pm, _vp, _pm, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "aisb_logw_partials_f32": (C.c_int, [_vp, _i64, _vp, _vp, _sz, _vp]),
     "aisb_normalize_weights_f32": (C.c_int, [_vp, _i64, C.POINTER(_dbl), _vp, _vp]),

@@ -69,20 +69,30 @@ __global__ void __launch_bounds__(kThreads,
 
 
 // ---------------------------------------------------------------------------------------------
-// Screen-and-refine variant for a spatially ordered KDE (pairwise.cuh, mixture_pass_screen): grid.x = ntiles * nsplit,
-// CTA b sweeps every nsplit-th chunk of the components, starting at chunk b / ntiles (interleaved split), for point tile
-// b % ntiles; warps own 32*E consecutive points. COUNT adds the (refined, screened) unit counters to stats[0..1].
+// Screen-and-refine variant for a spatially ordered KDE (pairwise.cuh, mixture_pass_screen).
+// CTA = ONE warp that owns 32*E consecutive points and its own 2-stage ring of kScreenChunk components: how much of a
+// chunk has to be refined differs wildly between neighbouring warps (a chunk of the Z-order curve is either next to a
+// warp's points or irrelevant to all of them), so warps that shared a ring and its per-chunk barrier spent a third of
+// their time waiting for each other (ncu: stall_barrier the top reason, profiles/r2_ncu_kde_screen_v1.txt). Up to 16 such
+// CTAs are resident per SM. grid.x = ntiles * nsplit; CTA b sweeps every nsplit-th chunk of the components, starting at
+// chunk b / ntiles (interleaved split), for point tile b % ntiles. COUNT adds the (refined, screened) unit counters to
+// stats[0..1].
 // ---------------------------------------------------------------------------------------------
+constexpr int kScreenThreads = 32;
+constexpr int kScreenChunk = 128;
+__host__ __device__ constexpr size_t screen_smem_bytes(int DP) {
+  return size_t(kStages) * (kScreenChunk * DP + kScreenChunk) * sizeof(float);
+}
+
 template <int DP, bool COUNT>
-__global__ void __launch_bounds__(kThreads, DP <= 8 ? 4 : 1)
+__global__ void __launch_bounds__(kScreenThreads, DP <= 8 ? 16 : 8)
     logpdf_screen_kernel(const float* __restrict__ x, int64_t n, PassArgs mix, const float* __restrict__ hs, float marg,
                          int nsplit, int64_t ntiles, float* __restrict__ out, float* __restrict__ ws_m,
                          float* __restrict__ ws_S, unsigned long long* __restrict__ stats) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[kStages];
-  __shared__ OuterAcc outer;
+  __shared__ OuterAccT<kScreenThreads> outer;
   constexpr int E = points_per_thread(DP);
-  constexpr int J = chunk_comps(AISB_COV_ISO_SHARED, DP);
 
   const int64_t tile = blockIdx.x % ntiles;
   const int64_t split = blockIdx.x / ntiles;
@@ -90,13 +100,13 @@ __global__ void __launch_bounds__(kThreads, DP <= 8 ? 4 : 1)
 
   float xr[E][DP];
   int64_t pidx[E];
-  load_points_warp<DP, E>(x, n, tile * (kThreads * E), xr, pidx);
+  load_points_warp<DP, E>(x, n, tile * (kScreenThreads * E), xr, pidx);
 
   float m[E], S[E];
   uint32_t it = 0;
   unsigned nscr = 0, nref = 0;
-  mixture_pass_screen<DP, E, COUNT>(mix.rows, hs, mix.KP, split * J, nsplit, mix.a_iso, marg, smem, bars, outer, it, xr,
-                                    m, S, &nscr, &nref);
+  mixture_pass_screen<DP, E, kScreenChunk, COUNT>(mix.rows, hs, mix.KP, split * kScreenChunk, nsplit, mix.a_iso, marg,
+                                                  smem, bars, outer, it, xr, m, S, &nscr, &nref);
   if constexpr (COUNT) {
     if ((threadIdx.x & 31) == 0) {
       atomicAdd(stats + 0, static_cast<unsigned long long>(nref));
@@ -115,6 +125,135 @@ __global__ void __launch_bounds__(kThreads, DP <= 8 ? 4 : 1)
         ws_S[split * n + pidx[e]] = S[e];
       }
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Fast variant for a spatially ordered KDE (pairwise.cuh, mixture_pass_fast): recentred expanded form, single-warp CTAs
+// with private rings like logpdf_screen_kernel. Every point's float32 error estimate
+//     eps = kFastErrC * 2^-24 * (||a x'||^2 + |t_max| + 1)      (natural-log units; model measured by
+//                                                                 scripts/kde_fast_error_model.py, 1.7x margin)
+// is compared with kFastTol * max(1, |log p|); points that fail are appended to `list` (their count in *list_n) and
+// re-evaluated by logpdf_subset_kernel with the centred form. With nsplit > 1 the test runs in fast_merge_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr float kFastErrC = 4.0f;
+constexpr float kFastTol = 3.0e-6f;
+
+__device__ __forceinline__ bool fast_needs_exact(float u2, float t_max, float logp) {
+  const float eps = kFastErrC * 5.9604645e-8f * (u2 + fabsf(t_max) + 1.f);
+  return eps > kFastTol * fmaxf(1.f, fabsf(logp));   // NaN / inf results compare false: nothing to refine there
+}
+
+template <int DP, bool COUNT>
+__global__ void __launch_bounds__(kScreenThreads, DP <= 8 ? 16 : 8)
+    logpdf_fast_kernel(const float* __restrict__ x, int64_t n, PassArgs mix, float marg, int nsplit, int64_t ntiles,
+                       float* __restrict__ out, float* __restrict__ ws_m, float* __restrict__ ws_S,
+                       float* __restrict__ ws_u2, int64_t* __restrict__ list, unsigned long long* __restrict__ list_n,
+                       unsigned long long* __restrict__ stats, int dbg) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bars[kStages];
+  __shared__ OuterAccT<kScreenThreads> outer;
+  __shared__ __align__(16) float sh_h[kScreenChunk];
+  constexpr int E = points_per_thread(DP);
+
+  const int64_t tile = blockIdx.x % ntiles;
+  const int64_t split = blockIdx.x / ntiles;
+  ring_init(bars);
+
+  float xr[E][DP];
+  int64_t pidx[E];
+  load_points_warp<DP, E>(x, n, tile * (kScreenThreads * E), xr, pidx);
+
+  float m[E], S[E], u2[E];
+  uint32_t it = 0;
+  unsigned nscr = 0, nfold = 0;
+  mixture_pass_fast<DP, E, kScreenChunk, COUNT>(mix.rows, mix.KP, split * kScreenChunk, nsplit, mix.a_iso, marg, smem,
+                                                sh_h, bars, outer, it, xr, m, S, u2, &nscr, &nfold, dbg);
+  if constexpr (COUNT) {
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(stats + 0, static_cast<unsigned long long>(nfold));
+      atomicAdd(stats + 1, static_cast<unsigned long long>(nscr));
+    }
+  }
+  if (nsplit == 1) {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (pidx[e] < n) {
+        const float lp = lse_finish(m[e], S[e]) + mix.uniform_offset;
+        out[pidx[e]] = lp;
+        if (fast_needs_exact(u2[e], m[e], lp)) list[atomicAdd(list_n, 1ull)] = pidx[e];
+      }
+  } else {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (pidx[e] < n) {
+        ws_m[split * n + pidx[e]] = m[e];
+        ws_S[split * n + pidx[e]] = S[e];
+        if (split == 0) ws_u2[pidx[e]] = u2[e];
+      }
+  }
+}
+
+__global__ void fast_merge_kernel(const float* __restrict__ ws_m, const float* __restrict__ ws_S,
+                                  const float* __restrict__ ws_u2, int nsplit, int64_t n, float add,
+                                  float* __restrict__ out, int64_t* __restrict__ list,
+                                  unsigned long long* __restrict__ list_n) {
+  const int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (p >= n) return;
+  float M = kNegBig;
+  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, ws_m[s * n + p]);
+  float S = 0.f;
+  for (int s = 0; s < nsplit; ++s) S += ws_S[s * n + p] * ex2(ws_m[s * n + p] - M);
+  const float lp = lse_finish(M, S) + add;
+  out[p] = lp;
+  if (fast_needs_exact(ws_u2[p], M, lp)) list[atomicAdd(list_n, 1ull)] = p;
+}
+
+// Exact (centred-form) re-evaluation of the listed points: out[list[k]] = log p(x[list[k]]) for k < *list_n.
+// CTAs beyond the list exit at once, so the launch covers the worst case (every point listed) at no cost when the list
+// is short. Same arithmetic as logpdf_kernel<ISO_SHARED, DP, false>.
+template <int DP>
+__global__ void __launch_bounds__(kThreads, DP <= 8 ? AISB_MIN_CTAS_SMALL : 1)
+    logpdf_subset_kernel(const float* __restrict__ x, int64_t n, PassArgs mix, const int64_t* __restrict__ list,
+                         const unsigned long long* __restrict__ list_n, float* __restrict__ out) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bars[kStages];
+  __shared__ OuterAcc outer;
+  constexpr int E = points_per_thread(DP);
+  const int64_t cnt = static_cast<int64_t>(*list_n) < n ? static_cast<int64_t>(*list_n) : n;
+  const int64_t tile_base = static_cast<int64_t>(blockIdx.x) * (kThreads * E);
+  if (tile_base >= cnt) return;
+  ring_init(bars);
+  float xr[E][DP];
+  int64_t pidx[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int64_t k = tile_base + e * kThreads + threadIdx.x;
+    const int64_t p = list[k < cnt ? k : cnt - 1];
+    pidx[e] = k < cnt ? p : -1;
+    if constexpr (DP >= 4) {
+      const float4* r = reinterpret_cast<const float4*>(x + p * DP);
+#pragma unroll
+      for (int q = 0; q < DP / 4; ++q) {
+        const float4 f = __ldg(r + q);
+        xr[e][4 * q + 0] = f.x;
+        xr[e][4 * q + 1] = f.y;
+        xr[e][4 * q + 2] = f.z;
+        xr[e][4 * q + 3] = f.w;
+      }
+    } else {
+      const float2 f = __ldg(reinterpret_cast<const float2*>(x + p * 2));
+      xr[e][0] = f.x;
+      xr[e][1] = f.y;
+    }
+  }
+  float m[E], S[E];
+  uint32_t it = 0;
+  mixture_pass<AISB_COV_ISO_SHARED, DP, E, false>(mix.rows, nullptr, 0, mix.KP, mix.a_iso, smem, bars, outer, it, xr, m,
+                                                  S);
+#pragma unroll
+  for (int e = 0; e < E; ++e)
+    if (pidx[e] >= 0) out[pidx[e]] = lse_finish(m[e], S[e]) + mix.uniform_offset;
 }
 
 // h_j = ||b_j||^2 / (2 a) per packed component (padding rows included) and, behind the vector, max_{j < K} ||b_j||^2
@@ -324,22 +463,62 @@ static int launch_logpdf_t(const float* x, int64_t n, int D, int vec_ok, const P
 
 
 template <int DP>
-static int launch_screen_t(const float* x, int64_t n, const PassArgs& mix, const float* hs, const Plan& plan, float* out,
+static int launch_screen_t(const float* x, int64_t n, const PassArgs& mix, const float* hs, int nsplit, float* out,
                            const Workspace& ws, unsigned long long* stats, cudaStream_t st) {
-  constexpr size_t smem = pass_smem_bytes(AISB_COV_ISO_SHARED, DP, true);
-  const int64_t grid = plan.ntiles * plan.nsplit;
+  constexpr size_t smem = screen_smem_bytes(DP);
+  constexpr int E = points_per_thread(DP);
+  const int64_t ntiles = (n + kScreenThreads * E - 1) / (kScreenThreads * E);
+  const int64_t grid = ntiles * nsplit;
   const float marg = 21.f + log2f(static_cast<float>(mix.KP));
   if (stats)
-    logpdf_screen_kernel<DP, true><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(
-        x, n, mix, hs, marg, plan.nsplit, plan.ntiles, out, ws.ws_m, ws.ws_S, stats);
+    logpdf_screen_kernel<DP, true><<<static_cast<unsigned>(grid), kScreenThreads, smem, st>>>(
+        x, n, mix, hs, marg, nsplit, ntiles, out, ws.ws_m, ws.ws_S, stats);
   else
-    logpdf_screen_kernel<DP, false><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(
-        x, n, mix, hs, marg, plan.nsplit, plan.ntiles, out, ws.ws_m, ws.ws_S, nullptr);
+    logpdf_screen_kernel<DP, false><<<static_cast<unsigned>(grid), kScreenThreads, smem, st>>>(
+        x, n, mix, hs, marg, nsplit, ntiles, out, ws.ws_m, ws.ws_S, nullptr);
   AISB_LAUNCH_CHECK("logpdf_screen_kernel");
-  if (plan.nsplit > 1) {
-    lse_merge_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ws.ws_m, ws.ws_S, plan.nsplit, n,
+  if (nsplit > 1) {
+    lse_merge_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ws.ws_m, ws.ws_S, nsplit, n,
                                                                              mix.uniform_offset, out);
     AISB_LAUNCH_CHECK("lse_merge_kernel");
+  }
+  return AISB_OK;
+}
+
+
+template <int DP>
+static int launch_fast_t(const float* x, int64_t n, const PassArgs& mix, int nsplit, float* out, const Workspace& ws,
+                         float* ws_u2, int64_t* list, unsigned long long* list_n, unsigned long long* stats,
+                         cudaStream_t st) {
+  constexpr size_t smem = size_t(kStages) * kScreenChunk * DP * sizeof(float);
+  constexpr int E = points_per_thread(DP);
+  const int64_t ntiles = (n + kScreenThreads * E - 1) / (kScreenThreads * E);
+  const int64_t grid = ntiles * nsplit;
+  const float marg = 21.f + log2f(static_cast<float>(mix.KP));
+  const char* dbg_env = getenv("AISB_FAST_DEBUG");  // bit 0: fold every group; bit 1: no recentring; bit 2: no exact pass
+  const int dbg = dbg_env ? atoi(dbg_env) : 0;
+  AISB_CUDA_CHECK(cudaMemsetAsync(list_n, 0, sizeof(unsigned long long), st));
+  if (stats)
+    logpdf_fast_kernel<DP, true><<<static_cast<unsigned>(grid), kScreenThreads, smem, st>>>(
+        x, n, mix, marg, nsplit, ntiles, out, ws.ws_m, ws.ws_S, ws_u2, list, list_n, stats, dbg);
+  else
+    logpdf_fast_kernel<DP, false><<<static_cast<unsigned>(grid), kScreenThreads, smem, st>>>(
+        x, n, mix, marg, nsplit, ntiles, out, ws.ws_m, ws.ws_S, ws_u2, list, list_n, nullptr, dbg);
+  AISB_LAUNCH_CHECK("logpdf_fast_kernel");
+  if (nsplit > 1) {
+    fast_merge_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ws.ws_m, ws.ws_S, ws_u2, nsplit, n,
+                                                                              mix.uniform_offset, out, list, list_n);
+    AISB_LAUNCH_CHECK("fast_merge_kernel");
+  }
+  // exact re-evaluation of the listed points (a no-op launch when the list is empty)
+  constexpr size_t smem_x = pass_smem_bytes(AISB_COV_ISO_SHARED, DP, false);
+  const int64_t grid_x = (n + kThreads * E - 1) / (kThreads * E);
+  if (!(dbg & 4)) {
+    logpdf_subset_kernel<DP><<<static_cast<unsigned>(grid_x), kThreads, smem_x, st>>>(x, n, mix, list, list_n, out);
+    AISB_LAUNCH_CHECK("logpdf_subset_kernel");
+  }
+  if (stats) {
+    AISB_CUDA_CHECK(cudaMemcpyAsync(stats + 2, list_n, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
   }
   return AISB_OK;
 }
@@ -575,21 +754,97 @@ extern "C" int aisb_mixture_logpdf_screened_f32(const float* d_x, int64_t n, con
     set_error("mixture_logpdf_screened: unsupported D=%d", mix->D);
     return AISB_ERR_UNSUPPORTED;
   }
-  // interleaved split: every CTA must get at least one chunk
-  const int64_t nchunks = (plan.KP + chunk_comps(AISB_COV_ISO_SHARED, DP) - 1) / chunk_comps(AISB_COV_ISO_SHARED, DP);
-  if (plan.nsplit > nchunks) plan.nsplit = static_cast<int>(nchunks);
+  // Single-warp CTAs, up to 16 resident per SM: split the component range (interleaved chunks) until the grid has ~8
+  // waves of them, never beyond what the shared workspace contract (aisb_workspace_bytes) provides, and so that every
+  // CTA still sweeps >= 16 chunks.
+  constexpr int E8 = 4;
+  const int64_t ntiles = (n + kScreenThreads * E8 - 1) / (kScreenThreads * E8);
+  const int64_t nchunks = (plan.KP + kScreenChunk - 1) / kScreenChunk;
+  int64_t want = (static_cast<int64_t>(sm_count()) * 16 * 8 + ntiles - 1) / ntiles;
+  if (want > nchunks / 16) want = nchunks / 16;
+  if (want > plan.nsplit) want = plan.nsplit;
+  if (want < 1) want = 1;
+  if (const char* e = getenv("AISB_SCREEN_NSPLIT")) {  // timing experiments
+    const int64_t v = atoll(e);
+    if (v >= 1 && v <= plan.nsplit && v <= nchunks) want = v;
+  }
+  const int nsplit = static_cast<int>(want);
   Workspace ws{};
-  if (plan.nsplit > 1) {
+  if (nsplit > 1) {
     rc = carve_checked(d_workspace, workspace_bytes, n, plan, &ws, "mixture_logpdf_screened");
     if (rc) return rc;
   }
   const PassArgs a = pass_args(mix);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (DP) {
-    case 2: return launch_screen_t<2>(d_x, n, a, d_screen, plan, d_out_logp, ws, d_stats, st);
-    case 4: return launch_screen_t<4>(d_x, n, a, d_screen, plan, d_out_logp, ws, d_stats, st);
-    case 8: return launch_screen_t<8>(d_x, n, a, d_screen, plan, d_out_logp, ws, d_stats, st);
-    case 16: return launch_screen_t<16>(d_x, n, a, d_screen, plan, d_out_logp, ws, d_stats, st);
+    case 2: return launch_screen_t<2>(d_x, n, a, d_screen, nsplit, d_out_logp, ws, d_stats, st);
+    case 4: return launch_screen_t<4>(d_x, n, a, d_screen, nsplit, d_out_logp, ws, d_stats, st);
+    case 8: return launch_screen_t<8>(d_x, n, a, d_screen, nsplit, d_out_logp, ws, d_stats, st);
+    case 16: return launch_screen_t<16>(d_x, n, a, d_screen, nsplit, d_out_logp, ws, d_stats, st);
+    default: break;
+  }
+  return AISB_ERR_UNSUPPORTED;
+}
+
+
+extern "C" size_t aisb_kde_fast_scratch_bytes(int64_t n) {
+  return n < 0 ? 0 : static_cast<size_t>(n) * (sizeof(int64_t) + sizeof(float)) + 256;
+}
+
+extern "C" int aisb_mixture_logpdf_fast_f32(const float* d_x, int64_t n, const aisb_packed_mixture* mix,
+                                            float* d_out_logp, void* d_workspace, size_t workspace_bytes,
+                                            void* d_scratch, size_t scratch_bytes, unsigned long long* d_stats,
+                                            void* stream) {
+  int rc = check_mixture(mix, "mixture_logpdf_fast");
+  if (rc) return rc;
+  if (n == 0) return AISB_OK;
+  if (!d_x || !d_out_logp || n < 0 || !d_scratch || reinterpret_cast<uintptr_t>(d_scratch) % 16 ||
+      scratch_bytes < aisb_kde_fast_scratch_bytes(n)) {
+    set_error("mixture_logpdf_fast: null / misaligned pointer, negative n or scratch smaller than "
+              "aisb_kde_fast_scratch_bytes(n)");
+    return AISB_ERR_INVALID;
+  }
+  const int DP = aisb_padded_dims(mix->D);
+  if (mix->cov_kind != AISB_COV_ISO_SHARED || mix->d_offsets || mix->D != DP || DP < 2 || DP > 16 ||
+      !vec_ok_for(d_x, mix->D)) {
+    set_error("mixture_logpdf_fast: needs an ISO_SHARED mixture without offsets, D in {2, 4, 8, 16} and 16-byte "
+              "aligned points (got cov_kind=%d D=%d)", mix->cov_kind, mix->D);
+    return AISB_ERR_UNSUPPORTED;
+  }
+  Plan plan;
+  if (!make_plan(n, mix->K, mix->D, &plan)) {
+    set_error("mixture_logpdf_fast: unsupported D=%d", mix->D);
+    return AISB_ERR_UNSUPPORTED;
+  }
+  // single-warp CTAs, up to 16 resident per SM: interleaved split of the component range until the grid has ~8 waves,
+  // within the shared workspace contract (aisb_workspace_bytes) and with >= 16 chunks per CTA
+  const int64_t ntiles = (n + kScreenThreads * 4 - 1) / (kScreenThreads * 4);
+  const int64_t nchunks = (plan.KP + kScreenChunk - 1) / kScreenChunk;
+  int64_t want = (static_cast<int64_t>(sm_count()) * 16 * 8 + ntiles - 1) / ntiles;
+  if (want > nchunks / 16) want = nchunks / 16;
+  if (want > plan.nsplit) want = plan.nsplit;
+  if (want < 1) want = 1;
+  if (const char* e = getenv("AISB_SCREEN_NSPLIT")) {  // timing experiments
+    const int64_t v = atoll(e);
+    if (v >= 1 && v <= plan.nsplit && v <= nchunks) want = v;
+  }
+  const int nsplit = static_cast<int>(want);
+  Workspace ws{};
+  if (nsplit > 1) {
+    rc = carve_checked(d_workspace, workspace_bytes, n, plan, &ws, "mixture_logpdf_fast");
+    if (rc) return rc;
+  }
+  char* sc = static_cast<char*>(d_scratch);
+  unsigned long long* list_n = reinterpret_cast<unsigned long long*>(sc);
+  int64_t* list = reinterpret_cast<int64_t*>(sc + 64);
+  float* ws_u2 = reinterpret_cast<float*>(sc + 64 + sizeof(int64_t) * n);
+  const PassArgs a = pass_args(mix);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (DP) {
+    case 2: return launch_fast_t<2>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, d_stats, st);
+    case 4: return launch_fast_t<4>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, d_stats, st);
+    case 8: return launch_fast_t<8>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, d_stats, st);
+    case 16: return launch_fast_t<16>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, d_stats, st);
     default: break;
   }
   return AISB_ERR_UNSUPPORTED;

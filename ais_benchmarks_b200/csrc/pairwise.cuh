@@ -322,13 +322,13 @@ __device__ __forceinline__ void accumulate_chunk2(const float* __restrict__ srow
 // `stride` > 1 visits every stride-th chunk only (chunk c of this CTA starts at k_begin + c * stride * J): an
 // INTERLEAVED split of the component range over CTAs, so that each of them sees a uniform sample of a spatially ordered
 // mixture (its running maximum then approaches the global one as fast as an unsplit sweep's would).
-template <int KIND, int DP, bool HAS_C, typename Fn>
+// J: components per staged chunk (default chunk_comps: ~16 KB of rows; single-warp CTAs use smaller chunks).
+template <int KIND, int DP, bool HAS_C, int J = chunk_comps(KIND, DP), typename Fn>
 __device__ __forceinline__ void stream_components(const float* __restrict__ g_rows, const float* __restrict__ g_offs,
                                                   int64_t k_begin, int64_t k_end, float* smem, uint64_t* bars,
                                                   uint32_t& it, Fn&& fn, int stride = 1) {
   constexpr int ROW = row_floats(KIND, DP);
-  constexpr int J = chunk_comps(KIND, DP);
-  constexpr int STAGE = stage_floats(KIND, DP, HAS_C);
+  constexpr int STAGE = J * ROW + (HAS_C ? J : 0);
   const int64_t step = static_cast<int64_t>(J) * stride;
   const int nchunks = k_end > k_begin ? static_cast<int>((k_end - k_begin + step - 1) / step) : 0;
   const uint32_t it0 = it;
@@ -374,13 +374,15 @@ __device__ __forceinline__ void stream_components(const float* __restrict__ g_ro
 // log-sum-exp rescale rule, into a float64 accumulator that lives in shared memory (one slot per thread and point,
 // touched once per chunk, no registers) and is reset. Cost: two MUFU and a DFMA per point per chunk.
 // ---------------------------------------------------------------------------------------------
-struct OuterAcc {
-  float M[4][kThreads];   // reference exponent of the outer sum (log2 domain)
-  double S[4][kThreads];  // outer sum, relative to M
+template <int T>
+struct OuterAccT {
+  float M[4][T];   // reference exponent of the outer sum (log2 domain)
+  double S[4][T];  // outer sum, relative to M
 };
+using OuterAcc = OuterAccT<kThreads>;
 
-template <int E>
-__device__ __forceinline__ void outer_init(OuterAcc& o) {
+template <int E, class OA>
+__device__ __forceinline__ void outer_init(OA& o) {
   static_assert(E <= 4, "OuterAcc holds at most 4 points per thread");
 #pragma unroll
   for (int e = 0; e < E; ++e) {
@@ -390,8 +392,8 @@ __device__ __forceinline__ void outer_init(OuterAcc& o) {
 }
 
 // merge the inner (m_e, S_e) into the outer accumulator and restart the inner sum (its reference m_e is kept)
-template <int E>
-__device__ __forceinline__ void outer_fold(OuterAcc& o, const float (&m)[E], float (&S)[E]) {
+template <int E, class OA>
+__device__ __forceinline__ void outer_fold(OA& o, const float (&m)[E], float (&S)[E]) {
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     if (S[e] != 0.f) {  // an empty inner sum must not move the outer reference (its own reference is not meaningful yet)
@@ -405,8 +407,8 @@ __device__ __forceinline__ void outer_fold(OuterAcc& o, const float (&m)[E], flo
   }
 }
 
-template <int E>
-__device__ __forceinline__ void outer_finish(const OuterAcc& o, float (&m)[E], float (&S)[E]) {
+template <int E, class OA>
+__device__ __forceinline__ void outer_finish(const OA& o, float (&m)[E], float (&S)[E]) {
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     m[e] = o.M[e][threadIdx.x];
@@ -495,6 +497,12 @@ __device__ __forceinline__ void mixture_pass(const float* __restrict__ g_rows, c
 // stops discriminating), never accuracy.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 min2(float2 a, float2 b) { return make_float2(fminf(a.x, b.x), fminf(a.y, b.y)); }
+// three-input minimum (FMNMX3 on sm_100); NaN inputs are dropped like fminf drops them
+__device__ __forceinline__ float min3f(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 
 template <int DP, int EP, int JJ, bool COUNT>
 __device__ __forceinline__ void accumulate_chunk_screen(const float* __restrict__ srows, const float* __restrict__ shs,
@@ -568,16 +576,17 @@ __device__ __forceinline__ void accumulate_chunk_screen(const float* __restrict_
 // Fold the components {k_begin + c * stride * J .. } (every stride-th chunk from k_begin on, below k_end) into (m, S).
 // g_hs: the screen vector h_j [KP] followed by its trailer (trailer[0] = max_j ||b_j||^2), see aisb_kde_screen_pack_f32.
 // COUNT: nscreened / nrefined count this thread's (point-pair, group) units (identical for all lanes of a warp).
-template <int DP, int E, bool COUNT = false>
+template <int DP, int E, int J, bool COUNT = false, class OA>
 __device__ __forceinline__ void mixture_pass_screen(const float* __restrict__ g_rows, const float* __restrict__ g_hs,
                                                     int64_t KP, int64_t k_begin, int stride, float a_iso, float marg,
-                                                    float* smem, uint64_t* bars, OuterAcc& outer, uint32_t& it,
+                                                    float* smem, uint64_t* bars, OA& outer, uint32_t& it,
                                                     const float (&x)[E][DP], float (&m)[E], float (&S)[E],
                                                     unsigned* nscreened = nullptr, unsigned* nrefined_out = nullptr) {
   constexpr int KIND = AISB_COV_ISO_SHARED;
   constexpr int JJ = comps_per_step(KIND, DP);
-  constexpr int kFoldEvery = chunk_comps(KIND, DP) >= 256 ? 4 : (chunk_comps(KIND, DP) >= 64 ? 16 : 32);
+  constexpr int kFoldEvery = 1024 / J > 0 ? 1024 / J : 1;   // the float32 inner sum spans ~1024 components
   static_assert(E % 2 == 0, "packed path needs an even number of points per thread");
+  static_assert(J % JJ == 0 && J % AISB_COMP_ALIGN == 0, "chunk size");
   constexpr int EP = E / 2;
   int nchunk = 0;
   unsigned nrefined = 0, nunits = 0;
@@ -614,7 +623,7 @@ __device__ __forceinline__ void mixture_pass_screen(const float* __restrict__ g_
 #pragma unroll
     for (int pp = 0; pp < EP; ++pp) S2[pp] = make_float2(0.f, 0.f);
   };
-  stream_components<KIND, DP, true>(
+  stream_components<KIND, DP, true, J>(
       g_rows, g_hs, k_begin, KP, smem, bars, it,
       [&](const float* srows, const float* shs, int cnt, int64_t) {
         accumulate_chunk_screen<DP, EP, JJ, COUNT>(srows, shs, cnt, a_iso, -inv2a, x2, cthr, thr, m2, S2, nrefined);
@@ -627,6 +636,199 @@ __device__ __forceinline__ void mixture_pass_screen(const float* __restrict__ g_
   if constexpr (COUNT) {
     *nscreened = nunits;
     *nrefined_out = nrefined;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast pass for a spatially ordered ISO_SHARED mixture without offsets: RECENTRED EXPANDED FORM, no exact refinement.
+//
+// With both sides shifted by the centroid c of the warp's 32*E points (x' = x - c, b'_j = b_j + a c: distances do not
+// change),   ||a x + b_j||^2 = ||a x'||^2 + 2 a s_ij,   s_ij = h'_j + x'_i . b'_j,   h'_j = ||b'_j||^2 / (2 a).
+// The chain for s costs DP FMAs per pair -- half of the centred form -- and after the shift every magnitude in it is a
+// LOCAL distance in kernel-bandwidth units (warp extent, distance to the components that matter) instead of a distance
+// from the origin, so its float32 rounding error, ~2.4 * 2^-24 (||a x'||^2 + |t_max| + 1) on the log density (measured,
+// scripts/kde_fast_error_model.py), stays far below the 1e-5 bar for warps whose points are close together in
+// bandwidth units. The kernel estimates that error per point from quantities it has anyway and LISTS the points whose
+// estimate exceeds 3e-6 max(1, |log p|); the caller re-evaluates exactly those with the centred kernel
+// (logpdf_subset_kernel). On BASELINE configs[3] that is < 0.1 % of the points.
+//
+// The shift is applied to each staged chunk IN PLACE by the warp itself (each lane rewrites J/32 rows and their h'),
+// ~2 % of the chunk's work. The online log-sum-exp runs on s directly: reference = running MINIMUM of s (the maximum
+// of the exponent -||a x'||^2 - 2 a s), terms ex2(-2a (s - s_min)); a group of JJ components is folded only if, for at
+// least one of the 64 points of a packed register set, some s is below s_min + marg / (2a).
+// ---------------------------------------------------------------------------------------------
+constexpr float kPosBig = 3.0e38f;
+
+template <int DP, int EP, int JJ, bool COUNT>
+__device__ __forceinline__ void accumulate_chunk_fast(const float* __restrict__ srows, const float* __restrict__ sh,
+                                                      int cnt, float n2a, float two_a, float dthr,
+                                                      const float2 (&x2)[EP][DP], float2 (&ms)[EP], float2 (&cr)[EP],
+                                                      float2 (&S2)[EP], float2 (&thr)[EP], unsigned (&nfolded)) {
+#pragma unroll 1
+  for (int j0 = 0; j0 < cnt; j0 += JJ) {
+    float h[JJ];
+    lds_vec<JJ>(sh + j0, h);
+    float2 s[JJ][EP], smin[EP];
+#pragma unroll
+    for (int jj = 0; jj < JJ; ++jj) {
+      float b[DP];
+      lds_vec<DP>(srows + (j0 + jj) * DP, b);
+#pragma unroll
+      for (int pp = 0; pp < EP; ++pp) {
+        float2 acc = bc2(h[jj]);
+#pragma unroll
+        for (int d = 0; d < DP; ++d) acc = __ffma2_rn(x2[pp][d], bc2(b[d]), acc);
+        s[jj][pp] = acc;
+      }
+    }
+    // group minimum with three-input FMNMX (every instruction that is not a packed FMA costs an issue slot the FMA
+    // pipe could have used: profiles/r2_ncu_kde_fast_v1.txt)
+#pragma unroll
+    for (int pp = 0; pp < EP; ++pp) {
+      float g0 = s[0][pp].x, g1 = s[0][pp].y;
+#pragma unroll
+      for (int jj = 1; jj + 1 < JJ; jj += 2) {
+        g0 = min3f(g0, s[jj][pp].x, s[jj + 1][pp].x);
+        g1 = min3f(g1, s[jj][pp].y, s[jj + 1][pp].y);
+      }
+      if constexpr (JJ % 2 == 0) {
+        g0 = fminf(g0, s[JJ - 1][pp].x);
+        g1 = fminf(g1, s[JJ - 1][pp].y);
+      }
+      smin[pp] = make_float2(g0, g1);
+    }
+#pragma unroll
+    for (int pp = 0; pp < EP; ++pp) {
+      // NaN compares false: NaN values are folded and propagate
+      const bool negligible = (smin[pp].x >= thr[pp].x) && (smin[pp].y >= thr[pp].y);
+      if (__all_sync(0xffffffffu, negligible)) continue;
+      if constexpr (COUNT) ++nfolded;
+      const float2 mn = min2(ms[pp], smin[pp]);
+      // The sum is kept relative to the FLOAT c = fl(2a s_min), the very number the term arguments are formed with.
+      // Rescaling by c_new - c_old is exactly 0 while the minimum stands (a factor derived from s_min itself, e.g.
+      // -2a s_min_old + c_new, is the rounding residual of the product instead: 2^(3e-6) on every fold, compounding).
+      const float2 c = make_float2(mn.x * two_a, mn.y * two_a);
+      const float2 dm = __fadd2_rn(c, neg2(cr[pp]));                   // <= 0; -inf on the first fold (cr = +inf)
+      float2 acc = __fmul2_rn(S2[pp], make_float2(ex2(dm.x), ex2(dm.y)));
+#pragma unroll
+      for (int jj = 0; jj < JJ; ++jj) {
+        const float2 a = __ffma2_rn(s[jj][pp], bc2(n2a), c);           // -2a (s - s_min) <= 0
+        acc = __fadd2_rn(acc, make_float2(ex2(a.x), ex2(a.y)));
+      }
+      S2[pp] = acc;
+      ms[pp] = mn;
+      cr[pp] = c;
+      thr[pp] = make_float2(mn.x + dthr, mn.y + dthr);
+    }
+  }
+}
+
+// Sweep every stride-th chunk (J components) from k_begin on. Results: (m, S) in the exponent domain, as mixture_pass,
+// and u2[e] = ||a x'_e||^2 (the caller's error estimate needs it). COUNT: nscreened / nfolded unit counters.
+template <int DP, int E, int J, bool COUNT = false, class OA>
+__device__ __forceinline__ void mixture_pass_fast(const float* __restrict__ g_rows, int64_t KP, int64_t k_begin,
+                                                  int stride, float a_iso, float marg, float* smem, float* sh_h,
+                                                  uint64_t* bars, OA& outer, uint32_t& it, const float (&x)[E][DP],
+                                                  float (&m)[E], float (&S)[E], float (&u2)[E],
+                                                  unsigned* nscreened = nullptr, unsigned* nfolded_out = nullptr,
+                                                  int dbg = 0) {
+  constexpr int KIND = AISB_COV_ISO_SHARED;
+  constexpr int JJ = comps_per_step(KIND, DP);
+  constexpr int kFoldEvery = 1024 / J > 0 ? 1024 / J : 1;   // the float32 inner sum spans ~1024 components
+  static_assert(E % 2 == 0, "packed path needs an even number of points per thread");
+  static_assert(J % JJ == 0 && J % 32 == 0, "chunk size");
+  constexpr int EP = E / 2;
+  const int lane = threadIdx.x & 31;
+  int nchunk = 0;
+  unsigned nfolded = 0, nunits = 0;
+  outer_init<E>(outer);
+  // centroid of the warp's 32*E points, and the shift a*c of the packed rows
+  float ac[DP];
+#pragma unroll
+  for (int d = 0; d < DP; ++d) {
+    float sum = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) sum += x[e][d];
+    sum = warp_sum(sum) * (1.f / (32 * E));
+    if (!(fabsf(sum) < 1.0e30f)) sum = 0.f;     // NaN / inf coordinates: no shift (the result is NaN / -inf anyway)
+    if (dbg & 2) sum = 0.f;
+    ac[d] = sum;
+  }
+  const float two_a = 2.f * a_iso, n2a = -2.f * a_iso, inv2a = 0.5f / a_iso;
+  const float dthr = (dbg & 1) ? INFINITY : marg * inv2a;
+  float2 x2[EP][DP], ms[EP], cr[EP], S2[EP], thr[EP];
+#pragma unroll
+  for (int pp = 0; pp < EP; ++pp) {
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      const float v0 = x[2 * pp][d] - ac[d], v1 = x[2 * pp + 1][d] - ac[d];
+      x2[pp][d] = make_float2(v0, v1);
+      q0 = fmaf(v0, v0, q0);
+      q1 = fmaf(v1, v1, q1);
+    }
+    u2[2 * pp] = q0 * (a_iso * a_iso);
+    u2[2 * pp + 1] = q1 * (a_iso * a_iso);
+    ms[pp] = make_float2(kPosBig, kPosBig);
+    cr[pp] = make_float2(INFINITY, INFINITY);
+    S2[pp] = make_float2(0.f, 0.f);
+    thr[pp] = make_float2(kPosBig, kPosBig);
+  }
+#pragma unroll
+  for (int d = 0; d < DP; ++d) ac[d] *= a_iso;
+  auto fold = [&]() {
+#pragma unroll
+    for (int pp = 0; pp < EP; ++pp) {
+      // exponent-domain reference t_max = -||a x'||^2 - c: a fixed function of c, so every inner sum formed under the
+      // same c meets the outer accumulator with the same reference (before the first fold c = +inf: the reference is
+      // clamped, the inner sum is 0 and outer_fold ignores it)
+      m[2 * pp] = fmaxf(-cr[pp].x - u2[2 * pp], kNegBig);
+      m[2 * pp + 1] = fmaxf(-cr[pp].y - u2[2 * pp + 1], kNegBig);
+      S[2 * pp] = S2[pp].x;
+      S[2 * pp + 1] = S2[pp].y;
+    }
+    outer_fold<E>(outer, m, S);
+#pragma unroll
+    for (int pp = 0; pp < EP; ++pp) S2[pp] = make_float2(0.f, 0.f);
+  };
+  stream_components<KIND, DP, false, J>(
+      g_rows, nullptr, k_begin, KP, smem, bars, it,
+      [&](const float* srows, const float*, int cnt, int64_t) {
+        // shift this chunk: b' = b + a c, h' = ||b'||^2 / (2a); every lane rewrites cnt / 32 rows
+        float* rows = const_cast<float*>(srows);
+#pragma unroll 1
+        for (int j = lane; j < cnt; j += 32) {
+          float b[DP];
+          lds_vec<DP>(rows + j * DP, b);
+          float q = 0.f;
+#pragma unroll
+          for (int d = 0; d < DP; ++d) {
+            b[d] += ac[d];
+            q = fmaf(b[d], b[d], q);
+          }
+          if constexpr (DP % 4 == 0) {
+#pragma unroll
+            for (int v = 0; v < DP / 4; ++v)
+              reinterpret_cast<float4*>(rows + j * DP)[v] = make_float4(b[4 * v], b[4 * v + 1], b[4 * v + 2], b[4 * v + 3]);
+          } else {
+#pragma unroll
+            for (int d = 0; d < DP; ++d) rows[j * DP + d] = b[d];
+          }
+          sh_h[j] = q * inv2a;
+        }
+        __syncwarp();
+        accumulate_chunk_fast<DP, EP, JJ, COUNT>(srows, sh_h, cnt, n2a, two_a, dthr, x2, ms, cr, S2, thr, nfolded);
+        if constexpr (COUNT) nunits += static_cast<unsigned>(cnt / JJ) * EP;
+        if ((++nchunk % kFoldEvery) == 0) fold();
+        // the next bulk copy (async proxy) overwrites rows this warp wrote through the generic proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      },
+      stride);
+  fold();
+  outer_finish<E>(outer, m, S);
+  if constexpr (COUNT) {
+    *nscreened = nunits;
+    *nfolded_out = nfolded;
   }
 }
 
@@ -678,7 +880,7 @@ template <int DP, int E>
 __device__ __forceinline__ void load_points_warp(const float* __restrict__ x, int64_t n, int64_t tile_base,
                                                  float (&xr)[E][DP], int64_t (&pidx)[E]) {
   static_assert(DP >= 4 || DP == 2, "vector loads");
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // single-warp CTAs: warp == 0
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int64_t p = tile_base + warp * (32 * E) + e * 32 + lane;

@@ -168,6 +168,27 @@ int aisb_mixture_logpdf_screened_f32(const float* d_x, int64_t n, const aisb_pac
                                      unsigned long long* d_stats, void* stream);
 
 /*
+ * Fast evaluation of a spatially ordered KDE (same contract as aisb_mixture_logpdf_ordered_f32; replaces the same
+ * reference code, CMixtureModel.py:43-57 reached through sampling_methods/base.py:156-179). Every warp shifts its 128
+ * consecutive points and each staged chunk of components by the warp's centroid and evaluates the pair exponent in
+ * the EXPANDED form ||a x'||^2 + 2 a (h'_j + x' . b'_j) -- half the FMAs of the centred form; after the shift its
+ * float32 error only depends on local distances in bandwidth units. The kernel bounds that error per point,
+ *     eps = 4 * 2^-24 * (||a x'||^2 + |t_max| + 1)      (measured model with a 1.7x margin),
+ * lists the points with eps > 3e-6 * max(1, |log p|) and re-evaluates exactly those with the centred form in a second,
+ * normally empty, launch: results stay within the 1e-5 parity bar whatever the data, only the speed depends on it.
+ * Groups of components that are negligible (2^-(21 + log2 KP) of the running maximum) for all 64 points of a packed
+ * register set are skipped after the screen. Needs: ISO_SHARED without offsets, D in {2, 4, 8, 16}, d_x 16-byte aligned,
+ * points and components in a spatially coherent order (else it is correct but slow).
+ *   d_scratch  aisb_kde_fast_scratch_bytes(n) bytes, 16-byte aligned (list of points to re-evaluate, per-point shifts)
+ *   d_stats    NULL, or 3 zero-initialised uint64: {folded, screened} units (64 points x one group of components) and
+ *              the number of points re-evaluated exactly; selects an instrumented kernel
+ */
+size_t aisb_kde_fast_scratch_bytes(int64_t n);
+int aisb_mixture_logpdf_fast_f32(const float* d_x, int64_t n, const aisb_packed_mixture* mix, float* d_out_logp,
+                                 void* d_workspace, size_t workspace_bytes, void* d_scratch, size_t scratch_bytes,
+                                 unsigned long long* d_stats, void* stream);
+
+/*
  * Deterministic-mixture importance weights in one pass over the samples:
  *   logp_i = log pi(x_i) (target mixture, or read from d_logp_in when target == NULL),
  *   logq_i = log q(x_i)  (proposal mixture),  logw_i = logp_i - logq_i.

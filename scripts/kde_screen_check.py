@@ -32,20 +32,37 @@ def timed(fn):
     return min(ts)
 
 
-o_plain, o_ord, o_scr = (torch.empty(n, device="cuda") for _ in range(3))
-stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+o_plain, o_ord, o_scr, o_fast = (torch.empty(n, device="cuda") for _ in range(4))
+stats = torch.zeros(3, dtype=torch.int64, device="cuda")
+sc = _device._kde_fast_scratch(n)
 f_plain = lambda: check(lib.aisb_mixture_logpdf_f32(_ptr(xs), n, mix.ref(), _ptr(o_plain), _ptr(ws), ws.numel(), stream_ptr()))
 f_ord = lambda: check(lib.aisb_mixture_logpdf_ordered_f32(_ptr(xs), n, mix.ref(), _ptr(o_ord), _ptr(ws), ws.numel(), stream_ptr()))
 f_scr = lambda: check(lib.aisb_mixture_logpdf_screened_f32(_ptr(xs), n, mix.ref(), _ptr(screen), _ptr(o_scr), _ptr(ws), ws.numel(), None, stream_ptr()))
 f_cnt = lambda: check(lib.aisb_mixture_logpdf_screened_f32(_ptr(xs), n, mix.ref(), _ptr(screen), _ptr(o_scr), _ptr(ws), ws.numel(), _ptr(stats), stream_ptr()))
+f_fast = lambda: check(lib.aisb_mixture_logpdf_fast_f32(_ptr(xs), n, mix.ref(), _ptr(o_fast), _ptr(ws), ws.numel(), _ptr(sc), sc.numel(), None, stream_ptr()))
+f_fcnt = lambda: check(lib.aisb_mixture_logpdf_fast_f32(_ptr(xs), n, mix.ref(), _ptr(o_fast), _ptr(ws), ws.numel(), _ptr(sc), sc.numel(), _ptr(stats), stream_ptr()))
 pairs = float(n) * K
-for name, f in (("plain", f_plain), ("ordered (fold skip)", f_ord), ("screened", f_scr)):
+for name, f in (("plain", f_plain), ("ordered (fold skip)", f_ord), ("screened", f_scr), ("fast (recentred)", f_fast)):
     t = timed(f)
     print("%-22s %9.3f ms  %.4e pairs/s" % (name, t, pairs / (t * 1e-3)))
 stats.zero_(); f_cnt(); torch.cuda.synchronize()
 st = stats.cpu().numpy()
 print("screen units refined / screened: %d / %d = %.4f" % (st[0], st[1], st[0] / max(1, st[1])))
+stats.zero_(); f_fcnt(); torch.cuda.synchronize()
+st = stats.cpu().numpy()
+print("fast units folded / screened: %d / %d = %.4f ; points re-evaluated exactly: %d of %d" % (st[0], st[1], st[0] / max(1, st[1]), st[2], n))
 a, b, c = o_plain.double(), o_ord.double(), o_scr.double()
+f = o_fast.double()
+rel = (f - a).abs() / torch.clamp(a.abs(), min=1.0)
+print("max |fast - plain| / max(1,|plain|)     = %.3e  (points above 3e-6: %d, above 1e-5: %d)" % (float(rel.max()), int((rel > 3e-6).sum()), int((rel > 1e-5).sum())))
+a_iso = float(lib.aisb_iso_scale(0.02))
+npad = (n + 127) // 128 * 128
+xp = torch.cat([xs, xs[-1:].expand(npad - n, -1)]).reshape(-1, 128, xs.shape[1]).double()
+cen = xp.mean(1, keepdim=True)
+U = (((xp - cen) * a_iso) ** 2).sum(-1).reshape(-1)[:n]
+worst = torch.argsort(rel, descending=True)[:8]
+for i in worst.tolist():
+    print("   i=%7d lp_plain=%10.5f lp_fast=%10.5f rel=%.2e  U_i=%8.2f U_warp_max=%8.2f" % (i, float(a[i]), float(f[i]), float(rel[i]), float(U[i]), float(U[(i // 128) * 128:(i // 128) * 128 + 128].max())))
 den = torch.clamp(a.abs(), min=1.0)
 print("max |ordered - plain| / max(1,|plain|)  = %.3e" % float(((b - a).abs() / den).max()))
 print("max |screened - plain| / max(1,|plain|) = %.3e" % float(((c - a).abs() / den).max()))
@@ -58,3 +75,5 @@ xs_h = xs[rows].cpu().numpy().astype(np.float64)
 ref = O.iso_mixture_log_prob(xs_h, centres_h.astype(np.float64), 0.02)
 got = o_scr[rows].cpu().numpy().astype(np.float64)
 print("screened vs float64 oracle on %d rows: max rel err %.3e" % (len(rows), float(np.max(np.abs(got - ref) / np.maximum(1, np.abs(ref))))))
+got = o_fast[rows].cpu().numpy().astype(np.float64)
+print("fast     vs float64 oracle on %d rows: max rel err %.3e" % (len(rows), float(np.max(np.abs(got - ref) / np.maximum(1, np.abs(ref))))))

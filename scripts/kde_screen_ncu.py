@@ -1,4 +1,4 @@
-"""Minimal driver for ncu captures of the screen-and-refine KDE kernel: setup + 3 launches on the configs[3] workload at
+"""Minimal driver for ncu captures of the fast (recentred expanded form) KDE kernel: setup + 3 launches on the configs[3] workload at
 `scale` (both sides in Z-order). Usage: kde_screen_ncu.py [scale]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,9 +18,9 @@ if not mix.spatially_ordered:       # below MORTON_MIN_ROWS the library does not
     mix = _device.DeviceMixture.kde(cd, None, K, 0.02, spatial_order=False)
 xs = xd[_device.morton_order(xd)].contiguous()
 ws = _device.workspace_for(n, K, 8)
-screen = _device.kde_screen(mix)
 out = torch.empty(n, device="cuda")
+sc = _device._kde_fast_scratch(n)
 for _ in range(3):
-    check(lib.aisb_mixture_logpdf_screened_f32(_ptr(xs), n, mix.ref(), _ptr(screen), _ptr(out), _ptr(ws), ws.numel(), None, stream_ptr()))
+    check(lib.aisb_mixture_logpdf_fast_f32(_ptr(xs), n, mix.ref(), _ptr(out), _ptr(ws), ws.numel(), _ptr(sc), sc.numel(), None, stream_ptr()))
 torch.cuda.synchronize()
 print("ok", float(out.double().mean()))
