@@ -68,14 +68,29 @@ def to_device_points(x, dims):
     require_cuda()
     if is_tensor(x):
         return x.to(device=device(), dtype=torch.float32).contiguous(), False
-    host = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
-    return host.to(device(), non_blocking=False), True
+    return upload_f32(x), True
+
+
+HOST_CAST_MAX = 1 << 16   # elements up to which a float64 -> float32 cast on the host is cheaper than moving 8-byte values
+
+
+def upload_f32(x):
+    """numpy array -> float32 contiguous CUDA tensor. The reference hands over float64 (README.md:41-43): small arrays
+    are cast on the host; large ones are uploaded as they are and cast by the device (numpy's single-threaded astype
+    runs at ~1.5 GB/s, an order of magnitude below the host link, and would otherwise dominate a 1e6 x 8 evaluation)."""
+    x = np.ascontiguousarray(x)
+    if x.dtype == np.float32 or x.size <= HOST_CAST_MAX or x.dtype.kind != "f":
+        return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(device(), non_blocking=False)
+    return torch.from_numpy(x).to(device(), non_blocking=False).to(torch.float32)
 
 
 def from_device(t, as_numpy):
     """float32 device vector -> numpy float64 (reference dtype) or the tensor itself."""
     if as_numpy:
-        return t.detach().cpu().numpy().astype(np.float64)
+        t = t.detach()
+        if t.numel() > HOST_CAST_MAX:
+            return t.double().cpu().numpy()          # widen on the device, copy 8-byte values
+        return t.cpu().numpy().astype(np.float64)
     return t
 
 
@@ -339,6 +354,13 @@ class TensorCoreOperand:
         self.image = torch.empty(nfl, dtype=torch.float32, device=mix.rows.device)
         check(lib.aisb_tc_pack_f32(mix.ref(), _ptr(self.image), stream_ptr()), "aisb_tc_pack_f32")
         self._screen_error = None
+        self._crowding = None
+
+    def _read_trailer(self):
+        t = self.image[-8:-6].cpu().numpy()           # one small D2H read for both statistics
+        vmax = float(t[0])
+        self._screen_error = vmax * vmax / 512.0
+        self._crowding = float(t[1]) / self.mix.K if t[1] > 0 else 1.0
 
     @property
     def screen_error(self):
@@ -346,9 +368,19 @@ class TensorCoreOperand:
         farthest component: 2^-9 max_j ||a mu_j||^2 (the image trailer holds the norm). The kernel widens each
         point's refine window by twice its own bound, so a large value costs time, never accuracy."""
         if self._screen_error is None:
-            vmax = float(self.image[-8].item())
-            self._screen_error = vmax * vmax / 512.0
+            self._read_trailer()
         return self._screen_error
+
+    @property
+    def crowding(self):
+        """Mean number of components (itself included) inside a component's exact-refinement window (2^-30 of its own
+        term). 1 for well separated proposals; after DM-PMC resampling many proposals are copies of the same few heavy
+        samples and the refinement re-evaluates all of them for every sample: measured at D = 32, 1024 proposals of
+        which 149 are distinct, the tensor-core kernel takes 6.0 ms where the CUDA-core kernel takes 0.79 ms
+        (un-adapted proposals: 0.15 vs 0.79 ms; scripts/tc_clustered_check.py)."""
+        if self._crowding is None:
+            self._read_trailer()
+        return self._crowding
 
 
 def tc_logq(x, operand, hint, out=None):
@@ -367,6 +399,7 @@ def tc_logq(x, operand, hint, out=None):
 
 
 TC_MAX_SCREEN_ERROR = 8.0  # beyond this most pairs would be re-evaluated exactly: the CUDA-core kernel is faster
+TC_MAX_CROWDING = 1.5      # mean components per refinement window beyond which the CUDA-core kernel is faster
 
 
 def tc_eligible(mix):
@@ -376,13 +409,15 @@ def tc_eligible(mix):
 
 
 def tc_operand(mix):
-    """The mixture's tensor-core operand (built once per parameter set), or None when the mixture is not eligible or
-    sits so far from the origin that the TF32 screen would not discriminate (see TensorCoreOperand.screen_error)."""
+    """The mixture's tensor-core operand (built once per parameter set), or None when the mixture is not eligible, sits so
+    far from the origin that the TF32 screen would not discriminate (TensorCoreOperand.screen_error), or its components
+    crowd each other's refinement windows (TensorCoreOperand.crowding: adapted / resampled proposals)."""
     if not tc_eligible(mix):
         return None
     if getattr(mix, "_tc_operand", None) is None:
         mix._tc_operand = TensorCoreOperand(mix)
-    return mix._tc_operand if mix._tc_operand.screen_error <= TC_MAX_SCREEN_ERROR else None
+    op = mix._tc_operand
+    return op if op.screen_error <= TC_MAX_SCREEN_ERROR and op.crowding <= TC_MAX_CROWDING else None
 
 
 def dm_weights(x, target, logp_in, proposals, want_logp=False, want_logq=False, hint=None, out_logw=None,

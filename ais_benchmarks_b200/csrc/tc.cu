@@ -226,7 +226,10 @@ __device__ __forceinline__ void tc_fold32(const uint32_t (&r)[32], float gr, flo
 // B image: per tile of 128 components the exact shared-memory image [K/4 chunks][128 rows][4 floats].
 // Input: the ISO_SHARED packed rows (b = -a mu). Padding components get w = -1e30.
 // ---------------------------------------------------------------------------------------------
-// Trailer (zeroed by the caller): [0] = max_j ||v_j|| (as ordered int bits).
+// Trailer (zeroed by the caller): [0] = max_j ||v_j|| (as ordered int bits); [1] = sum_j #{k : ||v_j - v_k||^2 < kTcRefine}
+// (crowding: how many components, itself included, sit inside a component's exact-refinement window -- the work the
+// refinement does per sample drawn from that component; only computed for K <= kTcCrowdMaxK, else left at 0 = unknown).
+constexpr int64_t kTcCrowdMaxK = 8192;
 __global__ void tc_pack_kernel(const float* __restrict__ rows, int64_t K, int D, int DP, float* __restrict__ image) {
   const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t KT = (K + kTcN - 1) / kTcN * kTcN;
@@ -254,6 +257,18 @@ __global__ void tc_pack_kernel(const float* __restrict__ rows, int64_t K, int D,
   put(DP + 1, wm);
   put(DP + 2, wl);
   atomicMax(trailer, __float_as_int(static_cast<float>(sqrt(-w)) * 1.0001f));  // non-negative floats order as ints
+  if (K <= kTcCrowdMaxK) {
+    int cnt = 0;
+    for (int64_t k = 0; k < K; ++k) {
+      float d2 = 0.f;
+      for (int d = 0; d < D; ++d) {
+        const float dl = rows[j * DP + d] - rows[k * DP + d];
+        d2 = fmaf(dl, dl, d2);
+      }
+      cnt += d2 < kTcRefine ? 1 : 0;
+    }
+    atomicAdd(reinterpret_cast<float*>(trailer) + 1, static_cast<float>(cnt));
+  }
 }
 
 struct TcBars {

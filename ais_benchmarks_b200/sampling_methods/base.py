@@ -60,7 +60,7 @@ class CSamplingMethod(metaclass=ABCMeta):
         self._samples_np = val
         if val.size:
             _device.require_cuda()
-            self._samples_dev = torch.from_numpy(val.reshape(-1, self.ndims)).to(_device.device(), torch.float32)
+            self._samples_dev = _device.upload_f32(val.reshape(-1, self.ndims))
         else:
             self._samples_dev = None
 
@@ -118,7 +118,8 @@ class CSamplingMethod(metaclass=ABCMeta):
     def _out(self, t, exp=False):
         if self.device_outputs:
             return torch.exp(t) if exp else t
-        return _device.exp_from_device(t, True) if exp else t.cpu().numpy().astype(np.float64)
+        # float64 numpy like the reference; large results are widened on the device (numpy's astype is single-threaded)
+        return _device.exp_from_device(t, True) if exp else _device.from_device(t, True)
 
     # -- statistics --------------------------------------------------------------------------------
     def get_acceptance_rate(self):

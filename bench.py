@@ -12,6 +12,12 @@ is measured in the same run and reported under "dm_ais" in the same JSON line.
 A "step" is one full evaluation of the metric on one batch: KDE build (pack) + q log-density (pairwise kernel)
 + target log-density + KLD reduction (+ the 8-double all-gather for N > 1). Evaluation points are sharded over
 the ranks (total work fixed -> "scaling": "strong").
+
+`value`  inputs resident in HBM (float32 tensors), device-timed.
+`e2e`    the same evaluation through the reference-facing classes with HOST numpy float64 arrays, the way
+         CBenchmark.evaluate_method hands them over (CBenchmark.py:529-532): sampler.samples = centres;
+         CKLDivergence().compute_from_samples(target, sampler, x) -- host->device copies of the float64 arrays, their
+         cast, KDE resampling + build, kernels and the read-back of the result all inside the timed region.
 """
 import argparse
 import gc
@@ -187,7 +193,7 @@ def run_cuda(args):
     kernel_ms = []
 
     def kde_step(resident=True):
-        """One metric evaluation. resident=False: inputs start in pinned host memory (e2e)."""
+        """One metric evaluation. resident=False: inputs start in pinned host memory (float32 tensors)."""
         cd = centres_d if resident else centres_pin.to(dev, non_blocking=True)
         xd = x_d if resident else x_pin.to(dev, non_blocking=True)
         kde = CDeviceKDE(cd, None, n_c, c["bw"], D, sup)                 # Z-order of the centres + pack kernel
@@ -204,6 +210,28 @@ def run_cuda(args):
         kld = parallel.global_kld(rec)                                   # 8 doubles D2H (+ all-gather)
         kernel_ms.append((e0, e1))
         return kld
+
+    # -- e2e: the reference-facing call with host numpy float64 buffers --------------------------------------------
+    from ais_benchmarks_b200.sampling_methods.base import CMixtureSamplingMethod
+
+    class _KdeSampler(CMixtureSamplingMethod):
+        """The smallest concrete CMixtureSamplingMethod (the reference's MH / nested / rejection samplers are such
+        classes): everything below is the package's public behaviour -- samples setter, lazy KDE build
+        (_update_model, base.py:162-179: n_samples_kde indices drawn with replacement), log_prob."""
+        def importance_sample(self, target_d, n_samples, timeout):
+            raise NotImplementedError
+
+    centres_np = centres_h.astype(np.float64)                            # what a numpy caller owns: float64, pageable
+    x_np = x_h[start:stop].astype(np.float64)
+    metric_np = CKLDivergence()
+    metric_np.sharded = world > 1
+
+    def kde_step_numpy():
+        np.random.seed(1234)       # the KDE resampling draws its seed from numpy: every rank must build the same KDE
+        q = _KdeSampler({"space_min": sup[0], "space_max": sup[1], "dims": D, "n_samples_kde": n_c})
+        q.bw = c["bw"]
+        q.samples = centres_np                                           # H2D of n_c x 8 float64 + device cast
+        return metric_np.compute_from_samples(target, q, x_np)           # H2D of the points, KDE build, kernels, D2H
 
     for _ in range(args.warmup):
         kld_val = kde_step()
@@ -224,24 +252,55 @@ def run_cuda(args):
     pair_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_ms]))
     kernel_ms.clear()
 
-    # e2e: inputs in pinned host memory every step, result read back; wall clock around the public API
+    # e2e (secondary): float32 inputs in PINNED host memory every step, result read back; wall clock
     for _ in range(max(1, args.warmup // 2)):
         kde_step(resident=False)
     barrier()
     w0 = time.perf_counter()
-    e2e_marks = [w0]
     for _ in range(args.steps):
         kde_step(resident=False)
+    barrier()
+    kde_pinned_ms = max_over_ranks((time.perf_counter() - w0) * 1e3) / args.steps
+    kernel_ms.clear()
+    # e2e (headline): host numpy float64 arrays through the reference-facing classes; wall clock
+    for _ in range(max(1, args.warmup // 2)):
+        kld_np = kde_step_numpy()
+    barrier()
+    w0 = time.perf_counter()
+    e2e_marks = [w0]
+    for _ in range(args.steps):
+        kld_np = kde_step_numpy()
         e2e_marks.append(time.perf_counter())
     barrier()
     kde_e2e_ms = max_over_ranks((time.perf_counter() - w0) * 1e3) / args.steps
     if rank == 0:
-        print("[bench] e2e step walls (ms): %s; pairwise kernel inside e2e (ms): %s" % (
-            ["%.1f" % ((b - a) * 1e3) for a, b in zip(e2e_marks, e2e_marks[1:])],
-            ["%.1f" % a.elapsed_time(b) for a, b in kernel_ms[-args.steps:]]), file=sys.stderr)
+        print("[bench] e2e (numpy float64 through the public classes) step walls (ms): %s; KLD %.6f (resident path %.6f)"
+              % (["%.1f" % ((b - a) * 1e3) for a, b in zip(e2e_marks, e2e_marks[1:])], kld_np, kld_val), file=sys.stderr)
+    # the KDE of the e2e path resamples its centres with replacement (base.py:164), so the two KLDs differ statistically
+    assert abs(kld_np - kld_val) < 0.05 * max(1.0, abs(kld_val)), (kld_np, kld_val)
     clock_info = clocks.stop() if rank == 0 else None
     kernel_ms.clear()
 
+    # how much of the sweep the kernel actually folds / re-evaluates (instrumented launch, untimed)
+    kde_counters = None
+    if _device.kde_mode() == "fast":
+        st_t = torch.zeros(3, dtype=torch.int64, device=dev)
+        kde_c = CDeviceKDE(centres_d, None, n_c, c["bw"], D, sup)
+        xq = parallel.spatial_shard(x_d, rank, world)[0] if spatial else x_d[_device.morton_order(x_d)].contiguous()
+        _device.mixture_logpdf(xq, kde_c.mixture, points_ordered=True, stats=st_t)
+        st_h = st_t.cpu().numpy()
+        kde_counters = {"units_folded": int(st_h[0]), "units_screened": int(st_h[1]),
+                        "folded_fraction": float(st_h[0]) / max(1.0, float(st_h[1])),
+                        "points_reevaluated_exactly": int(st_h[2]), "points": int(xq.shape[0]),
+                        "unit": "64 points x 8 components"}
+        del kde_c, xq
+    kde_traffic, kde_traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_kde_fast_dram.json")) as f:
+            tj = json.load(f)
+        kde_traffic, kde_traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    except (OSError, KeyError, ValueError):
+        pass
     total_pairs = float(n_c) * float(n_e)
     local_pairs = float(n_c) * float(stop - start)
     flop_per_pair = 3 * D + 6            # isotropic pair, direct form
@@ -338,6 +397,67 @@ def run_cuda(args):
     tgt_ms = best_ms(lambda: _device.mixture_logpdf(xs, tmix, scratch))
     del scratch
 
+    # ---- configs[4] through the sampler's own API: CDeterministicMixtureAIS.importance_sample (dm_ais.py:58-86) for one
+    # iteration of N x K draws, returning numpy float64 like the reference; stages timed separately ------
+    from ais_benchmarks_b200.sampling_methods import CDeterministicMixtureAIS
+
+    def timed(fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out_ = fn()
+        b.record()
+        torch.cuda.synchronize()
+        return out_, a.elapsed_time(b)
+
+    del xs_stage
+    np.random.seed(7)
+    _device.seed(77)
+    sampler = CDeterministicMixtureAIS({"space_min": sup2[0], "space_max": sup2[1], "dims": D2, "K": per, "N": N,
+                                        "J": 1000, "sigma": dc["sigma"], "sharded": world > 1, "cuda_graph": False})
+    sampler._set_means_host(pmeans)
+    for it_ in range(2):       # first pass untimed: lazy module loading of the torch ops behind resampling, allocator growth
+        sampler._set_means_host(pmeans)
+        draws, t_sample = timed(lambda: _device.sample_iso(sampler.proposal_means(), per_r, dc["sigma"]))
+        (lw_i, part_i), t_weigh = timed(lambda: sampler.weigh(draws, target2, hint=sampler._own_proposal(per_r)))
+        _, t_adapt = timed(lambda: sampler.resample(draws, lw_i))
+    sampler._pending_records.clear()
+    del draws, lw_i, part_i
+    sampler._set_means_host(pmeans)
+    barrier()
+    w0 = time.perf_counter()
+    xs_np, w_np = sampler.importance_sample(target2, n_total)             # numpy float64 out: [n, 32] and [n]
+    barrier()
+    is_total_ms = max_over_ranks((time.perf_counter() - w0) * 1e3)
+    is_rows = int(xs_np.shape[0])
+    if world == 1:
+        assert abs(float(w_np.sum()) - 1.0) < 1e-4, float(w_np.sum())
+    is_d2h_bytes = int(xs_np.shape[0] * D2 * 4 + w_np.shape[0] * 4)
+    del xs_np, w_np, sampler
+    dm_is = {"metric": "importance_sample(target, %d) one iteration, numpy out" % n_total,
+             "value": n_total / (is_total_ms * 1e-3), "unit": "samples/s", "ms_total": is_total_ms,
+             "stages_ms": {"sampling": t_sample, "weighting": t_weigh, "adaptation": t_adapt,
+                           "d2h_and_float64_conversion": max(0.0, is_total_ms - t_sample - t_weigh - t_adapt)},
+             "d2h_bytes": is_d2h_bytes, "rows_this_rank": is_rows,
+             "note": "stages timed alone with CUDA events on this rank, total by wall clock (max over ranks); the "
+                     "remainder is the device->host copy of the float32 samples / weights and their conversion to the "
+                     "reference's float64 numpy arrays (2.56 GB at N = 1)"}
+
+    # ---- the HBM-streaming kernels of the two steps, alone, against the measured copy bandwidth ----------------------
+    pk_hbm = measured_peaks()[0].get("hbm_gbs")
+    lp_v = torch.randn(n_local, device=dev)
+    lq_v = torch.randn(n_local, device=dev)
+    rec4 = _device.logw_partials(lp_v)
+    stream_kernels = {}
+    for name, fn, nbytes in (
+            ("kld_partials_kernel (2 x 4 B read per point)", lambda: _device.kld_partials(lp_v, lq_v), 8.0 * n_local),
+            ("logw_partials_kernel (4 B read per sample)", lambda: _device.logw_partials(lp_v), 4.0 * n_local),
+            ("normalize_weights_dev_kernel (4 B read + 4 B write)", lambda: _device.normalize_weights_dev(lp_v, rec4, out=lq_v), 8.0 * n_local)):
+        ms_ = best_ms(fn)
+        stream_kernels[name] = {"ms": ms_, "bytes": nbytes, "achieved_gbs": nbytes / (ms_ * 1e-3) / 1e9,
+                                "peak_gbs": pk_hbm, "frac": nbytes / (ms_ * 1e-3) / 1e9 / pk_hbm if pk_hbm else None,
+                                "n": n_local}
+    del lp_v, lq_v
+
     # ---- live FP32-FMA / MUFU.EX2 peaks on this GPU (roofline denominators for the compute-bound kernels), measured
     # after the workloads so that the clocks have ramped up exactly as they had for the timed kernels ---------------
     sink = torch.zeros(4, dtype=torch.float32, device=dev)
@@ -358,10 +478,27 @@ def run_cuda(args):
     ex2_peak = peaks["ex2"]
 
     gc.enable()
+    # ================================ sharded adapt loops (N > 1, untimed check) ==============================
+    # DM-AIS resampling, LAIS chains and the M-PMC moment all-reduce over the ranks of THIS run: replicated parameters
+    # stay identical, ranks draw different samples, weights are normalised over all ranks and agree with an unsharded
+    # evaluation of the same rows (scripts/sharded_samplers_check.py).
+    sharded_report = None
+    if world > 1:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import sharded_samplers_check
+        try:
+            sharded_report = {"ok": True, "lines": sharded_samplers_check.run_checks(rank, world, use_oracle=False)}
+        except AssertionError as e:
+            sharded_report = {"ok": False, "error": str(e)[:500]}
+        flag = torch.tensor([1 if sharded_report["ok"] else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        sharded_report["ok_all_ranks"] = bool(int(flag.item()))
     # ================================ CPU baseline (rank 0, N = 1 only) ======================================
     cpu = None
+    cpu_dm = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline_kde(cores=1, budget_s=12.0)
+        cpu_dm = cpu_baseline_dm()
 
     if rank == 0:
         pk, pk_src = measured_peaks()
@@ -376,24 +513,36 @@ def run_cuda(args):
                              "%.0f MB of points are read once" % (n_c * 30.0 / 8 / 4, n_c * D * 4 / 1e6, n_e * D * 4 / 1e6),
                        "kld": kld_val, "scale": scale},
             "e2e": {"value": total_pairs / (kde_e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(centres_pin.numel() * 4 + x_pin.numel() * 4), "d2h_bytes_per_step": 64,
-                    "ms_per_step": kde_e2e_ms},
+                    "h2d_bytes_per_step": int(centres_np.nbytes + x_np.nbytes), "d2h_bytes_per_step": 64,
+                    "ms_per_step": kde_e2e_ms,
+                    "api": "sampler.samples = centres (numpy float64); CKLDivergence().compute_from_samples(target, "
+                           "sampler, x) with x numpy float64 -- pageable host memory, per rank its shard of x"},
+            "e2e_pinned_f32": {"value": total_pairs / (kde_pinned_ms * 1e-3), "unit": UNIT,
+                               "h2d_bytes_per_step": int(centres_pin.numel() * 4 + x_pin.numel() * 4),
+                               "d2h_bytes_per_step": 64, "ms_per_step": kde_pinned_ms},
             "gpu_launches": 6 * args.steps,
             "clocks": clock_info,
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp32_peak_tflops,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch (ncu --set full capture,
-                         # profiles/r1_ncu_kde_kernel_fullsize_v5.txt); algorithmic bytes: 68 MB
-                         "traffic": 100072192 if (world == 1 and scale == 1.0) else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch of the timed kernel, read
+                         # from the committed ncu --set full capture (profiles/r2_kde_fast_dram.json); algorithmic: 68 MB
+                         "traffic": kde_traffic if (world == 1 and scale == 1.0) else None,
+                         "traffic_source": kde_traffic_src,
                          # kernel_ms brackets kde.log_prob: the Z-order sort of the evaluation points, the pairwise
-                         # kernel (fold-skipping variant, > 99.7 % of the bracket), the split merge and the scatter back
-                         "kernel": "logpdf_kernel<ISO_SHARED, 8, no offsets, ordered>", "kernel_ms": pair_kernel_ms,
+                         # kernel (> 99.5 % of the bracket), the split merge, the exact re-evaluation of the listed points
+                         # and the scatter back
+                         "kernel": "logpdf_fast_kernel<8> (recentred expanded form; + fast_merge_kernel, "
+                                   "logpdf_subset_kernel<8>)" if _device.kde_mode() == "fast" else
+                                   "AISB_KDE_MODE=%s" % _device.kde_mode(),
+                         "kernel_ms": pair_kernel_ms,
+                         "refined": kde_counters,
                          "flop_per_pair": flop_per_pair,
                          "peak_source": "live FFMA micro-benchmark in this run (aisb_peak_fma_f32); nominal 74.5",
                          "mufu": {"achieved_gops": local_pairs / (pair_kernel_ms * 1e-3) / 1e9,
                                   "peak_gops": ex2_peak / 1e9},
                          "hbm_peak_gbs": pk.get("hbm_gbs"), "hbm_peak_source": pk_src},
             "cpu_baseline": cpu,
+            "sharded_samplers": sharded_report,
             "dm_ais": {"metric": "DM-AIS weighted samples/sec", "value": n_total / (dm_ms * 1e-3), "unit": "samples/s",
                        "ms_per_step": dm_ms,
                        "config": {"workload": "BASELINE configs[4]: D=32, 64-mode GMM target, %d samples x %d "
@@ -428,6 +577,9 @@ def run_cuda(args):
                                             "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                                             "frac": float(n_local) * dc["modes"] * (4 * D2 + 6) / (tgt_ms * 1e-3) / 1e12
                                                     / fp32_peak_tflops}}},
+                       "importance_sample": dm_is,
+                       "cpu_baseline": cpu_dm,
+                       "hbm_streaming_kernels": stream_kernels,
                        # target logpdf + tc_logq + logw_combine + block-record merge + normalise (our kernels; the NCCL
                        # all-gather of the records for N > 1 is not counted)
                        "gpu_launches": 5 * args.steps},
@@ -489,6 +641,8 @@ def _port_eval_chunk(x):
 def cpu_kde_once(n_eval, n_centres, cores, seed=0, kind=None):
     """One KDE-KLD metric evaluation on the host: KDE build + q and p log-densities + KLD. -> (seconds, kld, kind)."""
     kind = kind or _reference()
+    if kind == "reference" and _reference() != "reference":      # (imports the reference from oracle/_ref)
+        raise RuntimeError("oracle/_ref is not available: run `python oracle/build_ref.py` where /root/reference exists")
     c = KDE_CFG
     mu, sig, w, sup = random_gmm(seed, c["D"], c["modes"])
     rs = np.random.RandomState(seed + 1)

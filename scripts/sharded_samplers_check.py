@@ -3,10 +3,16 @@
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
       scripts/sharded_samplers_check.py
 
-Checks, on every rank: replicated proposal parameters stay bit-identical across ranks after every call; the
-returned weights are normalised over ALL ranks; NESS agrees on every rank; the weights of this rank's rows match the
-float64 oracle evaluated with the proposal parameters that generated them; the adapted proposals have moved towards
-the target (KLD of the proposal mixture falls). Prints one line per sampler on rank 0 and exits non-zero on failure.
+Checks, on every rank: replicated proposal parameters stay bit-identical across ranks after every call; the ranks draw
+DIFFERENT samples (per-rank Philox streams); the returned weights are normalised over ALL ranks; NESS agrees on every
+rank; the weights of this rank's rows match the float64 oracle evaluated with the proposal parameters that generated
+them; the adapted proposals have moved towards the target (KLD of the proposal mixture falls). Prints one line per
+sampler on rank 0 and exits non-zero on failure.
+
+`run_checks(rank, world, use_oracle=False)` is what `bench.py --gpus N` (N > 1) calls after its timed sections, so the
+driver's scaling runs exercise the sharded adapt loops too; there the reference weights come from an UNSHARDED
+evaluation of the same rows with the library's weight kernel instead of the oracle (bench.py may not lean on oracle/
+outside its CPU-baseline leg).
 """
 import os
 import sys
@@ -21,7 +27,14 @@ from ais_benchmarks_b200 import _device, parallel
 from ais_benchmarks_b200.distributions import CGaussianMixtureModel
 from ais_benchmarks_b200.metrics import CKLDivergence
 from ais_benchmarks_b200.sampling_methods import CDeterministicMixtureAIS, CLayeredAIS, CMixturePMC
-from oracle import ais_oracle as O
+FAILURES = []
+
+
+def ensure(cond, msg):
+    """Record a failed check WITHOUT leaving the collective call sequence (a rank that raised while the others went
+    on to the next all-gather would hang the job); run_checks raises once, at the end, on every rank."""
+    if not cond:
+        FAILURES.append(str(msg))
 
 
 def same_on_all_ranks(t, what):
@@ -30,7 +43,7 @@ def same_on_all_ranks(t, what):
     out = torch.empty(ws * t.numel(), dtype=torch.float64, device="cuda")
     dist.all_gather_into_tensor(out, t)
     out = out.reshape(ws, -1)
-    assert bool((out == out[0:1]).all() or (torch.isnan(out).all())), "%s differs across ranks" % what
+    ensure(bool((out == out[0:1]).all() or (torch.isnan(out).all())), "%s differs across ranks" % what)
 
 
 def global_sum(v):
@@ -39,10 +52,22 @@ def global_sum(v):
     return float(t[0])
 
 
-def main():
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+def differs_across_ranks(t, what):
+    """First rows of every rank's draw: no two ranks may hold the same numbers."""
+    t = t.detach().to("cuda", torch.float64).contiguous().reshape(-1)[:64]
+    ws = dist.get_world_size()
+    out = torch.empty(ws * t.numel(), dtype=torch.float64, device="cuda")
+    dist.all_gather_into_tensor(out, t)
+    out = out.reshape(ws, -1)
+    for a in range(ws):
+        for b in range(a + 1, ws):
+            ensure(not bool((out[a] == out[b]).all()), "%s: ranks %d and %d drew identical samples" % (what, a, b))
+
+
+def run_checks(rank, world, use_oracle=True):
+    """-> list of report lines (identical on every rank). Raises AssertionError on failure."""
+    if use_oracle:
+        from oracle import ais_oracle as O
     D, N = 8, 64
     mu, sig, w, sup = bench.random_gmm(0, D, 16)
     target = CGaussianMixtureModel({"means": mu, "sigmas": sig, "weights": w, "support": sup})
@@ -53,7 +78,7 @@ def main():
 
     def run(cls, extra, K, iters, name):
         np.random.seed(1000 + rank)        # ranks disagree on purpose: rank 0's draw must win
-        _device.seed(77 + rank)
+        _device.seed(77)                   # the SAME seed everywhere: _device folds the rank into its Philox streams
         params = {"space_min": sup[0], "space_max": sup[1], "dims": D, "K": K, "N": N, "J": 1000, "sigma": 0.05,
                   "device_outputs": True, "sharded": True}
         params.update(extra)
@@ -68,32 +93,43 @@ def main():
         kld0 = metric.compute_from_samples(target, s, x_eval)
         x, wn = s.importance_sample(target, per_iter)            # one iteration: weights are pure functions of pm0
         n_loc = x.shape[0]
-        assert abs(global_sum(n_loc) - per_iter) < 0.5, (name, n_loc)
-        assert abs(global_sum(wn.double().sum()) - 1.0) < 1e-4, name
+        ensure(abs(global_sum(n_loc) - per_iter) < 0.5, (name, n_loc))
+        differs_across_ranks(x, name)
+        ensure(abs(global_sum(wn.double().sum()) - 1.0) < 1e-4, name)
         # oracle on a row subset of THIS rank's rows
         rs = np.random.RandomState(rank)
         pick = rs.choice(n_loc, size=min(500, n_loc), replace=False)
         xs = x[pick].double().cpu().numpy()
-        if cls is CMixturePMC:
-            ref_lq = O.gmm_log_prob(xs, pm0[0], pm0[1], pm0[2])
+        if use_oracle:
+            if cls is CMixturePMC:
+                ref_lq = O.gmm_log_prob(xs, pm0[0], pm0[1], pm0[2])
+            else:
+                ref_lq = O.iso_mixture_log_prob(xs, pm0, 0.05)
+            ref_lw = O.gmm_log_prob(xs, mu, sig, w) - ref_lq
         else:
-            ref_lq = O.iso_mixture_log_prob(xs, pm0, 0.05)
-        ref_lw = O.gmm_log_prob(xs, mu, sig, w) - ref_lq
+            # unsharded evaluation of the same rows with the library's weight kernel and the parameters saved above
+            from ais_benchmarks_b200._lib import COV_DIAG, COV_ISO_SHARED
+            if cls is CMixturePMC:
+                qm = _device.DeviceMixture.from_params(pm0[0], pm0[1], pm0[2], COV_DIAG)
+            else:
+                qm = _device.DeviceMixture.from_params(pm0, np.array([0.05]), None, COV_ISO_SHARED)
+            ref_lw = _device.dm_weights(x[pick].contiguous().float(), target.device_mixture(), None, qm)[0]
+            ref_lw = ref_lw.double().cpu().numpy()
         got_lw = np.log(wn[pick].double().cpu().numpy())
         ok = np.isfinite(got_lw) & np.isfinite(ref_lw)
         shift = np.median((got_lw - ref_lw)[ok])
         # the normaliser is global: every rank must see the same shift
         same_on_all_ranks(torch.tensor([round(float(shift), 3)]), name + " global normaliser")
         err = np.max(np.abs(got_lw[ok] - shift - ref_lw[ok]) / np.maximum(1.0, np.abs(ref_lw[ok])))
-        assert err < 1e-4, (name, err)
+        ensure(err < 1e-4, (name, err))
         x, wn = s.importance_sample(target, iters * per_iter)    # more adapt iterations
-        assert abs(global_sum(x.shape[0]) - iters * per_iter) < 0.5
+        ensure(abs(global_sum(x.shape[0]) - iters * per_iter) < 0.5, name + " sample count")
         if cls is CMixturePMC:
             same_on_all_ranks(torch.from_numpy(s._means), name + " adapted means")
             same_on_all_ranks(torch.from_numpy(s._mix_weights), name + " adapted weights")
         else:
             same_on_all_ranks(s.proposal_means(), name + " adapted means")
-            assert abs(global_sum(wn.double().sum()) - 1.0) < 1e-4, name
+            ensure(abs(global_sum(wn.double().sum()) - 1.0) < 1e-4, name)
         ness = s.get_approx_NESS() if cls is not CMixturePMC else float("nan")
         same_on_all_ranks(torch.tensor([ness]), name + " NESS")
         kld1 = metric.compute_from_samples(target, s, x_eval)
@@ -103,10 +139,26 @@ def main():
         return kld0, kld1
 
     k0, k1 = run(CDeterministicMixtureAIS, {}, 101, 8, "DM-AIS")
-    assert k1 < k0, ("DM-AIS did not adapt", k0, k1)
+    ensure(k1 < k0, ("DM-AIS did not adapt", k0, k1))
     k0, k1 = run(CLayeredAIS, {"L": 10, "mh_sigma": 0.05}, 101, 8, "LAIS")
-    assert k1 < k0, ("LAIS did not adapt", k0, k1)
+    ensure(k1 < k0, ("LAIS did not adapt", k0, k1))
     run(CMixturePMC, {}, 50001, 3, "M-PMC")
+    # agree on the verdict: every rank raises if any rank recorded a failure
+    bad = torch.tensor([len(FAILURES)], dtype=torch.int64, device="cuda")
+    dist.all_reduce(bad)
+    if int(bad.item()) > 0:
+        msgs = list(FAILURES)
+        FAILURES.clear()
+        raise AssertionError("sharded sampler checks failed on some rank (%d failures in total); this rank: %s"
+                             % (int(bad.item()), msgs))
+    return lines
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lines = run_checks(rank, world, use_oracle=True)
     if rank == 0:
         print("\n".join(lines))
         print("sharded samplers ok on %d ranks" % world)

@@ -1,5 +1,6 @@
-"""bench.py pieces that need no GPU: the synthetic workload generators, the CPU arm (oracle port of the reference
-algorithm) and the JSON contract of `bench.py --impl reference`."""
+"""bench.py pieces that need no GPU: the synthetic workload generators, the CPU arm (the UNMODIFIED reference from
+oracle/_ref when it has been built, else the oracle port of the same algorithm) and the JSON contract of
+`bench.py --impl reference`."""
 import json
 import os
 import subprocess
@@ -28,8 +29,8 @@ def test_workload_generators_are_seeded_and_shaped():
 
 
 def test_cpu_arm_matches_a_direct_evaluation():
-    dt, kld = bench.cpu_kde_once(64, 300, 1)
-    assert dt > 0 and np.isfinite(kld)
+    dt, kld, kind = bench.cpu_kde_once(64, 300, 1, kind="port")
+    assert dt > 0 and np.isfinite(kld) and kind == "port"
     # same numbers from the oracle's closed forms on the same seeded inputs
     c = bench.KDE_CFG
     mu, sig, w, sup = bench.random_gmm(0, c["D"], c["modes"])
@@ -38,7 +39,30 @@ def test_cpu_arm_matches_a_direct_evaluation():
     x = rs.uniform(sup[0], sup[1], size=(64, c["D"]))
     ref = O.kld_from_log_probs(O.gmm_log_prob(x, mu, sig, w), O.iso_mixture_log_prob(x, centres, c["bw"]))
     assert abs(kld - ref) <= 1e-9 * max(1.0, abs(ref))
-    dt2, kld2 = bench.cpu_kde_once(64, 300, 2)                            # two worker processes: same value
+    dt2, kld2, _ = bench.cpu_kde_once(64, 300, 2, kind="port")            # two worker processes: same value
+    assert abs(kld2 - kld) <= 1e-9 * max(1.0, abs(kld))
+
+
+def test_reference_cpu_arm_runs_the_real_reference():
+    """With oracle/_ref present (oracle/build_ref.py) the CPU arm drives the reference's own classes. Its KDE resamples
+    the centres with replacement (base.py:164, seeded through np.random.seed), so the value is compared with the oracle
+    evaluated on the SAME resampled centres."""
+    from oracle import build_ref
+    if not build_ref.available() and build_ref.build(verbose=False) == 0:
+        import pytest
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    dt, kld, kind = bench.cpu_kde_once(64, 300, 1, kind="reference")
+    assert kind == "reference" and np.isfinite(kld)
+    q = bench._REF_STATE["q"]
+    centres = np.array([m.loc for m in q.model.models])
+    c = bench.KDE_CFG
+    mu, sig, w, sup = bench.random_gmm(0, c["D"], c["modes"])
+    rs = np.random.RandomState(1)
+    bench.gmm_samples(rs, mu, sig, w, 300)
+    x = rs.uniform(sup[0], sup[1], size=(64, c["D"]))
+    ref = O.kld_from_log_probs(O.gmm_log_prob(x, mu, sig, w), O.iso_mixture_log_prob(x, centres, c["bw"]))
+    assert abs(kld - ref) <= 1e-9 * max(1.0, abs(ref))
+    dt2, kld2, _ = bench.cpu_kde_once(64, 300, 2, kind="reference")       # forked workers share the same KDE
     assert abs(kld2 - kld) <= 1e-9 * max(1.0, abs(kld))
 
 
@@ -52,7 +76,12 @@ def test_reference_arm_json_contract():
     assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT
     assert d["higher_is_better"] is True and d["steps"] == 1 and d["warmup"] == 1 and d["value"] > 0
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    from oracle import build_ref
+    assert cb["kind"] == ("reference" if build_ref.available() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    if cb["kind"] == "reference":                                         # DM-AIS as shipped + batched
+        dm = d["dm_ais"]["cpu_baseline"]
+        assert dm["kind"] == "reference" and dm["value"] > 0 and dm["batched"]["value"] > dm["value"]
     assert d["e2e"] == {"value": d["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and "workload" in d["config"]
     # non-zero ranks of a torchrun launch print nothing and exit 0

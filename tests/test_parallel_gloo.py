@@ -140,3 +140,30 @@ def test_world2_gloo_sharded_adaptation(tmp_path):
     assert abs((deg[:, 0] == 1).mean() - 600 / 1100) < 0.06
     assert np.array_equal(r[0]["summed"], np.arange(6).reshape(2, 3) * 3.0)
     assert np.array_equal(r[0]["gathered"], np.array([[1, 1]] * 3 + [[2, 2]], dtype=np.float32))
+
+
+def _seed_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from ais_benchmarks_b200 import _device
+    _device.seed(1234)                              # seeded BEFORE the process group exists: rank still unknown (0)
+    k_before = _device._key()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    k_after = _device._key()                        # the rank is folded in as soon as it is known
+    _device.seed(1234)
+    k_reseed = _device._key()
+    off0 = _device._next_offset(40)
+    off1 = _device._next_offset(40)
+    np.save(os.path.join(out_dir, "s%d.npy" % rank), np.array([k_before, k_after, k_reseed, off0, off1], dtype=np.uint64))
+    dist.destroy_process_group()
+
+
+def test_world2_per_rank_philox_streams(tmp_path):
+    """Sharded samplers draw each rank's share with the same (seed, offset) bookkeeping: the Philox KEY must differ by
+    rank or every rank would draw bit-identical samples. Rank 0 keeps the user's seed as its key."""
+    port = 29700 + os.getpid() % 200
+    mp.spawn(_seed_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (np.load(os.path.join(str(tmp_path), "s%d.npy" % r)) for r in (0, 1))
+    assert r0[0] == 1234 and r1[0] == 1234          # before init_process_group nobody knows its rank
+    assert r0[1] == 1234 and r1[1] != 1234 and r1[1] == r1[2]
+    assert r0[3] == r1[3] == 0 and r0[4] == r1[4] == 11   # the offsets advance identically: only the key separates ranks
