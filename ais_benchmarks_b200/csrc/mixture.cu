@@ -209,28 +209,36 @@ __global__ void fast_merge_kernel(const float* __restrict__ ws_m, const float* _
   if (fast_needs_exact(ws_u2[p], M, lp)) list[atomicAdd(list_n, 1ull)] = p;
 }
 
-// Exact (centred-form) re-evaluation of the listed points: out[list[k]] = log p(x[list[k]]) for k < *list_n.
-// CTAs beyond the list exit at once, so the launch covers the worst case (every point listed) at no cost when the list
-// is short. Same arithmetic as logpdf_kernel<ISO_SHARED, DP, false>.
+// Exact (centred-form) re-evaluation of the listed points: out[list[k]] = log p(x[list[k]]) for k_begin <= k < *list_n
+// (at most k_count entries from k_begin on). Same arithmetic as logpdf_kernel<ISO_SHARED, DP, false>. The list is
+// normally a few thousand points long, far too few point tiles to fill the machine, so the component range is split
+// nsplit ways (grid.x = tiles * nsplit): partial (m, S) go to ws[split * k_count + (k - k_begin)] and
+// subset_merge_kernel finishes. CTAs beyond the end of the list exit at once, so the launch can cover the worst case
+// at no cost when the list is short. nsplit == 1 writes the result directly (used for the entries beyond the split
+// path's capacity when almost everything is listed).
 template <int DP>
 __global__ void __launch_bounds__(kThreads, DP <= 8 ? AISB_MIN_CTAS_SMALL : 1)
     logpdf_subset_kernel(const float* __restrict__ x, int64_t n, PassArgs mix, const int64_t* __restrict__ list,
-                         const unsigned long long* __restrict__ list_n, float* __restrict__ out) {
+                         const unsigned long long* __restrict__ list_n, int64_t k_begin, int64_t k_count, int nsplit,
+                         int64_t comps_per_split, int64_t ntiles, float* __restrict__ ws_m, float* __restrict__ ws_S,
+                         float* __restrict__ out) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[kStages];
   __shared__ OuterAcc outer;
   constexpr int E = points_per_thread(DP);
-  const int64_t cnt = static_cast<int64_t>(*list_n) < n ? static_cast<int64_t>(*list_n) : n;
-  const int64_t tile_base = static_cast<int64_t>(blockIdx.x) * (kThreads * E);
+  int64_t cnt = static_cast<int64_t>(*list_n) < n ? static_cast<int64_t>(*list_n) : n;
+  if (cnt > k_begin + k_count) cnt = k_begin + k_count;
+  const int64_t tile = blockIdx.x % ntiles, split = blockIdx.x / ntiles;
+  const int64_t tile_base = k_begin + tile * (kThreads * E);
   if (tile_base >= cnt) return;
   ring_init(bars);
   float xr[E][DP];
-  int64_t pidx[E];
+  int64_t kidx[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const int64_t k = tile_base + e * kThreads + threadIdx.x;
     const int64_t p = list[k < cnt ? k : cnt - 1];
-    pidx[e] = k < cnt ? p : -1;
+    kidx[e] = k < cnt ? k : -1;
     if constexpr (DP >= 4) {
       const float4* r = reinterpret_cast<const float4*>(x + p * DP);
 #pragma unroll
@@ -249,12 +257,38 @@ __global__ void __launch_bounds__(kThreads, DP <= 8 ? AISB_MIN_CTAS_SMALL : 1)
   }
   float m[E], S[E];
   uint32_t it = 0;
-  mixture_pass<AISB_COV_ISO_SHARED, DP, E, false>(mix.rows, nullptr, 0, mix.KP, mix.a_iso, smem, bars, outer, it, xr, m,
-                                                  S);
+  const int64_t c_begin = split * comps_per_split;
+  const int64_t c_end = c_begin + comps_per_split < mix.KP ? c_begin + comps_per_split : mix.KP;
+  mixture_pass<AISB_COV_ISO_SHARED, DP, E, false>(mix.rows, nullptr, c_begin, c_end, mix.a_iso, smem, bars, outer, it, xr,
+                                                  m, S);
 #pragma unroll
-  for (int e = 0; e < E; ++e)
-    if (pidx[e] >= 0) out[pidx[e]] = lse_finish(m[e], S[e]) + mix.uniform_offset;
+  for (int e = 0; e < E; ++e) {
+    if (kidx[e] < 0) continue;
+    if (nsplit == 1) {
+      out[list[kidx[e]]] = lse_finish(m[e], S[e]) + mix.uniform_offset;
+    } else {
+      ws_m[split * k_count + (kidx[e] - k_begin)] = m[e];
+      ws_S[split * k_count + (kidx[e] - k_begin)] = S[e];
+    }
+  }
 }
+
+__global__ void subset_merge_kernel(const float* __restrict__ ws_m, const float* __restrict__ ws_S, int nsplit,
+                                    int64_t k_count, int64_t n, const int64_t* __restrict__ list,
+                                    const unsigned long long* __restrict__ list_n, float add, float* __restrict__ out) {
+  const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  int64_t cnt = static_cast<int64_t>(*list_n) < n ? static_cast<int64_t>(*list_n) : n;
+  if (cnt > k_count) cnt = k_count;
+  if (k >= cnt) return;
+  float M = kNegBig;
+  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, ws_m[s * k_count + k]);
+  float S = 0.f;
+  for (int s = 0; s < nsplit; ++s) S += ws_S[s * k_count + k] * ex2(ws_m[s * k_count + k] - M);
+  out[list[k]] = lse_finish(M, S) + add;
+}
+
+constexpr int64_t kSubsetCap = 1 << 16;   // list entries re-evaluated with the component range split kSubsetSplit ways
+constexpr int kSubsetSplit = 64;
 
 // h_j = ||b_j||^2 / (2 a) per packed component (padding rows included) and, behind the vector, max_{j < K} ||b_j||^2
 __global__ void kde_screen_pack_kernel(const float* __restrict__ rows, int64_t K, int64_t KP, int DP, float inv2a,
@@ -488,8 +522,8 @@ static int launch_screen_t(const float* x, int64_t n, const PassArgs& mix, const
 
 template <int DP>
 static int launch_fast_t(const float* x, int64_t n, const PassArgs& mix, int nsplit, float* out, const Workspace& ws,
-                         float* ws_u2, int64_t* list, unsigned long long* list_n, unsigned long long* stats,
-                         cudaStream_t st) {
+                         float* ws_u2, int64_t* list, unsigned long long* list_n, float* sub_m, float* sub_S,
+                         unsigned long long* stats, cudaStream_t st) {
   constexpr size_t smem = size_t(kStages) * kScreenChunk * DP * sizeof(float);
   constexpr int E = points_per_thread(DP);
   const int64_t ntiles = (n + kScreenThreads * E - 1) / (kScreenThreads * E);
@@ -510,12 +544,34 @@ static int launch_fast_t(const float* x, int64_t n, const PassArgs& mix, int nsp
                                                                               mix.uniform_offset, out, list, list_n);
     AISB_LAUNCH_CHECK("fast_merge_kernel");
   }
-  // exact re-evaluation of the listed points (a no-op launch when the list is empty)
-  constexpr size_t smem_x = pass_smem_bytes(AISB_COV_ISO_SHARED, DP, false);
-  const int64_t grid_x = (n + kThreads * E - 1) / (kThreads * E);
+  // exact re-evaluation of the listed points (no-op launches when the list is empty): the first kSubsetCap entries with
+  // the component range split so that a short list still fills the machine, the rest (only when almost everything is
+  // listed) with one CTA per point tile
   if (!(dbg & 4)) {
-    logpdf_subset_kernel<DP><<<static_cast<unsigned>(grid_x), kThreads, smem_x, st>>>(x, n, mix, list, list_n, out);
+    constexpr size_t smem_x = pass_smem_bytes(AISB_COV_ISO_SHARED, DP, false);
+    const int64_t tile_pts = kThreads * E;
+    const int64_t cap = n < kSubsetCap ? n : kSubsetCap;
+    int64_t nsp = mix.KP / 2048;
+    nsp = nsp < 1 ? 1 : (nsp > kSubsetSplit ? kSubsetSplit : nsp);
+    const int64_t units = mix.KP / AISB_COMP_ALIGN;
+    const int64_t cps = (units + nsp - 1) / nsp * AISB_COMP_ALIGN;
+    nsp = (mix.KP + cps - 1) / cps;
+    const int64_t tiles_a = (cap + tile_pts - 1) / tile_pts;
+    logpdf_subset_kernel<DP><<<static_cast<unsigned>(tiles_a * nsp), kThreads, smem_x, st>>>(
+        x, n, mix, list, list_n, 0, cap, static_cast<int>(nsp), cps, tiles_a, sub_m, sub_S, out);
     AISB_LAUNCH_CHECK("logpdf_subset_kernel");
+    if (nsp > 1) {
+      subset_merge_kernel<<<static_cast<unsigned>((cap + 255) / 256), 256, 0, st>>>(sub_m, sub_S, static_cast<int>(nsp),
+                                                                                  cap, n, list, list_n,
+                                                                                  mix.uniform_offset, out);
+      AISB_LAUNCH_CHECK("subset_merge_kernel");
+    }
+    if (n > cap) {
+      const int64_t tiles_b = (n - cap + tile_pts - 1) / tile_pts;
+      logpdf_subset_kernel<DP><<<static_cast<unsigned>(tiles_b), kThreads, smem_x, st>>>(
+          x, n, mix, list, list_n, cap, n - cap, 1, mix.KP, tiles_b, nullptr, nullptr, out);
+      AISB_LAUNCH_CHECK("logpdf_subset_kernel(overflow)");
+    }
   }
   if (stats) {
     AISB_CUDA_CHECK(cudaMemcpyAsync(stats + 2, list_n, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
@@ -788,7 +844,9 @@ extern "C" int aisb_mixture_logpdf_screened_f32(const float* d_x, int64_t n, con
 
 
 extern "C" size_t aisb_kde_fast_scratch_bytes(int64_t n) {
-  return n < 0 ? 0 : static_cast<size_t>(n) * (sizeof(int64_t) + sizeof(float)) + 256;
+  if (n < 0) return 0;
+  const size_t cap = static_cast<size_t>(n < kSubsetCap ? n : kSubsetCap);
+  return static_cast<size_t>(n) * (sizeof(int64_t) + sizeof(float)) + 2 * sizeof(float) * kSubsetSplit * cap + 512;
 }
 
 extern "C" int aisb_mixture_logpdf_fast_f32(const float* d_x, int64_t n, const aisb_packed_mixture* mix,
@@ -838,13 +896,17 @@ extern "C" int aisb_mixture_logpdf_fast_f32(const float* d_x, int64_t n, const a
   unsigned long long* list_n = reinterpret_cast<unsigned long long*>(sc);
   int64_t* list = reinterpret_cast<int64_t*>(sc + 64);
   float* ws_u2 = reinterpret_cast<float*>(sc + 64 + sizeof(int64_t) * n);
+  const size_t cap = static_cast<size_t>(n < kSubsetCap ? n : kSubsetCap);
+  float* sub_m = reinterpret_cast<float*>(sc + 64 + (sizeof(int64_t) + sizeof(float)) * n + 64);
+  sub_m = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sub_m) + 15) / 16 * 16);
+  float* sub_S = sub_m + kSubsetSplit * cap;
   const PassArgs a = pass_args(mix);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (DP) {
-    case 2: return launch_fast_t<2>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, d_stats, st);
-    case 4: return launch_fast_t<4>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, d_stats, st);
-    case 8: return launch_fast_t<8>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, d_stats, st);
-    case 16: return launch_fast_t<16>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, d_stats, st);
+    case 2: return launch_fast_t<2>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, sub_m, sub_S, d_stats, st);
+    case 4: return launch_fast_t<4>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, sub_m, sub_S, d_stats, st);
+    case 8: return launch_fast_t<8>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, sub_m, sub_S, d_stats, st);
+    case 16: return launch_fast_t<16>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, sub_m, sub_S, d_stats, st);
     default: break;
   }
   return AISB_ERR_UNSUPPORTED;

@@ -682,7 +682,7 @@ __device__ __forceinline__ void accumulate_chunk_fast(const float* __restrict__ 
       }
     }
     // group minimum with three-input FMNMX (every instruction that is not a packed FMA costs an issue slot the FMA
-    // pipe could have used: profiles/r2_ncu_kde_fast_v1.txt)
+    // pipe could have used: profiles/r2_ncu_kde_fast_fullsize.txt)
 #pragma unroll
     for (int pp = 0; pp < EP; ++pp) {
       float g0 = s[0][pp].x, g1 = s[0][pp].y;
