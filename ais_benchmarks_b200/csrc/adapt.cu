@@ -5,6 +5,17 @@
 
 namespace aisb {
 
+// log2 of the weight normaliser sum_i w_i: a host value, or derived in the kernel from a weight record {M, S1, ..} that
+// lives in device memory (M + log S1), so that an adapt iteration needs no host round trip between the weight kernel
+// and the moment kernel
+struct LogNorm {
+  float l2n;
+  const double* rec;
+  __device__ __forceinline__ float get() const {
+    return rec ? static_cast<float>((rec[0] + log(rec[1])) * 1.4426950408889634) : l2n;
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // M-PMC moments (reference sampling_methods/m_pmc.py:57-61,102-105)
 //   a_{d,i} = w~_i rho_{d,i} = 2^( t_d(x_i) - log2 q(x_i) + log2 w~_i ),  t_d = c_d - ||A_d x_i + b_d||^2
@@ -17,7 +28,7 @@ template <int KIND, int DP>
 __global__ void __launch_bounds__(kThreads)
     mpmc_moments_kernel(const float* __restrict__ x, int64_t n, int D, int vec_ok, const float* __restrict__ rows,
                         const float* __restrict__ offs, int64_t KP, int64_t K, float a_iso,
-                        const float* __restrict__ logq, const float* __restrict__ logw, float log2_norm,
+                        const float* __restrict__ logq, const float* __restrict__ logw, LogNorm log2_norm,
                         double* __restrict__ out) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[kStages];
@@ -36,7 +47,7 @@ __global__ void __launch_bounds__(kThreads)
   for (int e = 0; e < E; ++e) {
     if (pidx[e] < n) {
       const float lw = __ldg(logw + pidx[e]), lq = __ldg(logq + pidx[e]);
-      shift[e] = (lw - lq) * 1.4426950408889634f - log2_norm;
+      shift[e] = (lw - lq) * 1.4426950408889634f - log2_norm.get();
       if (!(shift[e] == shift[e]) || shift[e] == INFINITY) shift[e] = -INFINITY;
     } else {
       shift[e] = -INFINITY;
@@ -103,7 +114,7 @@ template <int KIND, int DP, bool SECOND>
 __global__ void __launch_bounds__(kCsThreads)
     mpmc_moments_cs_kernel(const float* __restrict__ x, int64_t n, int D, int vec_ok, const float* __restrict__ rows,
                            const float* __restrict__ offs, int64_t K, float a_iso, const float* __restrict__ logq,
-                           const float* __restrict__ logw, float log2_norm, double* __restrict__ out) {
+                           const float* __restrict__ logw, LogNorm log2_norm, double* __restrict__ out) {
   constexpr int ROW = row_floats(KIND, DP);
   constexpr int TRI2 = SECOND ? DP * (DP + 1) / 2 : 1;
   constexpr int XS = DP >= 4 ? DP : 4;                      // padded point row in shared memory (float4 reads)
@@ -156,7 +167,7 @@ __global__ void __launch_bounds__(kCsThreads)
             if (d < D) xv[d] = __ldg(x + p * D + d);
         }
         const float lw = __ldg(logw + p), lq = __ldg(logq + p);
-        sh = (lw - lq) * 1.4426950408889634f - log2_norm;
+        sh = (lw - lq) * 1.4426950408889634f - log2_norm.get();
         if (!(sh == sh) || sh == INFINITY) sh = -INFINITY;
       }
 #pragma unroll
@@ -254,7 +265,7 @@ __global__ void __launch_bounds__(kCsThreads)
 
 template <int KIND, int DP, bool SECOND = false>
 static int launch_mpmc_cs_t(const float* x, int64_t n, int D, int vec_ok, const aisb_packed_mixture* mix,
-                            const float* logq, const float* logw, float log2_norm, double* out, cudaStream_t st) {
+                            const float* logq, const float* logw, LogNorm log2_norm, double* out, cudaStream_t st) {
   const int64_t tiles = (n + kCsSub * kCsSubTiles - 1) / (kCsSub * kCsSubTiles);
   const dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>((mix->K + kCsThreads - 1) / kCsThreads));
   mpmc_moments_cs_kernel<KIND, DP, SECOND><<<grid, kCsThreads, 0, st>>>(
@@ -266,7 +277,7 @@ static int launch_mpmc_cs_t(const float* x, int64_t n, int D, int vec_ok, const 
 // second-order variant: D <= 8 (1 + D + D (D + 1) / 2 <= 45 accumulators per thread)
 template <int KIND>
 static int launch_mpmc2_dp(int DP, const float* x, int64_t n, int D, int vec_ok, const aisb_packed_mixture* mix,
-                           const float* logq, const float* logw, float log2_norm, double* out, cudaStream_t st) {
+                           const float* logq, const float* logw, LogNorm log2_norm, double* out, cudaStream_t st) {
   switch (DP) {
     case 1: return launch_mpmc_cs_t<KIND, 1, true>(x, n, D, vec_ok, mix, logq, logw, log2_norm, out, st);
     case 2: return launch_mpmc_cs_t<KIND, 2, true>(x, n, D, vec_ok, mix, logq, logw, log2_norm, out, st);
@@ -284,7 +295,7 @@ __host__ __device__ constexpr bool mpmc_cs_ok(int kind, int DP) {
 
 template <int KIND, int DP>
 static int launch_mpmc_t(const float* x, int64_t n, int D, int vec_ok, const aisb_packed_mixture* mix,
-                         const float* logq, const float* logw, float log2_norm, double* out, cudaStream_t st) {
+                         const float* logq, const float* logw, LogNorm log2_norm, double* out, cudaStream_t st) {
   if constexpr (mpmc_cs_ok(KIND, DP)) {
     static const bool ps = [] {  // AISB_MPMC_POINT_STATIONARY=1 keeps the point-stationary kernel (timing experiments)
       const char* e = getenv("AISB_MPMC_POINT_STATIONARY");
@@ -306,7 +317,7 @@ static int launch_mpmc_t(const float* x, int64_t n, int D, int vec_ok, const ais
 
 template <int KIND>
 static int launch_mpmc_dp(int DP, const float* x, int64_t n, int D, int vec_ok, const aisb_packed_mixture* mix,
-                          const float* logq, const float* logw, float log2_norm, double* out, cudaStream_t st) {
+                          const float* logq, const float* logw, LogNorm log2_norm, double* out, cudaStream_t st) {
   switch (DP) {
     case 1: return launch_mpmc_t<KIND, 1>(x, n, D, vec_ok, mix, logq, logw, log2_norm, out, st);
     case 2: return launch_mpmc_t<KIND, 2>(x, n, D, vec_ok, mix, logq, logw, log2_norm, out, st);
@@ -433,9 +444,29 @@ static int check_mix_basic(const aisb_packed_mixture* mix, const char* who) {
   return AISB_OK;
 }
 
+static int mpmc_moments_impl(const float* d_x, int64_t n, const aisb_packed_mixture* proposals, const float* d_logq,
+                             const float* d_logw, double log_norm, const double* d_record, double* d_out,
+                             void* stream);
+
 extern "C" int aisb_mpmc_moments_f32(const float* d_x, int64_t n, const aisb_packed_mixture* proposals,
                                      const float* d_logq, const float* d_logw, double log_norm, double* d_out,
                                      void* stream) {
+  return mpmc_moments_impl(d_x, n, proposals, d_logq, d_logw, log_norm, nullptr, d_out, stream);
+}
+
+extern "C" int aisb_mpmc_moments_dev_f32(const float* d_x, int64_t n, const aisb_packed_mixture* proposals,
+                                         const float* d_logq, const float* d_logw, const double* d_record,
+                                         double* d_out, void* stream) {
+  if (!d_record) {
+    set_error("mpmc_moments_dev: null weight record");
+    return AISB_ERR_INVALID;
+  }
+  return mpmc_moments_impl(d_x, n, proposals, d_logq, d_logw, 0.0, d_record, d_out, stream);
+}
+
+static int mpmc_moments_impl(const float* d_x, int64_t n, const aisb_packed_mixture* proposals, const float* d_logq,
+                             const float* d_logw, double log_norm, const double* d_record, double* d_out,
+                             void* stream) {
   int rc = check_mix_basic(proposals, "mpmc_moments");
   if (rc) return rc;
   if (!proposals->d_offsets) {
@@ -451,7 +482,7 @@ extern "C" int aisb_mpmc_moments_f32(const float* d_x, int64_t n, const aisb_pac
   int vec_ok = 0;
   if (D == DP && DP >= 4) vec_ok = reinterpret_cast<uintptr_t>(d_x) % 16 == 0;
   if (D == DP && DP == 2) vec_ok = reinterpret_cast<uintptr_t>(d_x) % 8 == 0;
-  const float l2n = static_cast<float>(log_norm * kLog2e);
+  const LogNorm l2n{static_cast<float>(log_norm * kLog2e), d_record};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (proposals->cov_kind) {
     case AISB_COV_ISO_SHARED: return launch_mpmc_dp<AISB_COV_ISO_SHARED>(DP, d_x, n, D, vec_ok, proposals, d_logq, d_logw, l2n, d_out, st);
@@ -480,7 +511,7 @@ extern "C" int aisb_mpmc_moments2_f32(const float* d_x, int64_t n, const aisb_pa
   const int D = proposals->D, DP = aisb_padded_dims(D);
   int vec_ok = 0;
   if (D == DP && DP >= 4) vec_ok = reinterpret_cast<uintptr_t>(d_x) % 16 == 0;
-  const float l2n = static_cast<float>(log_norm * kLog2e);
+  const LogNorm l2n{static_cast<float>(log_norm * kLog2e), nullptr};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (proposals->cov_kind) {
     case AISB_COV_ISO_SHARED: return launch_mpmc2_dp<AISB_COV_ISO_SHARED>(DP, d_x, n, D, vec_ok, proposals, d_logq, d_logw, l2n, d_out, st);

@@ -117,7 +117,7 @@ def test_tensor_core_path_on_clustered_proposals(D, modes, capsys):
     pm0 = torch.from_numpy(np.random.RandomState(1).uniform(sup[0], sup[1], size=(N, D))).cuda().float().contiguous()
     q0 = _device.DeviceMixture.kde(pm0, None, N, 0.05)
     x0 = _device.sample_iso(pm0, per, 0.05)
-    assert _device.tc_operand(q0) is not None and _device.tc_operand(q0).crowding < 1.2
+    assert _device.tc_operand(q0) is not None and _device.tc_operand(q0).crowding < _device.TC_MAX_CROWDING
     t_tc0 = _timed(lambda: _device.tc_logq(x0, _device.tc_operand(q0), hint, out))
     with capsys.disabled():
         print("\n[clustered proposals D=%d] %d distinct means of %d; tc_logq %.3f ms (uniform proposals: %.3f ms), "
