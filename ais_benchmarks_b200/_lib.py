@@ -68,6 +68,9 @@ PROTOTYPES = {
     "aisb_weighted_mean_f32": (C.c_int, [_vp, _i64, _i32, _vp, _dbl, _vp, _vp]),
     "aisb_mpmc_moments_f32": (C.c_int, [_vp, _i64, _pm, _vp, _vp, _dbl, _vp, _vp]),
     "aisb_mpmc_moments2_f32": (C.c_int, [_vp, _i64, _pm, _vp, _vp, _dbl, _vp, _vp]),
+    "aisb_mpmc_moments_dev_f32": (C.c_int, [_vp, _i64, _pm, _vp, _vp, _vp, _vp, _vp]),
+    "aisb_mpmc_update_f64": (C.c_int, [_vp, _vp, _dbl, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       _vp, _vp]),
     "aisb_raw_moments_f32": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "aisb_lais_mh_f32": (C.c_int, [_vp, _i64, _pm, _vp, _vp, _i32, _vp, _vp, _vp]),
     "aisb_box_mixture_logpdf_f32": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),

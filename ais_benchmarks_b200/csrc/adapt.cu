@@ -331,6 +331,199 @@ static int launch_mpmc_dp(int DP, const float* x, int64_t n, int D, int vec_ok, 
   return AISB_ERR_UNSUPPORTED;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// M-PMC parameter update on the device: alpha / mu / Sigma of m_pmc.py:53-78 from the sufficient statistics the moment
+// kernels left in HBM, the 10*I failsafe (:71-72, quirk Q3: the covariance is the UNWEIGHTED scatter about mu_d),
+// set_moments' det > 0 check (CMultivariateNormal.py:55-56), set_weights' sanitising (CMixtureModel.py:25-41), and the
+// re-packing of the proposal mixture for the next weighting (both the DIAG and the FULL layout of include/ais_b200.h:
+// the caller picks DIAG when status says every covariance is diagonal -- the usual case, the failsafe) plus the float32
+// means / Cholesky factors the ancestral sampler wants. One thread per proposal, everything in float64 in local arrays
+// (D <= 16); N <= a few thousand proposals, so one CTA. Replaces three device->host reads, the host linear algebra and
+// the host packing + upload of an iteration.
+//   status[0] proposals on the failsafe, [1] proposals with a non-diagonal covariance, [2] proposals whose covariance
+//   has det <= 0 or is not positive definite (the reference would raise AssertionError), [3] 1 if every mixture weight
+//   was sanitised to 0 (the reference then draws every sample from the last component).
+// ---------------------------------------------------------------------------------------------
+constexpr int kUpdMaxD = 16;
+constexpr int kUpdThreads = 256;
+
+__device__ double upd_block_sum(double v, double* sh) {
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = kUpdThreads / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+// Gauss-Jordan inverse with partial pivoting and the determinant (host.cu, invert_with_det); false if singular
+__device__ bool upd_invert(const double* C, int D, double* M, double* P, double* det) {
+  for (int i = 0; i < D * D; ++i) M[i] = C[i];
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) P[i * D + j] = i == j ? 1.0 : 0.0;
+  double d = 1.0;
+  for (int c = 0; c < D; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < D; ++r)
+      if (fabs(M[r * D + c]) > fabs(M[piv * D + c])) piv = r;
+    if (M[piv * D + c] == 0.0 || M[piv * D + c] != M[piv * D + c]) return false;
+    if (piv != c) {
+      for (int j = 0; j < D; ++j) {
+        double t = M[piv * D + j]; M[piv * D + j] = M[c * D + j]; M[c * D + j] = t;
+        t = P[piv * D + j]; P[piv * D + j] = P[c * D + j]; P[c * D + j] = t;
+      }
+      d = -d;
+    }
+    const double pv = M[c * D + c];
+    d *= pv;
+    for (int j = 0; j < D; ++j) {
+      M[c * D + j] /= pv;
+      P[c * D + j] /= pv;
+    }
+    for (int r = 0; r < D; ++r) {
+      if (r == c) continue;
+      const double f = M[r * D + c];
+      if (f == 0.0) continue;
+      for (int j = 0; j < D; ++j) {
+        M[r * D + j] -= f * M[c * D + j];
+        P[r * D + j] -= f * P[c * D + j];
+      }
+    }
+  }
+  *det = d;
+  return true;
+}
+
+__global__ void __launch_bounds__(kUpdThreads)
+    mpmc_update_kernel(const double* __restrict__ mom, const double* __restrict__ raw, double n, int64_t N, int D,
+                       int DP, int64_t KP, int RF, double* __restrict__ means, double* __restrict__ covs,
+                       double* __restrict__ alpha, double* __restrict__ wmix, float* __restrict__ rows_diag,
+                       float* __restrict__ rows_full, float* __restrict__ offsets, float* __restrict__ means32,
+                       float* __restrict__ chol32, float* __restrict__ w32, int* __restrict__ status) {
+  __shared__ double sh[kUpdThreads];
+  const int tid = threadIdx.x;
+  const double* s1 = raw;
+  const double* s2 = raw + D;
+  const int W = D + 1;
+  if (tid < 4) status[tid] = 0;
+  // wproposals = alpha / alpha.sum() (m_pmc.py:77), then set_weights: NaN / <= 0 -> 0, / sum if the sum is positive
+  double part = 0.0;
+  for (int64_t k = tid; k < N; k += kUpdThreads) part += mom[k * W];
+  const double sum1 = upd_block_sum(part, sh);
+  part = 0.0;
+  for (int64_t k = tid; k < N; k += kUpdThreads) {
+    const double a = mom[k * W] / sum1;
+    part += (a != a || a <= 0.0) ? 0.0 : a;
+  }
+  const double sum2 = upd_block_sum(part, sh);
+  if (tid == 0 && !(sum2 > 0.0)) status[3] = 1;
+  const float ninf = -INFINITY;
+  const double base = -0.5 * D * kLog2Pi, sfac = sqrt(kLog2e / 2.0);
+  const int TRI = DP * (DP + 1) / 2;
+  for (int64_t k = tid; k < KP; k += kUpdThreads) {
+    float* rd = rows_diag + k * 2 * DP;
+    float* rf = rows_full + k * RF;
+    for (int q = 0; q < 2 * DP; ++q) rd[q] = 0.f;
+    for (int q = 0; q < RF; ++q) rf[q] = 0.f;
+    if (k >= N) {
+      offsets[k] = ninf;
+      continue;
+    }
+    const double a_raw = mom[k * W];
+    const double wprop = a_raw / sum1;
+    alpha[k] = wprop;
+    double w = (wprop != wprop || wprop <= 0.0) ? 0.0 : wprop;
+    if (sum2 > 0.0) w /= sum2;
+    wmix[k] = w;
+    w32[k] = static_cast<float>(w);
+    double mu[kUpdMaxD], C[kUpdMaxD * kUpdMaxD], M[kUpdMaxD * kUpdMaxD], P[kUpdMaxD * kUpdMaxD], G[kUpdMaxD * kUpdMaxD];
+    for (int d = 0; d < D; ++d) mu[d] = mom[k * W + 1 + d] / a_raw;                      // eq. 14.2 (NaN / inf if alpha = 0)
+    bool bad = false;
+    for (int r = 0; r < D; ++r)
+      for (int c = 0; c < D; ++c) {
+        const double v = s2[r * D + c] - mu[r] * s1[c] - s1[r] * mu[c] + n * mu[r] * mu[c];  // raw scatter about mu (Q3)
+        C[r * D + c] = v;
+        bad |= (v != v) || (v > 10.0);
+      }
+    if (bad) {
+      atomicAdd(&status[0], 1);
+      for (int r = 0; r < D; ++r)
+        for (int c = 0; c < D; ++c) C[r * D + c] = r == c ? 10.0 : 0.0;
+    }
+    bool offdiag = false;
+    for (int r = 0; r < D; ++r)
+      for (int c = 0; c < D; ++c) {
+        covs[(k * D + r) * D + c] = C[r * D + c];
+        if (r != c && C[r * D + c] != 0.0) offdiag = true;
+      }
+    if (offdiag) atomicAdd(&status[1], 1);
+    for (int d = 0; d < D; ++d) {
+      means[k * D + d] = mu[d];
+      means32[k * D + d] = static_cast<float>(mu[d]);
+    }
+    bool broken = false;
+    // Cholesky factor of sym(C) for the sampler (x = mu + L z)
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j <= i; ++j) {
+        double acc = 0.5 * (C[i * D + j] + C[j * D + i]);
+        for (int t = 0; t < j; ++t) acc -= G[i * D + t] * G[j * D + t];
+        if (i == j) {
+          if (!(acc > 0.0)) broken = true;
+          G[i * D + i] = sqrt(acc);
+        } else {
+          G[i * D + j] = acc / G[j * D + j];
+        }
+      }
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < D; ++j) chol32[(k * D + i) * D + j] = j <= i ? static_cast<float>(G[i * D + j]) : 0.f;
+    // log det and the packed rows
+    double logdet = 0.0, det = 0.0;
+    if (!offdiag) {
+      for (int d = 0; d < D; ++d) {
+        const double v = C[d * D + d];
+        if (!(v > 0.0)) broken = true;
+        logdet += log(v);
+        const float af = static_cast<float>(sqrt(kLog2e / (2.0 * v)));
+        rd[d] = af;
+        rd[DP + d] = static_cast<float>(-static_cast<double>(af) * mu[d]);
+      }
+    }
+    if (!upd_invert(C, D, M, P, &det) || !(det > 0.0)) {
+      broken = true;
+    } else {
+      if (offdiag) logdet = log(det);
+      // Q = J sym(P) J = G G^T;  A = J G^T J  (host.cu, aisb_pack_mixture_f64, FULL)
+      for (int i = 0; i < D; ++i)
+        for (int j = 0; j <= i; ++j) {
+          const int ri = D - 1 - i, rj = D - 1 - j;
+          double acc = 0.5 * (P[ri * D + rj] + P[rj * D + ri]);
+          for (int t = 0; t < j; ++t) acc -= G[i * D + t] * G[j * D + t];
+          if (i == j) {
+            if (!(acc > 0.0)) broken = true;
+            G[i * D + i] = sqrt(acc);
+          } else {
+            G[i * D + j] = acc / G[j * D + j];
+          }
+        }
+      for (int r = 0; r < D; ++r) {
+        double br = 0.0;
+        for (int c = 0; c <= r; ++c) {
+          const float af = static_cast<float>(sfac * G[(D - 1 - c) * D + (D - 1 - r)]);
+          rf[r * (r + 1) / 2 + c] = af;
+          br -= static_cast<double>(af) * mu[c];
+        }
+        rf[TRI + r] = static_cast<float>(br);
+      }
+    }
+    if (broken) atomicAdd(&status[2], 1);
+    offsets[k] = w > 0.0 ? static_cast<float>(kLog2e * (log(w) + base - 0.5 * logdet)) : ninf;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Raw first and second moments in float64: out = { sum x [D], sum x x^T [D*D] }
 // ---------------------------------------------------------------------------------------------
@@ -521,6 +714,27 @@ extern "C" int aisb_mpmc_moments2_f32(const float* d_x, int64_t n, const aisb_pa
   }
   set_error("mpmc_moments2: unknown cov_kind %d", proposals->cov_kind);
   return AISB_ERR_INVALID;
+}
+
+
+extern "C" int aisb_mpmc_update_f64(const double* d_mom, const double* d_raw, double n_samples, int64_t N, int32_t D,
+                                    double* d_means, double* d_covs, double* d_alpha, double* d_wmix,
+                                    float* d_rows_diag, float* d_rows_full, float* d_offsets, float* d_means32,
+                                    float* d_chol32, float* d_w32, int32_t* d_status, void* stream) {
+  const int DP = aisb_padded_dims(D);
+  if (!d_mom || !d_raw || !d_means || !d_covs || !d_alpha || !d_wmix || !d_rows_diag || !d_rows_full || !d_offsets ||
+      !d_means32 || !d_chol32 || !d_w32 || !d_status || N < 1 || D < 1 || D > kUpdMaxD || DP == 0) {
+    set_error("mpmc_update: null pointer or unsupported shape (N=%lld, D=%d; D <= %d)", static_cast<long long>(N), D,
+              kUpdMaxD);
+    return D > kUpdMaxD ? AISB_ERR_UNSUPPORTED : AISB_ERR_INVALID;
+  }
+  const int64_t KP = aisb_padded_components(N);
+  const int RF = static_cast<int>(aisb_packed_row_floats(AISB_COV_FULL, D));
+  mpmc_update_kernel<<<1, kUpdThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_mom, d_raw, n_samples, N, D, DP, KP, RF, d_means, d_covs, d_alpha, d_wmix, d_rows_diag, d_rows_full, d_offsets,
+      d_means32, d_chol32, d_w32, d_status);
+  AISB_LAUNCH_CHECK("mpmc_update_kernel");
+  return AISB_OK;
 }
 
 extern "C" int aisb_raw_moments_f32(const float* d_x, int64_t n, int32_t D, double* d_out, void* stream) {

@@ -3,8 +3,12 @@
 
 Per iteration: K draws from the proposal mixture, one fused weight kernel (log pi, log q, log w,
 normaliser), one Rao-Blackwellised moment kernel (alpha_d and mu_d numerators over all K x N
-(sample, proposal) pairs; C ABI aisb_mpmc_moments_f32) and one raw-moment kernel for the scatter.
-The O(N D^2) parameter update runs on the host in float64, as in the reference.
+(sample, proposal) pairs; C ABI aisb_mpmc_moments[_dev]_f32), one raw-moment kernel for the scatter and ONE
+update kernel (C ABI aisb_mpmc_update_f64: alpha / mu / Sigma, failsafe, determinant check, weight sanitising
+and the re-packing of the proposal mixture, all in float64 on the device). The proposal parameters live in
+HBM between iterations; the host reads 16 bytes of status per iteration (which packed layout to use, did a
+covariance lose positive definiteness) and mirrors the parameters as numpy arrays only when somebody asks
+(`proposals`, `model`, `wproposals`, ...). D > 16 and `paper_covariance=True` keep the float64 host update.
 
 Reference quirks kept on purpose: Q3 - the covariance update multiplies the UNWEIGHTED scatter
 (X - mu_d)^T (X - mu_d) by sum_i w_i rho_di / alpha_d = 1, and falls back to 10*I when any entry is NaN or > 10
@@ -39,24 +43,56 @@ class CMixturePMC(CMixtureISSamplingMethod):
         # the sufficient statistics (weight record, alpha / mu numerators, raw moments) are summed over the ranks and
         # every rank performs the identical float64 parameter update
         self.sharded = bool(params.get("sharded", False))
+        # False keeps the float64 host update of round 1 (also taken for D > 16 and paper_covariance)
+        self.device_update = bool(params.get("device_update", True))
+        self._dev = None
+        self._host = {}
         self.reset()
 
     def reset(self):
         super(CMixturePMC, self).reset()
-        self._means = np.random.uniform(self.space_min, self.space_max, size=(self.N, self.ndims))
+        means = np.random.uniform(self.space_min, self.space_max, size=(self.N, self.ndims))
         if self.sharded:
             from .. import parallel
-            self._means = parallel.broadcast_array(self._means)
+            means = parallel.broadcast_array(means)
         self._n_all_ranks = 0
-        self._covs = np.tile(np.diag(np.array([self.sigma] * self.ndims, dtype=np.float64)), (self.N, 1, 1))
-        self.wproposals = np.array([1 / self.N] * self.N)
-        self._mix_weights = sanitize_weights(self.wproposals.copy())
+        self._dev_valid = False
+        self._host = {"means": means,
+                      "covs": np.tile(np.diag(np.array([self.sigma] * self.ndims, dtype=np.float64)), (self.N, 1, 1)),
+                      "alpha": np.array([1 / self.N] * self.N)}
+        self._host["wmix"] = sanitize_weights(self._host["alpha"].copy())
         self._mixture = None
         self._objects = None
         self._sampler_params = None
 
+    # -- proposal parameters: numpy float64 mirrors of the device state, pulled on demand ----------------
+    def _pull(self):
+        if self._dev_valid and self._host is None:
+            d = self._dev
+            self._host = {"means": d["means"].cpu().numpy(), "covs": d["covs"].cpu().numpy(),
+                          "alpha": d["alpha"].cpu().numpy(), "wmix": d["wmix"].cpu().numpy()}
+        return self._host
+
+    def _set_host(self, key, val):
+        self._pull()[key] = val
+        self._dev_valid = False            # the host copy is the truth again: re-pack from it
+        self._mixture = None
+        self._objects = None
+        self._sampler_params = None
+
+    _means = property(lambda self: self._pull()["means"], lambda self, v: self._set_host("means", v))
+    _covs = property(lambda self: self._pull()["covs"], lambda self, v: self._set_host("covs", v))
+    wproposals = property(lambda self: self._pull()["alpha"], lambda self, v: self._set_host("alpha", v))
+    _mix_weights = property(lambda self: self._pull()["wmix"], lambda self, v: self._set_host("wmix", v))
+
     # -- proposal mixture --------------------------------------------------------------------------
     def proposal_mixture(self):
+        if self._mixture is None and self._dev_valid:
+            d = self._dev
+            from .._lib import COV_DIAG
+            kind = COV_DIAG if d["all_diag"] else COV_FULL
+            self._mixture = _device.DeviceMixture(d["rows_diag"] if d["all_diag"] else d["rows_full"], d["offsets"],
+                                                  self.N, self.ndims, kind)
         if self._mixture is None:
             diag = np.diagonal(self._covs, axis1=1, axis2=2)
             if np.count_nonzero(self._covs - diag[:, :, None] * np.eye(self.ndims)[None]) == 0:
@@ -104,6 +140,13 @@ class CMixturePMC(CMixtureISSamplingMethod):
         indices from a device multinomial, then ONE kernel for x = mu_k + L_k z (C ABI aisb_sample_mixture_f32). The
         Cholesky factors are computed on the host in float64 once per parameter update (N small D x D matrices)."""
         dev = _device.device()
+        if self._dev_valid:
+            d = self._dev
+            if d["all_zero"]:    # degenerate adaptation: the reference draws every sample from the LAST component
+                idx = torch.full((int(n),), self.N - 1, dtype=torch.int64, device=dev)
+            else:
+                idx = torch.multinomial(d["w32"], int(n), replacement=True)
+            return _device.sample_mixture(d["means32"], d["chol32"], idx.contiguous())
         if self._sampler_params is None:
             L = np.linalg.cholesky(0.5 * (self._covs + np.transpose(self._covs, (0, 2, 1))))
             self._sampler_params = (torch.from_numpy(self._means).to(dev, torch.float32).contiguous(),
@@ -125,8 +168,62 @@ class CMixturePMC(CMixtureISSamplingMethod):
                                                     want_logq=True)
         return logw, logq, partials
 
+    # -- the update on the device ------------------------------------------------------------------------
+    def _device_update_ok(self):
+        return self.device_update and not self.paper_covariance and self.ndims <= 16
+
+    def _device_buffers(self):
+        if self._dev is None:
+            lib = _device.require_cuda()
+            dev, N, D = _device.device(), int(self.N), int(self.ndims)
+            KP, DP = lib.aisb_padded_components(N), lib.aisb_padded_dims(D)
+            RF = lib.aisb_packed_row_floats(COV_FULL, D)
+            f64 = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)
+            f32 = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+            self._dev = {"mom": f64(N, D + 1), "raw": f64(D + D * D), "means": f64(N, D), "covs": f64(N, D, D),
+                         "alpha": f64(N), "wmix": f64(N), "rows_diag": f32(KP, 2 * DP), "rows_full": f32(KP, RF),
+                         "offsets": f32(KP), "means32": f32(N, D), "chol32": f32(N, D, D), "w32": f32(N),
+                         "status": torch.zeros(4, dtype=torch.int32, device=dev), "all_diag": True, "all_zero": False}
+        return self._dev
+
+    def adapt_device(self, samples, logw, logq, record, n_total):
+        """m_pmc.py:53-78 without leaving HBM: moment kernels -> (all-reduce over the ranks when sharded) -> one update
+        kernel that also re-packs the proposal mixture. `record`: float64 CUDA [4] weight record of the whole batch
+        (merged over the ranks when sharded). One 16-byte status read-back per call."""
+        lib = _device.require_cuda()
+        d = self._device_buffers()
+        mix = self.proposal_mixture()                     # the mixture the samples were drawn from / weighed against
+        d["mom"].zero_()
+        d["raw"].zero_()
+        p = _device._ptr
+        _device.check(lib.aisb_mpmc_moments_dev_f32(p(samples), samples.shape[0], mix.ref(), p(logq), p(logw),
+                                                    p(record), p(d["mom"]), _device.stream_ptr()),
+                      "aisb_mpmc_moments_dev_f32")
+        _device.check(lib.aisb_raw_moments_f32(p(samples), samples.shape[0], self.ndims, p(d["raw"]),
+                                               _device.stream_ptr()), "aisb_raw_moments_f32")
+        if self.sharded:
+            from .. import parallel
+            parallel.all_reduce_sum(d["mom"])
+            parallel.all_reduce_sum(d["raw"])
+        # the moment kernel above was the last reader of the old packed rows: the update may overwrite them in place
+        _device.check(lib.aisb_mpmc_update_f64(p(d["mom"]), p(d["raw"]), float(n_total), int(self.N), int(self.ndims),
+                                               p(d["means"]), p(d["covs"]), p(d["alpha"]), p(d["wmix"]),
+                                               p(d["rows_diag"]), p(d["rows_full"]), p(d["offsets"]), p(d["means32"]),
+                                               p(d["chol32"]), p(d["w32"]), p(d["status"]), _device.stream_ptr()),
+                      "aisb_mpmc_update_f64")
+        st = d["status"].cpu().numpy()                    # 16 bytes: the one host read of the iteration
+        # CMultivariateNormal.set_moments asserts det > 0 (CMultivariateNormal.py:55-56)
+        assert st[2] == 0, "%d proposal covariance(s) lost positive definiteness in the M-PMC update" % int(st[2])
+        d["all_diag"], d["all_zero"] = bool(st[1] == 0), bool(st[3] != 0)
+        self._dev_valid = True
+        self._host = None                                  # numpy mirrors are pulled when somebody reads them
+        self._mixture = None
+        self._objects = None
+        self._sampler_params = None
+
     def adapt(self, samples, logw, logq, partials_host):
-        """alpha, mu, Sigma update (m_pmc.py:53-78) from device-side sufficient statistics."""
+        """alpha, mu, Sigma update (m_pmc.py:53-78) from device-side sufficient statistics, finished on the HOST in
+        float64 (the round-1 path; still used for D > 16, paper_covariance and as the parity entry point of the tests)."""
         log_norm = _device.weight_logsum(partials_host)  # log sum_i w_i: weights are batch-normalised (m_pmc.py:108)
         D = self.ndims
         mom = _device.mpmc_moments(samples, self.proposal_mixture(), logq, logw, log_norm,
@@ -198,6 +295,17 @@ class CMixturePMC(CMixtureISSamplingMethod):
             logw, logq, partials = self.weigh(new_samples, target_d)
             self._num_pi_evals += k
             self._num_q_evals += k * (self.N + 1)
+            if self._device_update_ok():
+                rec = partials
+                if self.sharded:
+                    from .. import parallel                 # the batch is the union of all ranks' draws
+                    rec = _device.merge_weight_records(parallel.all_gather_records_dev(partials))
+                self.adapt_device(new_samples, logw, logq, rec, int(self.K))
+                # accumulated weights are the batch-normalised ones (quirk Q4); the normaliser never visits the host
+                self._append(new_samples, logw - (rec[0] + torch.log(rec[1])).to(torch.float32))
+                self._n_all_ranks += int(self.K)
+                elapsed_time = time.time() - t_ini
+                continue
             ph = partials.cpu().numpy()
             if self.sharded:
                 from .. import parallel

@@ -309,6 +309,34 @@ int aisb_mpmc_moments_f32(const float* d_x, int64_t n, const aisb_packed_mixture
 int aisb_mpmc_moments2_f32(const float* d_x, int64_t n, const aisb_packed_mixture* proposals, const float* d_logq,
                            const float* d_logw, double log_norm, double* d_out, void* stream);
 
+/* aisb_mpmc_moments_f32 with the normaliser taken from a weight record {M, S1, S2, n} that lives in DEVICE memory
+ * (log_norm = M + log S1, e.g. the d_out_partials of aisb_dm_weights_f32 or a merged multi-rank record): no host round
+ * trip between the weight kernel and the moment kernel. */
+int aisb_mpmc_moments_dev_f32(const float* d_x, int64_t n, const aisb_packed_mixture* proposals, const float* d_logq,
+                              const float* d_logw, const double* d_record, double* d_out, void* stream);
+
+/*
+ * M-PMC parameter update on the device. Replaces CMixturePMC.adapt (sampling_methods/m_pmc.py:53-78) together with the
+ * CMultivariateNormal.set_moments calls (CMultivariateNormal.py:52-62) and CMixtureModel.set_weights
+ * (CMixtureModel.py:25-41) it ends in: alpha_d = mom[d][0] / sum, mu_d = mom[d][1..D] / mom[d][0],
+ * Sigma_d = raw scatter about mu_d (quirk Q3) or 10*I when any entry is NaN or > 10, weights sanitised, and the
+ * proposal mixture RE-PACKED for the next weighting without leaving HBM.
+ *   d_mom [N, D+1]      output of aisb_mpmc_moments*_f32 (summed over ranks)
+ *   d_raw [D + D*D]     output of aisb_raw_moments_f32 (summed over ranks); n_samples = number of points behind it
+ *   d_means [N, D], d_covs [N, D, D], d_alpha [N] (normalised, may hold NaN like the reference's wproposals),
+ *   d_wmix [N] (sanitised mixture weights): float64 state, read by the host only when somebody asks for it
+ *   d_rows_diag [KP, 2 DP], d_rows_full [KP, RF], d_offsets [KP]: the packed mixture in the DIAG and in the FULL layout
+ *       (use DIAG iff status[1] == 0); d_means32 [N, D], d_chol32 [N, D, D] (lower-triangular): sampler parameters;
+ *   d_w32 [N]: the mixture weights as float32 (component draws)
+ *   d_status [4] int32: {proposals on the 10*I failsafe, proposals with off-diagonal covariance, proposals whose
+ *       covariance is not positive definite / det <= 0 (the reference raises AssertionError), all weights zero}
+ * D <= 16.
+ */
+int aisb_mpmc_update_f64(const double* d_mom, const double* d_raw, double n_samples, int64_t N, int32_t D,
+                         double* d_means, double* d_covs, double* d_alpha, double* d_wmix, float* d_rows_diag,
+                         float* d_rows_full, float* d_offsets, float* d_means32, float* d_chol32, float* d_w32,
+                         int32_t* d_status, void* stream);
+
 /*
  * First and second raw moments of a point set, in float64:  out = { sum_i x_i [D], sum_i x_i x_i^T [D*D] }.
  * Used for the (unweighted, quirk Q3) scatter of m_pmc.py:64-68. d_out [D + D*D] doubles, zeroed by the caller.

@@ -120,6 +120,15 @@ def run_unittests(build_ref):
              "tests.distributions.test_multivariate_uniform_unittest",
              "tests.metrics.test_metric_kldivergence"]
     import importlib
+    import numpy as np
+    # the reference's KLD tests are statistical (1e5 uniform evaluation points from the UNSEEDED global numpy RNG,
+    # 1 % tolerance) and fail now and then on the reference itself (observed: test_different2 at 1.04 %); re-seed the
+    # stream before EVERY test so that both legs of the drop-in test see the same, passing, evaluation points
+    class SeededResult(unittest.TextTestResult):
+        def startTest(self, test):
+            np.random.seed(20240)
+            super().startTest(test)
+
     suite = unittest.TestSuite()
     for n in names:
         suite.addTests(unittest.defaultTestLoader.loadTestsFromModule(importlib.import_module(n)))
@@ -128,7 +137,7 @@ def run_unittests(build_ref):
     old = sys.stdout
     sys.stdout = sink                       # the reference's tests print every probability they check
     try:
-        res = unittest.TextTestRunner(stream=stream, verbosity=0).run(suite)
+        res = unittest.TextTestRunner(stream=stream, verbosity=0, resultclass=SeededResult).run(suite)
     finally:
         sys.stdout = old
     return {"run": res.testsRun, "failures": [str(t[0]) + ": " + t[1][-400:] for t in res.failures],

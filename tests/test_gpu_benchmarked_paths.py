@@ -124,12 +124,14 @@ def test_tensor_core_path_on_clustered_proposals(D, modes, capsys):
               "CUDA-core kernel %.3f ms, %d samples" % (D, n_unique, N, t_tc, t_tc0, t_cc, xs.shape[0]))
 
 
+@pytest.mark.parametrize("update", ["host", "device"])
 @pytest.mark.parametrize("geom", ["std", "tiny"])
-def test_mpmc_config3_shape_against_reference_iterations(geom):
+def test_mpmc_config3_shape_against_reference_iterations(geom, update):
     """Two consecutive iterations of the reference's CMixturePMC at the BASELINE configs[2] shape (D = 8, 16-mode target,
     N = 256 proposals; make_config3): batch-normalised weights, alpha, mu and Sigma (incl. which proposals hit the 10*I
     failsafe of quirk Q3). "tiny" iteration 0 produces genuine full covariances for all 256 proposals; its iteration 1
-    then samples from / weighs against those FULL-covariance proposals."""
+    then samples from / weighs against those FULL-covariance proposals. update = "host": the float64 numpy update of
+    CMixturePMC.adapt; "device": aisb_mpmc_update_f64 (CMixturePMC.adapt_device), the path importance_sample takes."""
     from ais_benchmarks_b200 import _device
     from ais_benchmarks_b200.sampling_methods import CMixturePMC
     g = load_golden("config3")
@@ -169,7 +171,12 @@ def test_mpmc_config3_shape_against_reference_iterations(geom):
         big = ref_w > 1e-9 * ref_w.max()
         assert big.sum() > 0 and np.max(np.abs(w[big] - ref_w[big]) / ref_w[big]) < W_TOL
         assert abs(w.sum() - ref_w.sum()) < 1e-6
-        s.adapt(xd, logw, logq, ph)
+        if update == "host":
+            s.adapt(xd, logw, logq, ph)
+        else:
+            s.adapt_device(xd, logw, logq, part, K)
+            assert s._dev_valid and s._host is None            # parameters live in HBM until somebody reads them
+            assert s.proposal_mixture().kind == (1 if g["failsafe" + t].all() else 2)   # DIAG after the failsafe, else FULL
         assert np.allclose(s.wproposals, g["new_alpha" + t], rtol=W_TOL, atol=1e-9)
         live = g["new_alpha" + t] > 1e-9
         assert live.sum() > 0

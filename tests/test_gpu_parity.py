@@ -446,11 +446,28 @@ def test_mpmc_iteration_golden():
             ref_w = g["w" + t]
             big = ref_w > 1e-9
             assert np.max(np.abs(w[big] - ref_w[big]) / ref_w[big]) < W_TOL
+            pre = (s._means.copy(), s._covs.copy(), s.wproposals.copy(), s._mix_weights.copy())
             s.adapt(xd, logw, logq, ph)
             assert np.allclose(s.wproposals, g["new_alpha" + t], rtol=W_TOL, atol=1e-9)
             live = g["new_alpha" + t] > 1e-9
             assert np.allclose(s._means[live], g["new_means" + t][live], rtol=W_TOL, atol=1e-5)
             assert np.allclose(s._covs[live], g["new_covs" + t][live], rtol=1e-3, atol=1e-5)
+            # the same update by the device kernel (aisb_mpmc_update_f64): must agree with the host float64 update
+            host = (s._means.copy(), s._covs.copy(), s.wproposals.copy(), s._mix_weights.copy())
+            s._means, s._covs = pre[0], pre[1]
+            s.wproposals, s._mix_weights = pre[2], pre[3]
+            logw2, logq2, part2 = s.weigh(xd, target)
+            s.adapt_device(xd, logw2, logq2, part2, K)
+            ok = np.isfinite(host[0]).all(axis=1)
+            assert np.allclose(s._means[ok], host[0][ok], rtol=1e-9, atol=1e-12)
+            assert np.allclose(s._covs[ok], host[1][ok], rtol=1e-9, atol=1e-12)
+            assert np.allclose(s.wproposals, host[2], rtol=1e-9, atol=1e-15, equal_nan=True)
+            assert np.allclose(s._mix_weights, host[3], rtol=1e-9, atol=1e-15)
+            # ... and the mixture it packed on the device evaluates like the one the host packs from the same parameters
+            lq_dev = _device.mixture_logpdf(xd, s.proposal_mixture()).cpu().numpy()
+            s._means = s._means                                 # hand the parameters back to the host packer
+            lq_host = _device.mixture_logpdf(xd, s.proposal_mixture()).cpu().numpy()
+            assert rel_err(lq_dev, lq_host.astype(np.float64)) < 2e-6, rel_err.last
 
 
 @pytest.mark.parametrize("D", [1, 3, 8, 16, 32])
