@@ -170,15 +170,14 @@ def morton_order_torch(x):
 
 def morton_keys(x):
     """Signed 32-bit Z-order keys of the rows of x (float32 CUDA [n, D]) over their bounding box (C ABI
-    aisb_morton_keys_f32): one kernel instead of the element-wise chain of morton_order_torch."""
+    aisb_morton_keys_auto_f32: bounding box + keys in one call, no torch reductions on the serial path)."""
     lib = require_cuda()
     n, D = x.shape
     x = x.contiguous()
-    lo = x.min(dim=0).values
-    span = (x.max(dim=0).values - lo).contiguous()
     keys = torch.empty(n, dtype=torch.int32, device=x.device)
-    check(lib.aisb_morton_keys_f32(_ptr(x), n, D, morton_bits(D), _ptr(lo.contiguous()), _ptr(span), _ptr(keys),
-                                   stream_ptr()), "aisb_morton_keys_f32")
+    box = torch.empty(2 * D, dtype=torch.int32, device=x.device)      # scratch: encoded per-dimension min / max
+    check(lib.aisb_morton_keys_auto_f32(_ptr(x), n, D, morton_bits(D), _ptr(box), _ptr(keys), stream_ptr()),
+          "aisb_morton_keys_auto_f32")
     return keys
 
 

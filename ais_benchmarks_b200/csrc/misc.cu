@@ -176,6 +176,66 @@ __global__ void __launch_bounds__(256) morton_keys_kernel(const float* __restric
   keys[i] = static_cast<int32_t>(code ^ 0x80000000u);
 }
 
+
+// Bounding box of a point set in ONE pass (replaces two torch reductions + their glue per Z-order): per-dimension
+// minimum / maximum through block reductions and atomicMin / atomicMax on order-preserving unsigned encodings of the
+// floats (enc(f) = bits ^ 0x80000000 for f >= 0, ~bits otherwise; NaN coordinates are skipped). box[0..D) = encoded
+// minima (initialised to 0xFFFFFFFF), box[D..2D) = encoded maxima (initialised to 0).
+__device__ __forceinline__ uint32_t enc_ordered(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(uint32_t e) {
+  return __uint_as_float((e & 0x80000000u) ? (e & 0x7FFFFFFFu) : ~e);
+}
+
+__global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ x, int64_t n, int D,
+                                                   uint32_t* __restrict__ box) {
+  __shared__ uint32_t smin[AISB_MAX_DIMS], smax[AISB_MAX_DIMS];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    smin[d] = 0xFFFFFFFFu;
+    smax[d] = 0u;
+  }
+  __syncthreads();
+  const int64_t total = n * D;
+  // flat, coalesced sweep; element e belongs to dimension e % D
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float v = __ldg(x + e);
+    if (v == v) {
+      const uint32_t c = enc_ordered(v);
+      const int d = static_cast<int>(e % D);
+      atomicMin(&smin[d], c);
+      atomicMax(&smax[d], c);
+    }
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    atomicMin(&box[d], smin[d]);
+    atomicMax(&box[D + d], smax[d]);
+  }
+}
+
+// morton_keys_kernel with the box taken from bbox_kernel's encoded output
+__global__ void __launch_bounds__(256) morton_keys_box_kernel(const float* __restrict__ x, int64_t n, int D, int bits,
+                                                              const uint32_t* __restrict__ box,
+                                                              int32_t* __restrict__ keys) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float scale = static_cast<float>(1 << bits);
+  const float top = static_cast<float>((1 << bits) - 1);
+  uint32_t code = 0;
+  for (int d = 0; d < D; ++d) {
+    const float lo = dec_ordered(box[d]);
+    const float span = __fsub_rn(dec_ordered(box[D + d]), lo);
+    float v = __fmul_rn(__fdiv_rn(__fsub_rn(x[i * D + d], lo), fmaxf(span, 1e-30f)), scale);
+    v = fminf(fmaxf(v, 0.f), top);   // NaN -> 0
+    const uint32_t q = static_cast<uint32_t>(static_cast<int>(v));
+    for (int b = 0; b < bits; ++b) code |= ((q >> b) & 1u) << (b * D + d);
+  }
+  keys[i] = static_cast<int32_t>(code ^ 0x80000000u);
+}
+
 __global__ void counter_add_kernel(unsigned long long* ctr, unsigned long long inc) { *ctr += inc; }
 
 __global__ void uniform_box_kernel(const float* __restrict__ lo, const float* __restrict__ hi, int D, int64_t n,
@@ -296,6 +356,28 @@ extern "C" int aisb_morton_keys_f32(const float* d_x, int64_t n, int32_t D, int3
   morton_keys_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_x, n, D, bits, d_lo, d_span, d_keys);
   AISB_LAUNCH_CHECK("morton_keys_kernel");
+  return AISB_OK;
+}
+
+
+extern "C" int aisb_morton_keys_auto_f32(const float* d_x, int64_t n, int32_t D, int32_t bits, uint32_t* d_box,
+                                         int32_t* d_keys, void* stream) {
+  if (n < 0 || D < 1 || D > AISB_MAX_DIMS || bits < 1 || bits * D > 32 || !d_box || (n > 0 && (!d_x || !d_keys))) {
+    set_error("morton_keys_auto: invalid argument (n=%lld D=%d bits=%d; bits * D must not exceed 32)",
+              static_cast<long long>(n), D, bits);
+    return AISB_ERR_INVALID;
+  }
+  if (n == 0) return AISB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AISB_CUDA_CHECK(cudaMemsetAsync(d_box, 0xFF, sizeof(uint32_t) * D, st));
+  AISB_CUDA_CHECK(cudaMemsetAsync(d_box + D, 0, sizeof(uint32_t) * D, st));
+  int64_t blocks = (n * D + 256 * 16 - 1) / (256 * 16);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  bbox_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(d_x, n, D, d_box);
+  AISB_LAUNCH_CHECK("bbox_kernel");
+  morton_keys_box_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(d_x, n, D, bits, d_box, d_keys);
+  AISB_LAUNCH_CHECK("morton_keys_box_kernel");
   return AISB_OK;
 }
 

@@ -192,23 +192,31 @@ def run_cuda(args):
     metric = CKLDivergence()
     kernel_ms = []
 
+    phases = []                                                          # CUDA-event marks of the last resident steps
+
     def kde_step(resident=True):
         """One metric evaluation. resident=False: inputs start in pinned host memory (float32 tensors)."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev[0].record()
         cd = centres_d if resident else centres_pin.to(dev, non_blocking=True)
         xd = x_d if resident else x_pin.to(dev, non_blocking=True)
         kde = CDeviceKDE(cd, None, n_c, c["bw"], D, sup)                 # Z-order of the centres + pack kernel
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        ev[1].record()
         if spatial:
             xd, _ = parallel.spatial_shard(xd, rank, world)             # Z-order of all points, this rank's piece
+            ev[2].record()
             lq = _device.mixture_logpdf(xd, kde.mixture, points_ordered=True)
         else:
+            ev[2].record()
             lq = kde.log_prob(xd)                                        # Z-order + pairwise kernel (+ merge) + scatter
-        e1.record()
+        ev[3].record()
         lp = target.log_prob(xd)
         rec = _device.kld_partials(lp, lq)                               # device reduction
+        ev[4].record()
         kld = parallel.global_kld(rec)                                   # 8 doubles D2H (+ all-gather)
-        kernel_ms.append((e0, e1))
+        ev[5].record()
+        kernel_ms.append((ev[1] if spatial else ev[2], ev[3]))
+        phases.append(ev)
         return kld
 
     # -- e2e: the reference-facing call with host numpy float64 buffers --------------------------------------------
@@ -250,6 +258,11 @@ def run_cuda(args):
     barrier()
     kde_ms = max_over_ranks(t0.elapsed_time(t1)) / args.steps
     pair_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_ms]))
+    ph = np.mean([[e[i].elapsed_time(e[i + 1]) for i in range(5)] for e in phases[-args.steps:]], axis=0)
+    kde_phases = {"kde_build": float(ph[0]), "point_sharding": float(ph[1]), "pairwise": float(ph[2]),
+                  "target_and_reduction": float(ph[3]), "record_exchange_and_readback": float(ph[4]),
+                  "unit": "ms per step on rank %d (device time between CUDA events)" % rank}
+    phases.clear()
     kernel_ms.clear()
 
     # e2e (secondary): float32 inputs in PINNED host memory every step, result read back; wall clock
@@ -535,6 +548,7 @@ def run_cuda(args):
                                    "logpdf_subset_kernel<8>)" if _device.kde_mode() == "fast" else
                                    "AISB_KDE_MODE=%s" % _device.kde_mode(),
                          "kernel_ms": pair_kernel_ms,
+                         "step_phases": kde_phases,
                          "refined": kde_counters,
                          "flop_per_pair": flop_per_pair,
                          "peak_source": "live FFMA micro-benchmark in this run (aisb_peak_fma_f32); nominal 74.5",

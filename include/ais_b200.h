@@ -376,6 +376,12 @@ int aisb_box_mixture_logpdf_f32(const float* d_x, int64_t n, int32_t D, const fl
  *      aisb_mixture_logpdf_ordered_f32); no reference counterpart. */
 int aisb_morton_keys_f32(const float* d_x, int64_t n, int32_t D, int32_t bits, const float* d_lo, const float* d_span,
                          int32_t* d_keys, void* stream);
+/*  aisb_morton_keys_auto_f32: the same keys over the points' OWN bounding box, which it computes first in one pass
+ *      (d_box: 2*D uint32 of scratch: order-preserving encodings of the per-dimension minima / maxima; NaN coordinates
+ *      are ignored). One call instead of two reductions + the key kernel: the Z-order of a point set is on the serial
+ *      path of every KDE evaluation on every rank. */
+int aisb_morton_keys_auto_f32(const float* d_x, int64_t n, int32_t D, int32_t bits, uint32_t* d_box, int32_t* d_keys,
+                              void* stream);
 /*  aisb_sample_mixture_f32: ancestral draws from a full-covariance Gaussian mixture, given the component of every draw:
  *      out[i, :] = means[idx[i], :] + chol[idx[i]] z_i,  z_i ~ N(0, I)   (chol: lower-triangular factors, row-major
  *      [K, D, D]). Replaces CMixtureModel.sample (CMixtureModel.py:79-89) over CMultivariateNormal.sample

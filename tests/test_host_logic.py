@@ -316,9 +316,10 @@ def test_multinomial_resample_is_sync_free_and_handles_degenerate_weights():
     assert multinomial_resample(torch.zeros(3), 0).shape == (0,)
 
 
-def test_spatial_shard_partitions_the_point_set_cpu():
+def test_spatial_shard_partitions_the_point_set_cpu(monkeypatch):
     import torch
     from ais_benchmarks_b200 import parallel
+    monkeypatch.setattr(parallel, "SPATIAL_BLOCK", 16)
     rs = np.random.RandomState(3)
     x = torch.from_numpy(rs.normal(size=(1001, 3)).astype(np.float32))
     seen = torch.zeros(1001, dtype=torch.int64)
@@ -328,11 +329,16 @@ def test_spatial_shard_partitions_the_point_set_cpu():
         assert torch.equal(rows, x[idx])
         seen[idx] += 1
         sizes.append(len(idx))
-    assert bool((seen == 1).all()) and max(sizes) - min(sizes) <= 1
-    # every shard is spatially compact: its bounding box is much smaller than the whole set's
+    assert bool((seen == 1).all()) and max(sizes) - min(sizes) <= 16     # block-cyclic: balanced to within one block
+    # every block a rank receives is a run of curve neighbours: its bounding box is much smaller than the whole set's,
+    # while the rank as a whole sees every region of space (that is what balances the refinement load)
     whole = (x.max(0).values - x.min(0).values).prod()
     rows, _ = parallel.spatial_shard(x, 1, 4)
-    assert (rows.max(0).values - rows.min(0).values).prod() < 0.8 * whole
+    block = rows[:16]
+    assert (block.max(0).values - block.min(0).values).prod() < 0.1 * whole
+    assert (rows.max(0).values - rows.min(0).values).prod() > 0.5 * whole
+    one, idx1 = parallel.spatial_shard(x, 0, 1)                          # a single rank: the whole curve, in order
+    assert len(idx1) == 1001 and torch.equal(one, x[idx1])
 
 
 def test_peer_exchange_is_off_without_nccl():
