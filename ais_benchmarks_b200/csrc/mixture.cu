@@ -289,6 +289,13 @@ __global__ void subset_merge_kernel(const float* __restrict__ ws_m, const float*
 
 constexpr int64_t kSubsetCap = 1 << 16;   // list entries re-evaluated with the component range split kSubsetSplit ways
 constexpr int kSubsetSplit = 64;
+// Interleaved component splits of the fast kernel. A CTA (one warp, 128 points) that swept all 1e6 components would run
+// for ~100 ms, and CTAs differ 3-4x in how much they fold: with few, long CTAs the SMs drain unevenly at the end of the
+// launch (measured: +3.7 ms on a 190 ms launch at 5 splits; at full size 375.2 / 373.0 / 373.3 / 374.8 ms with 3 / 5 / 8 / 16
+// splits). The grid is therefore cut until it has kFastWaves waves of
+// resident CTAs (capped at kFastMaxSplit: every split starts its running maxima from scratch, +0.5 % folds per split).
+constexpr int kFastMaxSplit = 16;
+constexpr int kFastWaves = 20;
 
 // h_j = ||b_j||^2 / (2 a) per packed component (padding rows included) and, behind the vector, max_{j < K} ||b_j||^2
 __global__ void kde_screen_pack_kernel(const float* __restrict__ rows, int64_t K, int64_t KP, int DP, float inv2a,
@@ -846,7 +853,8 @@ extern "C" int aisb_mixture_logpdf_screened_f32(const float* d_x, int64_t n, con
 extern "C" size_t aisb_kde_fast_scratch_bytes(int64_t n) {
   if (n < 0) return 0;
   const size_t cap = static_cast<size_t>(n < kSubsetCap ? n : kSubsetCap);
-  return static_cast<size_t>(n) * (sizeof(int64_t) + sizeof(float)) + 2 * sizeof(float) * kSubsetSplit * cap + 512;
+  return static_cast<size_t>(n) * (sizeof(int64_t) + sizeof(float)) + 2 * sizeof(float) * kSubsetSplit * cap +
+         2 * sizeof(float) * kFastMaxSplit * static_cast<size_t>(n) + 1024;
 }
 
 extern "C" int aisb_mixture_logpdf_fast_f32(const float* d_x, int64_t n, const aisb_packed_mixture* mix,
@@ -869,29 +877,22 @@ extern "C" int aisb_mixture_logpdf_fast_f32(const float* d_x, int64_t n, const a
               "aligned points (got cov_kind=%d D=%d)", mix->cov_kind, mix->D);
     return AISB_ERR_UNSUPPORTED;
   }
-  Plan plan;
-  if (!make_plan(n, mix->K, mix->D, &plan)) {
-    set_error("mixture_logpdf_fast: unsupported D=%d", mix->D);
-    return AISB_ERR_UNSUPPORTED;
-  }
-  // single-warp CTAs, up to 16 resident per SM: interleaved split of the component range until the grid has ~8 waves,
-  // within the shared workspace contract (aisb_workspace_bytes) and with >= 16 chunks per CTA
+  // single-warp CTAs, up to 16 resident per SM: interleaved split of the component range (see kFastWaves), >= 16 chunks
+  // per CTA; the partial (m, S) of the splits live in the scratch buffer
+  const int64_t KPc = aisb_padded_components(mix->K);
   const int64_t ntiles = (n + kScreenThreads * 4 - 1) / (kScreenThreads * 4);
-  const int64_t nchunks = (plan.KP + kScreenChunk - 1) / kScreenChunk;
-  int64_t want = (static_cast<int64_t>(sm_count()) * 16 * 8 + ntiles - 1) / ntiles;
+  const int64_t nchunks = (KPc + kScreenChunk - 1) / kScreenChunk;
+  int64_t want = (static_cast<int64_t>(sm_count()) * 16 * kFastWaves + ntiles - 1) / ntiles;
   if (want > nchunks / 16) want = nchunks / 16;
-  if (want > plan.nsplit) want = plan.nsplit;
+  if (want > kFastMaxSplit) want = kFastMaxSplit;
   if (want < 1) want = 1;
   if (const char* e = getenv("AISB_SCREEN_NSPLIT")) {  // timing experiments
     const int64_t v = atoll(e);
-    if (v >= 1 && v <= plan.nsplit && v <= nchunks) want = v;
+    if (v >= 1 && v <= kFastMaxSplit && v <= nchunks) want = v;
   }
   const int nsplit = static_cast<int>(want);
-  Workspace ws{};
-  if (nsplit > 1) {
-    rc = carve_checked(d_workspace, workspace_bytes, n, plan, &ws, "mixture_logpdf_fast");
-    if (rc) return rc;
-  }
+  (void)d_workspace;
+  (void)workspace_bytes;
   char* sc = static_cast<char*>(d_scratch);
   unsigned long long* list_n = reinterpret_cast<unsigned long long*>(sc);
   int64_t* list = reinterpret_cast<int64_t*>(sc + 64);
@@ -900,6 +901,9 @@ extern "C" int aisb_mixture_logpdf_fast_f32(const float* d_x, int64_t n, const a
   float* sub_m = reinterpret_cast<float*>(sc + 64 + (sizeof(int64_t) + sizeof(float)) * n + 64);
   sub_m = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sub_m) + 15) / 16 * 16);
   float* sub_S = sub_m + kSubsetSplit * cap;
+  Workspace ws{};
+  ws.ws_m = sub_S + kSubsetSplit * cap;
+  ws.ws_S = ws.ws_m + static_cast<size_t>(kFastMaxSplit) * n;
   const PassArgs a = pass_args(mix);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (DP) {

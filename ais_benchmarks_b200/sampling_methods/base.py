@@ -223,7 +223,12 @@ class CDeviceKDE(CDistribution):
         self._idx = idx_dev
         self._src = samples_dev
         self.mixture = _device.DeviceMixture.kde(samples_dev, idx_dev, n_kde, bw)
-        self.weights = np.full(shape=(self.n_kde,), fill_value=1 / self.n_kde)
+
+    @property
+    def weights(self):
+        """Equal mixture weights 1 / n_kde (base.py:177), materialised only when somebody reads them: filling a
+        1e6-element numpy array costs ~1 ms of host time, more than the whole device-side build of the KDE."""
+        return np.full(shape=(self.n_kde,), fill_value=1 / self.n_kde)
 
     def centres(self):
         return self._src if self._idx is None else self._src[self._idx]
