@@ -167,11 +167,23 @@ struct TcExactIso {
   }
 };
 
+// maximum of a 32-column chunk: four independent chains of three-input maxima (a single chain is 16 dependent FMNMX3,
+// ~70 cycles of latency per chunk for a warp that has only one other warp on its scheduler to hide behind)
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 __device__ __forceinline__ float tc_chunk_max(const uint32_t (&r)[32]) {
-  float gr = __uint_as_float(r[0]);
+  float g[4];
 #pragma unroll
-  for (int i = 1; i < 32; ++i) gr = fmaxf(gr, __uint_as_float(r[i]));
-  return gr;
+  for (int q = 0; q < 4; ++q) {
+    g[q] = max3f(__uint_as_float(r[8 * q]), __uint_as_float(r[8 * q + 1]), __uint_as_float(r[8 * q + 2]));
+    g[q] = max3f(g[q], __uint_as_float(r[8 * q + 3]), __uint_as_float(r[8 * q + 4]));
+    g[q] = max3f(g[q], __uint_as_float(r[8 * q + 5]), __uint_as_float(r[8 * q + 6]));
+    g[q] = fmaxf(g[q], __uint_as_float(r[8 * q + 7]));
+  }
+  return fmaxf(max3f(g[0], g[1], g[2]), g[3]);
 }
 
 // fold 32 screened accumulator values (columns j0 .. j0+31, chunk maximum gr) into the partial sums, relative to the
