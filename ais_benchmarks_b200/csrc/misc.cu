@@ -181,14 +181,6 @@ __global__ void __launch_bounds__(256) morton_keys_kernel(const float* __restric
 // minimum / maximum through block reductions and atomicMin / atomicMax on order-preserving unsigned encodings of the
 // floats (enc(f) = bits ^ 0x80000000 for f >= 0, ~bits otherwise; NaN coordinates are skipped). box[0..D) = encoded
 // minima (initialised to 0xFFFFFFFF), box[D..2D) = encoded maxima (initialised to 0).
-__device__ __forceinline__ uint32_t enc_ordered(float f) {
-  const uint32_t b = __float_as_uint(f);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float dec_ordered(uint32_t e) {
-  return __uint_as_float((e & 0x80000000u) ? (e & 0x7FFFFFFFu) : ~e);
-}
-
 __global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ x, int64_t n, int D,
                                                    uint32_t* __restrict__ box) {
   __shared__ uint32_t smin[AISB_MAX_DIMS], smax[AISB_MAX_DIMS];

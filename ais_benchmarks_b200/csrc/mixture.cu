@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kScreenThreads, DP <= 8 ? 16 : 8)
     logpdf_fast_kernel(const float* __restrict__ x, int64_t n, PassArgs mix, float marg, int nsplit, int64_t ntiles,
                        float* __restrict__ out, float* __restrict__ ws_m, float* __restrict__ ws_S,
                        float* __restrict__ ws_u2, int64_t* __restrict__ list, unsigned long long* __restrict__ list_n,
-                       unsigned long long* __restrict__ stats, int dbg) {
+                       unsigned long long* __restrict__ stats, int dbg, uint32_t* __restrict__ gmin) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[kStages];
   __shared__ OuterAccT<kScreenThreads> outer;
@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(kScreenThreads, DP <= 8 ? 16 : 8)
   uint32_t it = 0;
   unsigned nscr = 0, nfold = 0;
   mixture_pass_fast<DP, E, kScreenChunk, COUNT>(mix.rows, mix.KP, split * kScreenChunk, nsplit, mix.a_iso, marg, smem,
-                                                sh_h, bars, outer, it, xr, m, S, u2, &nscr, &nfold, dbg);
+                                                sh_h, bars, outer, it, xr, m, S, u2, &nscr, &nfold, dbg,
+                                                nsplit > 1 ? gmin : nullptr, pidx, n);
   if constexpr (COUNT) {
     if ((threadIdx.x & 31) == 0) {
       atomicAdd(stats + 0, static_cast<unsigned long long>(nfold));
@@ -530,21 +531,24 @@ static int launch_screen_t(const float* x, int64_t n, const PassArgs& mix, const
 template <int DP>
 static int launch_fast_t(const float* x, int64_t n, const PassArgs& mix, int nsplit, float* out, const Workspace& ws,
                          float* ws_u2, int64_t* list, unsigned long long* list_n, float* sub_m, float* sub_S,
-                         unsigned long long* stats, cudaStream_t st) {
+                         uint32_t* gmin, unsigned long long* stats, cudaStream_t st) {
   constexpr size_t smem = size_t(kStages) * kScreenChunk * DP * sizeof(float);
   constexpr int E = points_per_thread(DP);
   const int64_t ntiles = (n + kScreenThreads * E - 1) / (kScreenThreads * E);
   const int64_t grid = ntiles * nsplit;
   const float marg = 21.f + log2f(static_cast<float>(mix.KP));
-  const char* dbg_env = getenv("AISB_FAST_DEBUG");  // bit 0: fold every group; bit 1: no recentring; bit 2: no exact pass
+  // bit 0: fold every group; bit 1: no recentring; bit 2: no exact pass; bit 3: no exchange of minima between splits
+  const char* dbg_env = getenv("AISB_FAST_DEBUG");
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
   AISB_CUDA_CHECK(cudaMemsetAsync(list_n, 0, sizeof(unsigned long long), st));
+  if (dbg & 8) gmin = nullptr;   // bit 3: no exchange of the running minima between the splits
+  if (nsplit > 1 && gmin) AISB_CUDA_CHECK(cudaMemsetAsync(gmin, 0xFF, sizeof(uint32_t) * n, st));
   if (stats)
     logpdf_fast_kernel<DP, true><<<static_cast<unsigned>(grid), kScreenThreads, smem, st>>>(
-        x, n, mix, marg, nsplit, ntiles, out, ws.ws_m, ws.ws_S, ws_u2, list, list_n, stats, dbg);
+        x, n, mix, marg, nsplit, ntiles, out, ws.ws_m, ws.ws_S, ws_u2, list, list_n, stats, dbg, gmin);
   else
     logpdf_fast_kernel<DP, false><<<static_cast<unsigned>(grid), kScreenThreads, smem, st>>>(
-        x, n, mix, marg, nsplit, ntiles, out, ws.ws_m, ws.ws_S, ws_u2, list, list_n, nullptr, dbg);
+        x, n, mix, marg, nsplit, ntiles, out, ws.ws_m, ws.ws_S, ws_u2, list, list_n, nullptr, dbg, gmin);
   AISB_LAUNCH_CHECK("logpdf_fast_kernel");
   if (nsplit > 1) {
     fast_merge_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ws.ws_m, ws.ws_S, ws_u2, nsplit, n,
@@ -854,7 +858,7 @@ extern "C" size_t aisb_kde_fast_scratch_bytes(int64_t n) {
   if (n < 0) return 0;
   const size_t cap = static_cast<size_t>(n < kSubsetCap ? n : kSubsetCap);
   return static_cast<size_t>(n) * (sizeof(int64_t) + sizeof(float)) + 2 * sizeof(float) * kSubsetSplit * cap +
-         2 * sizeof(float) * kFastMaxSplit * static_cast<size_t>(n) + 1024;
+         2 * sizeof(float) * kFastMaxSplit * static_cast<size_t>(n) + sizeof(uint32_t) * static_cast<size_t>(n) + 1024;
 }
 
 extern "C" int aisb_mixture_logpdf_fast_f32(const float* d_x, int64_t n, const aisb_packed_mixture* mix,
@@ -904,13 +908,14 @@ extern "C" int aisb_mixture_logpdf_fast_f32(const float* d_x, int64_t n, const a
   Workspace ws{};
   ws.ws_m = sub_S + kSubsetSplit * cap;
   ws.ws_S = ws.ws_m + static_cast<size_t>(kFastMaxSplit) * n;
+  uint32_t* gmin = reinterpret_cast<uint32_t*>(ws.ws_S + static_cast<size_t>(kFastMaxSplit) * n);
   const PassArgs a = pass_args(mix);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (DP) {
-    case 2: return launch_fast_t<2>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, sub_m, sub_S, d_stats, st);
-    case 4: return launch_fast_t<4>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, sub_m, sub_S, d_stats, st);
-    case 8: return launch_fast_t<8>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, sub_m, sub_S, d_stats, st);
-    case 16: return launch_fast_t<16>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, sub_m, sub_S, d_stats, st);
+    case 2: return launch_fast_t<2>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, sub_m, sub_S, gmin, d_stats, st);
+    case 4: return launch_fast_t<4>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, sub_m, sub_S, gmin, d_stats, st);
+    case 8: return launch_fast_t<8>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, sub_m, sub_S, gmin, d_stats, st);
+    case 16: return launch_fast_t<16>(d_x, n, a, nsplit, d_out_logp, ws, ws_u2, list, list_n, sub_m, sub_S, gmin, d_stats, st);
     default: break;
   }
   return AISB_ERR_UNSUPPORTED;

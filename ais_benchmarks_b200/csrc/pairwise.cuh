@@ -663,7 +663,8 @@ template <int DP, int EP, int JJ, bool COUNT>
 __device__ __forceinline__ void accumulate_chunk_fast(const float* __restrict__ srows, const float* __restrict__ sh,
                                                       int cnt, float n2a, float two_a, float dthr,
                                                       const float2 (&x2)[EP][DP], float2 (&ms)[EP], float2 (&cr)[EP],
-                                                      float2 (&S2)[EP], float2 (&thr)[EP], unsigned (&nfolded)) {
+                                                      float2 (&S2)[EP], float2 (&thr)[EP], const float2 (&gbest)[EP],
+                                                      unsigned (&nfolded)) {
 #pragma unroll 1
   for (int j0 = 0; j0 < cnt; j0 += JJ) {
     float h[JJ];
@@ -718,7 +719,7 @@ __device__ __forceinline__ void accumulate_chunk_fast(const float* __restrict__ 
       S2[pp] = acc;
       ms[pp] = mn;
       cr[pp] = c;
-      thr[pp] = make_float2(mn.x + dthr, mn.y + dthr);
+      thr[pp] = make_float2(fminf(mn.x, gbest[pp].x) + dthr, fminf(mn.y, gbest[pp].y) + dthr);
     }
   }
 }
@@ -731,7 +732,8 @@ __device__ __forceinline__ void mixture_pass_fast(const float* __restrict__ g_ro
                                                   uint64_t* bars, OA& outer, uint32_t& it, const float (&x)[E][DP],
                                                   float (&m)[E], float (&S)[E], float (&u2)[E],
                                                   unsigned* nscreened = nullptr, unsigned* nfolded_out = nullptr,
-                                                  int dbg = 0) {
+                                                  int dbg = 0, uint32_t* __restrict__ gmin = nullptr,
+                                                  const int64_t* pidx = nullptr, int64_t n = 0) {
   constexpr int KIND = AISB_COV_ISO_SHARED;
   constexpr int JJ = comps_per_step(KIND, DP);
   constexpr int kFoldEvery = 1024 / J > 0 ? 1024 / J : 1;   // the float32 inner sum spans ~1024 components
@@ -756,9 +758,13 @@ __device__ __forceinline__ void mixture_pass_fast(const float* __restrict__ g_ro
   }
   const float two_a = 2.f * a_iso, n2a = -2.f * a_iso, inv2a = 0.5f / a_iso;
   const float dthr = (dbg & 1) ? INFINITY : marg * inv2a;
-  float2 x2[EP][DP], ms[EP], cr[EP], S2[EP], thr[EP];
+  // gbest: the smallest s any CTA working on the same points (another interleaved split of the components) has seen so
+  // far, exchanged through `gmin` (one encoded float per point, initialised to 0xFFFFFFFF). It only tightens the SKIP
+  // threshold -- every split then prunes almost as well as a single sweep would -- the sums keep their own reference.
+  float2 x2[EP][DP], ms[EP], cr[EP], S2[EP], thr[EP], gbest[EP];
 #pragma unroll
   for (int pp = 0; pp < EP; ++pp) {
+    gbest[pp] = make_float2(kPosBig, kPosBig);
     float q0 = 0.f, q1 = 0.f;
 #pragma unroll
     for (int d = 0; d < DP; ++d) {
@@ -790,10 +796,24 @@ __device__ __forceinline__ void mixture_pass_fast(const float* __restrict__ g_ro
     outer_fold<E>(outer, m, S);
 #pragma unroll
     for (int pp = 0; pp < EP; ++pp) S2[pp] = make_float2(0.f, 0.f);
+    if (gmin != nullptr) {   // publish this CTA's minima (fire-and-forget reductions)
+#pragma unroll
+      for (int pp = 0; pp < EP; ++pp) {
+        if (pidx[2 * pp] < n) atomicMin(gmin + pidx[2 * pp], enc_ordered(ms[pp].x));
+        if (pidx[2 * pp + 1] < n) atomicMin(gmin + pidx[2 * pp + 1], enc_ordered(ms[pp].y));
+      }
+    }
   };
   stream_components<KIND, DP, false, J>(
       g_rows, nullptr, k_begin, KP, smem, bars, it,
       [&](const float* srows, const float*, int cnt, int64_t) {
+        // the other splits' minima: loads issued now, consumed after this chunk (their latency hides behind it)
+        uint32_t gseen[E];
+        if (gmin != nullptr) {
+#pragma unroll
+          for (int e = 0; e < E; ++e)
+            gseen[e] = pidx[e] < n ? *reinterpret_cast<volatile uint32_t*>(gmin + pidx[e]) : 0xFFFFFFFFu;
+        }
         // shift this chunk: b' = b + a c, h' = ||b'||^2 / (2a); every lane rewrites cnt / 32 rows
         float* rows = const_cast<float*>(srows);
 #pragma unroll 1
@@ -817,8 +837,18 @@ __device__ __forceinline__ void mixture_pass_fast(const float* __restrict__ g_ro
           sh_h[j] = q * inv2a;
         }
         __syncwarp();
-        accumulate_chunk_fast<DP, EP, JJ, COUNT>(srows, sh_h, cnt, n2a, two_a, dthr, x2, ms, cr, S2, thr, nfolded);
+        accumulate_chunk_fast<DP, EP, JJ, COUNT>(srows, sh_h, cnt, n2a, two_a, dthr, x2, ms, cr, S2, thr, gbest,
+                                                 nfolded);
         if constexpr (COUNT) nunits += static_cast<unsigned>(cnt / JJ) * EP;
+        if (gmin != nullptr) {
+#pragma unroll
+          for (int pp = 0; pp < EP; ++pp) {
+            // fminf drops NaN (the decoded initial pattern)
+            gbest[pp] = make_float2(fminf(gbest[pp].x, dec_ordered(gseen[2 * pp])),
+                                    fminf(gbest[pp].y, dec_ordered(gseen[2 * pp + 1])));
+            thr[pp] = make_float2(fminf(ms[pp].x, gbest[pp].x) + dthr, fminf(ms[pp].y, gbest[pp].y) + dthr);
+          }
+        }
         if ((++nchunk % kFoldEvery) == 0) fold();
         // the next bulk copy (async proxy) overwrites rows this warp wrote through the generic proxy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

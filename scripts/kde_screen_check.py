@@ -1,6 +1,6 @@
 """Screen-and-refine KDE kernel against the fold-skipping and the plain pairwise kernels on the configs[3] workload:
 agreement (max |diff| of the log densities), time per launch (CUDA events) and the refined fraction of the screen.
-Usage: kde_screen_check.py [scale] [reps]"""
+Usage: kde_screen_check.py [scale] [reps] [point fraction]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes as C
@@ -13,6 +13,8 @@ scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.25
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 lib = _lib.load()
 mu, sig, w, sup, centres_h, x_h = bench.kde_workload(scale=scale)
+if len(sys.argv) > 3:                      # evaluate only a fraction of the points (the per-rank share of an N-GPU run)
+    x_h = x_h[:int(len(x_h) * float(sys.argv[3]))]
 cd, xd = torch.from_numpy(centres_h).cuda(), torch.from_numpy(x_h).cuda()
 n, K = len(x_h), len(centres_h)
 mix = _device.DeviceMixture.kde(cd, None, K, 0.02)
