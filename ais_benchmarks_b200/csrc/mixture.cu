@@ -275,21 +275,31 @@ __global__ void __launch_bounds__(kThreads, DP <= 8 ? AISB_MIN_CTAS_SMALL : 1)
 }
 
 __global__ void subset_merge_kernel(const float* __restrict__ ws_m, const float* __restrict__ ws_S, int nsplit,
-                                    int64_t k_count, int64_t n, const int64_t* __restrict__ list,
+                                    int64_t k_begin, int64_t k_count, int64_t n, const int64_t* __restrict__ list,
                                     const unsigned long long* __restrict__ list_n, float add, float* __restrict__ out) {
-  const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;   // position inside this tier
   int64_t cnt = static_cast<int64_t>(*list_n) < n ? static_cast<int64_t>(*list_n) : n;
+  cnt -= k_begin;
   if (cnt > k_count) cnt = k_count;
   if (k >= cnt) return;
   float M = kNegBig;
   for (int s = 0; s < nsplit; ++s) M = fmaxf(M, ws_m[s * k_count + k]);
   float S = 0.f;
   for (int s = 0; s < nsplit; ++s) S += ws_S[s * k_count + k] * ex2(ws_m[s * k_count + k] - M);
-  out[list[k]] = lse_finish(M, S) + add;
+  out[list[k_begin + k]] = lse_finish(M, S) + add;
 }
 
-constexpr int64_t kSubsetCap = 1 << 16;   // list entries re-evaluated with the component range split kSubsetSplit ways
-constexpr int kSubsetSplit = 64;
+// Exact re-evaluation tiers: the first kSubsetCapA list entries with the component range split kSubsetSplitA ways (a
+// list of a few thousand points is 6 point tiles: unsplit, or split 64 ways, the re-evaluation ran for 58 / 2.7 ms on an
+// otherwise idle GPU -- a fixed cost that does not shrink with the number of ranks), the next kSubsetCapB entries split
+// kSubsetSplitB ways, the rest (almost everything listed: the machine is full anyway) unsplit. The tiers run back to back
+// and share one partials buffer of kSubsetWs floats per array.
+constexpr int64_t kSubsetCapA = 1 << 13;
+constexpr int kSubsetSplitA = 256;
+constexpr int64_t kSubsetCapB = 1 << 16;
+constexpr int kSubsetSplitB = 32;
+constexpr int64_t kSubsetWs = kSubsetCapA * kSubsetSplitA > kSubsetCapB * kSubsetSplitB ? kSubsetCapA * kSubsetSplitA
+                                                                                        : kSubsetCapB * kSubsetSplitB;
 // Interleaved component splits of the fast kernel. A CTA (one warp, 128 points) that swept all 1e6 components would run
 // for ~100 ms, and CTAs differ 3-4x in how much they fold: with few, long CTAs the SMs drain unevenly at the end of the
 // launch (measured: +3.7 ms on a 190 ms launch at 5 splits; at full size 375.2 / 373.0 / 373.3 / 374.8 ms with 3 / 5 / 8 / 16
@@ -555,33 +565,36 @@ static int launch_fast_t(const float* x, int64_t n, const PassArgs& mix, int nsp
                                                                               mix.uniform_offset, out, list, list_n);
     AISB_LAUNCH_CHECK("fast_merge_kernel");
   }
-  // exact re-evaluation of the listed points (no-op launches when the list is empty): the first kSubsetCap entries with
-  // the component range split so that a short list still fills the machine, the rest (only when almost everything is
-  // listed) with one CTA per point tile
+  // exact re-evaluation of the listed points (no-op launches when the list is empty), in tiers (see kSubsetCapA)
   if (!(dbg & 4)) {
     constexpr size_t smem_x = pass_smem_bytes(AISB_COV_ISO_SHARED, DP, false);
     const int64_t tile_pts = kThreads * E;
-    const int64_t cap = n < kSubsetCap ? n : kSubsetCap;
-    int64_t nsp = mix.KP / 2048;
-    nsp = nsp < 1 ? 1 : (nsp > kSubsetSplit ? kSubsetSplit : nsp);
     const int64_t units = mix.KP / AISB_COMP_ALIGN;
-    const int64_t cps = (units + nsp - 1) / nsp * AISB_COMP_ALIGN;
-    nsp = (mix.KP + cps - 1) / cps;
-    const int64_t tiles_a = (cap + tile_pts - 1) / tile_pts;
-    logpdf_subset_kernel<DP><<<static_cast<unsigned>(tiles_a * nsp), kThreads, smem_x, st>>>(
-        x, n, mix, list, list_n, 0, cap, static_cast<int>(nsp), cps, tiles_a, sub_m, sub_S, out);
-    AISB_LAUNCH_CHECK("logpdf_subset_kernel");
-    if (nsp > 1) {
-      subset_merge_kernel<<<static_cast<unsigned>((cap + 255) / 256), 256, 0, st>>>(sub_m, sub_S, static_cast<int>(nsp),
-                                                                                  cap, n, list, list_n,
-                                                                                  mix.uniform_offset, out);
-      AISB_LAUNCH_CHECK("subset_merge_kernel");
+    int64_t k0 = 0;
+    const int64_t caps[2] = {kSubsetCapA, kSubsetCapB};
+    const int splits[2] = {kSubsetSplitA, kSubsetSplitB};
+    for (int tier = 0; tier < 2 && k0 < n; ++tier) {
+      const int64_t cap = n - k0 < caps[tier] ? n - k0 : caps[tier];
+      int64_t nsp = units / 8;                       // >= 256 components per split
+      nsp = nsp < 1 ? 1 : (nsp > splits[tier] ? splits[tier] : nsp);
+      const int64_t cps = (units + nsp - 1) / nsp * AISB_COMP_ALIGN;
+      nsp = (mix.KP + cps - 1) / cps;
+      const int64_t tiles = (cap + tile_pts - 1) / tile_pts;
+      logpdf_subset_kernel<DP><<<static_cast<unsigned>(tiles * nsp), kThreads, smem_x, st>>>(
+          x, n, mix, list, list_n, k0, cap, static_cast<int>(nsp), cps, tiles, sub_m, sub_S, out);
+      AISB_LAUNCH_CHECK("logpdf_subset_kernel");
+      if (nsp > 1) {
+        subset_merge_kernel<<<static_cast<unsigned>((cap + 255) / 256), 256, 0, st>>>(
+            sub_m, sub_S, static_cast<int>(nsp), k0, cap, n, list, list_n, mix.uniform_offset, out);
+        AISB_LAUNCH_CHECK("subset_merge_kernel");
+      }
+      k0 += cap;
     }
-    if (n > cap) {
-      const int64_t tiles_b = (n - cap + tile_pts - 1) / tile_pts;
-      logpdf_subset_kernel<DP><<<static_cast<unsigned>(tiles_b), kThreads, smem_x, st>>>(
-          x, n, mix, list, list_n, cap, n - cap, 1, mix.KP, tiles_b, nullptr, nullptr, out);
-      AISB_LAUNCH_CHECK("logpdf_subset_kernel(overflow)");
+    if (k0 < n) {
+      const int64_t tiles = (n - k0 + tile_pts - 1) / tile_pts;
+      logpdf_subset_kernel<DP><<<static_cast<unsigned>(tiles), kThreads, smem_x, st>>>(
+          x, n, mix, list, list_n, k0, n - k0, 1, mix.KP, tiles, nullptr, nullptr, out);
+      AISB_LAUNCH_CHECK("logpdf_subset_kernel(rest)");
     }
   }
   if (stats) {
@@ -856,8 +869,7 @@ extern "C" int aisb_mixture_logpdf_screened_f32(const float* d_x, int64_t n, con
 
 extern "C" size_t aisb_kde_fast_scratch_bytes(int64_t n) {
   if (n < 0) return 0;
-  const size_t cap = static_cast<size_t>(n < kSubsetCap ? n : kSubsetCap);
-  return static_cast<size_t>(n) * (sizeof(int64_t) + sizeof(float)) + 2 * sizeof(float) * kSubsetSplit * cap +
+  return static_cast<size_t>(n) * (sizeof(int64_t) + sizeof(float)) + 2 * sizeof(float) * kSubsetWs +
          2 * sizeof(float) * kFastMaxSplit * static_cast<size_t>(n) + sizeof(uint32_t) * static_cast<size_t>(n) + 1024;
 }
 
@@ -901,12 +913,11 @@ extern "C" int aisb_mixture_logpdf_fast_f32(const float* d_x, int64_t n, const a
   unsigned long long* list_n = reinterpret_cast<unsigned long long*>(sc);
   int64_t* list = reinterpret_cast<int64_t*>(sc + 64);
   float* ws_u2 = reinterpret_cast<float*>(sc + 64 + sizeof(int64_t) * n);
-  const size_t cap = static_cast<size_t>(n < kSubsetCap ? n : kSubsetCap);
   float* sub_m = reinterpret_cast<float*>(sc + 64 + (sizeof(int64_t) + sizeof(float)) * n + 64);
   sub_m = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sub_m) + 15) / 16 * 16);
-  float* sub_S = sub_m + kSubsetSplit * cap;
+  float* sub_S = sub_m + kSubsetWs;
   Workspace ws{};
-  ws.ws_m = sub_S + kSubsetSplit * cap;
+  ws.ws_m = sub_S + kSubsetWs;
   ws.ws_S = ws.ws_m + static_cast<size_t>(kFastMaxSplit) * n;
   uint32_t* gmin = reinterpret_cast<uint32_t*>(ws.ws_S + static_cast<size_t>(kFastMaxSplit) * n);
   const PassArgs a = pass_args(mix);
