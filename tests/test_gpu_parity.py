@@ -853,12 +853,18 @@ def test_morton_key_kernel(D):
     assert bool((ref[perm_t][1:] >= ref[perm_t][:-1]).all())
 
 
+@pytest.mark.parametrize("mode", ["fast", "screen", "ordered"])
 @pytest.mark.parametrize("D", [1, 2, 8, 16])
-def test_spatially_ordered_kde_path(D, monkeypatch):
-    """Large KDEs pack their centres in Z-order and evaluate the points in Z-order (fold-skipping kernel variants behind
-    aisb_mixture_logpdf_ordered_f32, results scattered back). Same values as the ordinary path and as the float64
-    oracle; row order of the output is the caller's; clustered data far from the origin included."""
+def test_spatially_ordered_kde_path(D, mode, monkeypatch):
+    """Large KDEs pack their centres in Z-order and evaluate the points in Z-order with one of three kernel families
+    (AISB_KDE_MODE): "fast" = recentred expanded form + exact re-evaluation of the points whose error estimate is too
+    large (aisb_mixture_logpdf_fast_f32, the default), "screen" = expanded-form screen + exact refinement
+    (aisb_mixture_logpdf_screened_f32), "ordered" = centred form with fold skipping (aisb_mixture_logpdf_ordered_f32).
+    Same values as the ordinary path and as the float64 oracle; row order of the output is the caller's; clustered data
+    far from the origin included (there the fast kernel's estimate sends most points to the exact re-evaluation)."""
     from ais_benchmarks_b200 import _device
+    monkeypatch.setenv("AISB_KDE_MODE", mode)
+    assert _device.kde_mode() == mode
     monkeypatch.setattr(_device, "MORTON_MIN_ROWS", 1 << 16)
     monkeypatch.setattr(_device, "MORTON_MIN_PAIRS", 1 << 32)
     rs = np.random.RandomState(40 + D)
