@@ -105,24 +105,40 @@ class CMixtureModel(CDistribution):
             means, cov, kind = gaussian_pack_args(self.models)
             packed = ("gauss", _device.DeviceMixture.from_params(means, cov, self.weights, kind))
         elif all(_is_uniform(m) for m in self.models):
-            _device.require_cuda()
-            dev = _device.device()
-            K, D = len(self.models), self.dims
-            lo = np.empty((K, D)); hi = np.empty((K, D)); lwv = np.empty(K)
-            for k, m in enumerate(self.models):
-                c = np.asarray(m.loc, dtype=np.float64).reshape(-1)
-                r = np.broadcast_to(np.asarray(m.scale, dtype=np.float64).reshape(-1), (D,))
-                lo[k], hi[k] = c - r, c + r
-                with np.errstate(divide="ignore"):
-                    lwv[k] = np.log(self.weights[k]) - np.sum(np.log(2.0 * r))
-            packed = ("box", (torch.from_numpy(lo).to(dev, torch.float32), torch.from_numpy(hi).to(dev, torch.float32),
-                              torch.from_numpy(lwv).to(dev, torch.float32)))
+            packed = ("box", self._pack_boxes(list(range(len(self.models)))))
         else:
-            raise NotImplementedError(
-                "CMixtureModel on B200 evaluates all-Gaussian or all-uniform component lists; got %s"
-                % sorted({type(m).__name__ for m in self.models}))
+            # heterogeneous component list (CMixtureModel.py:53-56 accepts any objects with log_prob): the Gaussian
+            # components form one packed sub-mixture, the uniform ones one box mixture, anything else is evaluated
+            # through its own log_prob; log_prob joins the groups with a log-sum-exp on the device
+            ig = [k for k, m in enumerate(self.models) if _is_normal(m)]
+            ib = [k for k, m in enumerate(self.models) if _is_uniform(m)]
+            io = [k for k in range(len(self.models)) if k not in ig and k not in ib]
+            groups = []
+            if ig and self.weights[ig].sum() > 0:
+                means, cov, kind = gaussian_pack_args([self.models[k] for k in ig])
+                # from_params renormalises the sub-weights: the group's total mass comes back as an offset
+                groups.append(("gauss", _device.DeviceMixture.from_params(means, cov, self.weights[ig], kind),
+                               float(np.log(self.weights[ig].sum()))))
+            if ib:
+                groups.append(("box", self._pack_boxes(ib), 0.0))
+            packed = ("mixed", (groups, [(self.models[k], float(self.weights[k])) for k in io if self.weights[k] > 0]))
         self._cache_key, self._cache = key, packed
         return packed
+
+    def _pack_boxes(self, which):
+        _device.require_cuda()
+        dev = _device.device()
+        K, D = len(which), self.dims
+        lo = np.empty((K, D)); hi = np.empty((K, D)); lwv = np.empty(K)
+        for j, k in enumerate(which):
+            m = self.models[k]
+            c = np.asarray(m.loc, dtype=np.float64).reshape(-1)
+            r = np.broadcast_to(np.asarray(m.scale, dtype=np.float64).reshape(-1), (D,))
+            lo[j], hi[j] = c - r, c + r
+            with np.errstate(divide="ignore"):
+                lwv[j] = np.log(self.weights[k]) - np.sum(np.log(2.0 * r))
+        return (torch.from_numpy(lo).to(dev, torch.float32), torch.from_numpy(hi).to(dev, torch.float32),
+                torch.from_numpy(lwv).to(dev, torch.float32))
 
     def _points(self, data):
         if not _device.is_tensor(data):
@@ -135,8 +151,24 @@ class CMixtureModel(CDistribution):
         kind, packed = self._packed()
         if kind == "gauss":
             return _device.mixture_logpdf(x, packed)
-        lo, hi, lwv = packed
-        return _device.box_mixture_logpdf(x, lo, hi, lwv, open_upper=False)
+        if kind == "box":
+            lo, hi, lwv = packed
+            return _device.box_mixture_logpdf(x, lo, hi, lwv, open_upper=False)
+        groups, others = packed
+        parts = []
+        for gkind, gpacked, goff in groups:
+            if gkind == "gauss":
+                parts.append(_device.mixture_logpdf(x, gpacked) + goff)
+            else:
+                parts.append(_device.box_mixture_logpdf(x, gpacked[0], gpacked[1], gpacked[2], open_upper=False))
+        for m, w in others:                              # foreign components: their own log_prob, wherever it runs
+            lp = m.log_prob(x) if getattr(type(m), "__module__", "").startswith("ais_benchmarks_b200") else \
+                m.log_prob(x.double().cpu().numpy())
+            lp = lp if _device.is_tensor(lp) else torch.from_numpy(np.asarray(lp, dtype=np.float64).reshape(-1))
+            parts.append(lp.to(x.device, torch.float32) + float(np.log(w)))
+        if not parts:
+            return torch.full((x.shape[0],), -np.inf, dtype=torch.float32, device=x.device)
+        return torch.logsumexp(torch.stack(parts), dim=0)
 
     def log_prob(self, data):
         """log sum_k w_k p_k(x) (CMixtureModel.py:43-57)."""
@@ -155,6 +187,16 @@ class CMixtureModel(CDistribution):
         dev = _device.device()
         n = int(n_samples)
         idx = _device.mixture_component_draws(self.weights, n, dev)
+        if kind == "mixed":
+            # heterogeneous list: each component draws its own share (like CMixtureModel.py:84-88, batched per component)
+            counts = torch.bincount(idx, minlength=len(self.models)).cpu().numpy()
+            x = torch.empty((n, self.dims), dtype=torch.float32, device=dev)
+            for k, cnt in enumerate(counts):
+                if cnt:
+                    draw = self.models[k].sample(int(cnt))
+                    draw = draw if _device.is_tensor(draw) else torch.from_numpy(np.asarray(draw, dtype=np.float64))
+                    x[idx == k] = draw.to(dev, torch.float32).reshape(int(cnt), self.dims)
+            return x if as_tensor else x.cpu().numpy().astype(np.float64)
         if kind == "gauss":
             means, cov, ckind = gaussian_pack_args(self.models)
             z = _device.sample_iso(torch.zeros((1, self.dims), dtype=torch.float32, device=dev), n, 1.0)

@@ -533,7 +533,11 @@ def run_cuda(args):
             "e2e_pinned_f32": {"value": total_pairs / (kde_pinned_ms * 1e-3), "unit": UNIT,
                                "h2d_bytes_per_step": int(centres_pin.numel() * 4 + x_pin.numel() * 4),
                                "d2h_bytes_per_step": 64, "ms_per_step": kde_pinned_ms},
-            "gpu_launches": 6 * args.steps,
+            # kernels of libais_b200.so per resident step (profiles/r2_launches_bench_final.csv): bounding box + Morton keys
+            # for the centres and for the points (4), kde_pack, logpdf_fast, fast_merge, 3 x logpdf_subset + 2 x
+            # subset_merge (exact re-evaluation tiers), target logpdf, kld_partials + its merge; torch adds a radix sort
+            # and a gather per side
+            "gpu_launches": 15 * args.steps,
             "clocks": clock_info,
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp32_peak_tflops,

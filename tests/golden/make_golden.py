@@ -404,6 +404,21 @@ def _config3_logs(out, rows=1000):
             out["lq" + tag] = q.log_prob(x)
 
 
+def make_hetero():
+    """A CMixtureModel over a HETEROGENEOUS component list (CMixtureModel.py:53-56 takes any models[] with log_prob):
+    two Gaussians (one full covariance), two boxes and a zero-weight component, 2-D."""
+    rs = np.random.RandomState(123)
+    comps = [CMultivariateNormal({"mean": np.array([0.3, -0.2]), "sigma": np.diag([0.05, 0.02])}),
+             CMultivariateUniform({"center": np.array([-0.4, 0.1]), "radius": np.array([0.3, 0.2])}),
+             CMultivariateNormal({"mean": np.array([-0.5, 0.5]), "sigma": np.array([[0.04, 0.01], [0.01, 0.03]])}),
+             CMultivariateUniform({"center": np.array([0.5, 0.5]), "radius": np.array([0.25])}),
+             CMultivariateNormal({"mean": np.array([0.9, 0.9]), "sigma": np.diag([0.01, 0.01])})]
+    w = np.array([0.3, 0.2, 0.25, 0.25, 0.0])
+    mix = CMixtureModel({"models": comps, "weights": w.copy(), "dims": 2, "support": [[-1, -1], [1, 1]]})
+    x = rs.uniform(-1, 1, size=(400, 2))
+    save("hetero", x=x, w=w, logp=mix.log_prob(x), prob=mix.prob(x))
+
+
 def make_lais():
     """LAIS upper layer (sampling_methods/layered_ais.py:54-74) with the random draws captured."""
     out = {}
@@ -534,6 +549,7 @@ if __name__ == "__main__":
     make_metrics()
     make_mpmc()
     make_config3()
+    make_hetero()
     make_lais()
     make_uniform()
     make_tpais()

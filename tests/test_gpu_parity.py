@@ -582,6 +582,27 @@ def test_mpmc_paper_covariance_adapts():
         CMixturePMC(dict(params, dims=9, space_min=np.full(9, -1.0), space_max=np.full(9, 1.0)))
 
 
+def test_heterogeneous_mixture_golden():
+    """CMixtureModel over Gaussian + uniform components (the reference's loop takes any models[], CMixtureModel.py:53-56;
+    round 1 raised NotImplementedError): packed Gaussian sub-mixture + box sub-mixture joined by a device log-sum-exp,
+    against the reference's values (tests/golden/make_golden.py::make_hetero). A zero-weight component contributes
+    nothing; points outside every box and far from every Gaussian keep a finite density from the Gaussians."""
+    from ais_benchmarks_b200.distributions import CMixtureModel, CMultivariateNormal, CMultivariateUniform
+    g = load_golden("hetero")
+    comps = [CMultivariateNormal({"mean": np.array([0.3, -0.2]), "sigma": np.diag([0.05, 0.02])}),
+             CMultivariateUniform({"center": np.array([-0.4, 0.1]), "radius": np.array([0.3, 0.2])}),
+             CMultivariateNormal({"mean": np.array([-0.5, 0.5]), "sigma": np.array([[0.04, 0.01], [0.01, 0.03]])}),
+             CMultivariateUniform({"center": np.array([0.5, 0.5]), "radius": np.array([0.25])}),
+             CMultivariateNormal({"mean": np.array([0.9, 0.9]), "sigma": np.diag([0.01, 0.01])})]
+    mix = CMixtureModel({"models": comps, "weights": g["w"].copy(), "dims": 2, "support": [[-1, -1], [1, 1]]})
+    assert rel_err(mix.log_prob(g["x"]), g["logp"]) < LOGP_TOL, rel_err.last
+    assert np.allclose(mix.prob(g["x"]), g["prob"], rtol=1e-5, atol=1e-300)
+    s = mix.sample(2000)
+    assert s.shape == (2000, 2) and np.isfinite(mix.log_prob(s)).all()
+    in_box = np.all(np.abs(s - np.array([-0.4, 0.1])) <= np.array([0.3, 0.2]), axis=1).mean()
+    assert 0.15 < in_box < 0.40           # ~0.2 from the first box + the Gaussian mass that overlaps it
+
+
 def test_lais_chains_golden():
     from ais_benchmarks_b200.sampling_methods import CLayeredAIS
     g = load_golden("lais")
