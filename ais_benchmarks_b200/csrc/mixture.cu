@@ -210,103 +210,136 @@ __global__ void fast_merge_kernel(const float* __restrict__ ws_m, const float* _
   if (fast_needs_exact(ws_u2[p], M, lp)) list[atomicAdd(list_n, 1ull)] = p;
 }
 
-// Exact (centred-form) re-evaluation of the listed points: out[list[k]] = log p(x[list[k]]) for k_begin <= k < *list_n
-// (at most k_count entries from k_begin on). Same arithmetic as logpdf_kernel<ISO_SHARED, DP, false>. The list is
-// normally a few thousand points long, far too few point tiles to fill the machine, so the component range is split
-// nsplit ways (grid.x = tiles * nsplit): partial (m, S) go to ws[split * k_count + (k - k_begin)] and
-// subset_merge_kernel finishes. CTAs beyond the end of the list exit at once, so the launch can cover the worst case
-// at no cost when the list is short. nsplit == 1 writes the result directly (used for the entries beyond the split
-// path's capacity when almost everything is listed).
+// Exact (centred-form) re-evaluation of the listed points: out[list[k]] = log p(x[list[k]]) for k < *list_n. Same
+// arithmetic as logpdf_kernel<ISO_SHARED, DP, false>. The length of the list is only known on the device (normally a few
+// hundred to a few thousand points, far too few point tiles to fill the machine), so the launch has a FIXED grid of
+// kSubsetGrid CTAs and every CTA derives the same plan from *list_n: the component range is split nsp ways so that
+// tiles * nsp fills the grid (>= 256 components per split, at most kSubsetMaxSplit), work item w = (tile w % tiles,
+// split w / tiles); partial (m, S) go to ws[split * tiles * tile_pts + k] and subset_merge_kernel finishes. With more
+// tiles than CTAs (nearly everything listed) nsp = 1, the CTAs stride over the tiles and write the result directly.
+// History: unsplit / 64 splits / 256 splits of the first 8192 entries took 58 / 2.7 / 1.1 ms for the 387 points a rank
+// of an 8-GPU job lists (255 CTAs of 4 warps, 1-2 per SM) -- a fixed cost that did not shrink with the number of ranks.
+constexpr int kSubsetGrid = 4096;
+constexpr int kSubsetMaxSplit = 1024;
+constexpr int64_t kSubsetWs = static_cast<int64_t>(kSubsetGrid) * kThreads * 4;   // floats per partial array
+
+struct SubsetPlan {
+  int64_t cnt, tiles, cps;   // list entries, point tiles, components per split
+  int nsp;
+};
+
+__device__ __forceinline__ SubsetPlan subset_plan(const unsigned long long* __restrict__ list_n, int64_t n, int64_t KP,
+                                                  int tile_pts, int grid) {
+  SubsetPlan p;
+  p.cnt = static_cast<int64_t>(*list_n) < n ? static_cast<int64_t>(*list_n) : n;
+  p.tiles = (p.cnt + tile_pts - 1) / tile_pts;
+  const int64_t units = KP / AISB_COMP_ALIGN;
+  int64_t nsp = p.tiles > 0 ? grid / p.tiles : 1;
+  if (nsp > units / 8) nsp = units / 8;
+  if (nsp > kSubsetMaxSplit) nsp = kSubsetMaxSplit;
+  if (nsp < 1) nsp = 1;
+  p.cps = (units + nsp - 1) / nsp * AISB_COMP_ALIGN;
+  p.nsp = static_cast<int>((KP + p.cps - 1) / p.cps);
+  return p;
+}
+
 template <int DP>
 __global__ void __launch_bounds__(kThreads, DP <= 8 ? AISB_MIN_CTAS_SMALL : 1)
     logpdf_subset_kernel(const float* __restrict__ x, int64_t n, PassArgs mix, const int64_t* __restrict__ list,
-                         const unsigned long long* __restrict__ list_n, int64_t k_begin, int64_t k_count, int nsplit,
-                         int64_t comps_per_split, int64_t ntiles, float* __restrict__ ws_m, float* __restrict__ ws_S,
-                         float* __restrict__ out) {
+                         const unsigned long long* __restrict__ list_n, float* __restrict__ ws_m,
+                         float* __restrict__ ws_S, float* __restrict__ out) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[kStages];
   __shared__ OuterAcc outer;
   constexpr int E = points_per_thread(DP);
-  int64_t cnt = static_cast<int64_t>(*list_n) < n ? static_cast<int64_t>(*list_n) : n;
-  if (cnt > k_begin + k_count) cnt = k_begin + k_count;
-  const int64_t tile = blockIdx.x % ntiles, split = blockIdx.x / ntiles;
-  const int64_t tile_base = k_begin + tile * (kThreads * E);
-  if (tile_base >= cnt) return;
+  const SubsetPlan plan = subset_plan(list_n, n, mix.KP, kThreads * E, static_cast<int>(gridDim.x));
+  const int64_t nwork = plan.tiles * plan.nsp;
+  if (static_cast<int64_t>(blockIdx.x) >= nwork) return;
   ring_init(bars);
-  float xr[E][DP];
-  int64_t kidx[E];
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    const int64_t k = tile_base + e * kThreads + threadIdx.x;
-    const int64_t p = list[k < cnt ? k : cnt - 1];
-    kidx[e] = k < cnt ? k : -1;
-    if constexpr (DP >= 4) {
-      const float4* r = reinterpret_cast<const float4*>(x + p * DP);
-#pragma unroll
-      for (int q = 0; q < DP / 4; ++q) {
-        const float4 f = __ldg(r + q);
-        xr[e][4 * q + 0] = f.x;
-        xr[e][4 * q + 1] = f.y;
-        xr[e][4 * q + 2] = f.z;
-        xr[e][4 * q + 3] = f.w;
-      }
-    } else {
-      const float2 f = __ldg(reinterpret_cast<const float2*>(x + p * 2));
-      xr[e][0] = f.x;
-      xr[e][1] = f.y;
-    }
-  }
-  float m[E], S[E];
   uint32_t it = 0;
-  const int64_t c_begin = split * comps_per_split;
-  const int64_t c_end = c_begin + comps_per_split < mix.KP ? c_begin + comps_per_split : mix.KP;
-  mixture_pass<AISB_COV_ISO_SHARED, DP, E, false>(mix.rows, nullptr, c_begin, c_end, mix.a_iso, smem, bars, outer, it, xr,
-                                                  m, S);
+  for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const int64_t tile = w % plan.tiles, split = w / plan.tiles;
+    const int64_t tile_base = tile * (kThreads * E);
+    float xr[E][DP];
+    int64_t kidx[E];
 #pragma unroll
-  for (int e = 0; e < E; ++e) {
-    if (kidx[e] < 0) continue;
-    if (nsplit == 1) {
-      out[list[kidx[e]]] = lse_finish(m[e], S[e]) + mix.uniform_offset;
-    } else {
-      ws_m[split * k_count + (kidx[e] - k_begin)] = m[e];
-      ws_S[split * k_count + (kidx[e] - k_begin)] = S[e];
+    for (int e = 0; e < E; ++e) {
+      const int64_t k = tile_base + e * kThreads + threadIdx.x;
+      const int64_t p = list[k < plan.cnt ? k : plan.cnt - 1];
+      kidx[e] = k < plan.cnt ? k : -1;
+      if constexpr (DP >= 4) {
+        const float4* r = reinterpret_cast<const float4*>(x + p * DP);
+#pragma unroll
+        for (int q = 0; q < DP / 4; ++q) {
+          const float4 f = __ldg(r + q);
+          xr[e][4 * q + 0] = f.x;
+          xr[e][4 * q + 1] = f.y;
+          xr[e][4 * q + 2] = f.z;
+          xr[e][4 * q + 3] = f.w;
+        }
+      } else {
+        const float2 f = __ldg(reinterpret_cast<const float2*>(x + p * 2));
+        xr[e][0] = f.x;
+        xr[e][1] = f.y;
+      }
+    }
+    float m[E], S[E];
+    const int64_t c_begin = split * plan.cps;
+    const int64_t c_end = c_begin + plan.cps < mix.KP ? c_begin + plan.cps : mix.KP;
+    mixture_pass<AISB_COV_ISO_SHARED, DP, E, false>(mix.rows, nullptr, c_begin, c_end, mix.a_iso, smem, bars, outer, it,
+                                                    xr, m, S);
+    const int64_t stride = plan.tiles * (kThreads * E);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if (kidx[e] < 0) continue;
+      if (plan.nsp == 1) {
+        out[list[kidx[e]]] = lse_finish(m[e], S[e]) + mix.uniform_offset;
+      } else {
+        ws_m[split * stride + kidx[e]] = m[e];
+        ws_S[split * stride + kidx[e]] = S[e];
+      }
     }
   }
 }
 
-__global__ void subset_merge_kernel(const float* __restrict__ ws_m, const float* __restrict__ ws_S, int nsplit,
-                                    int64_t k_begin, int64_t k_count, int64_t n, const int64_t* __restrict__ list,
+__global__ void subset_merge_kernel(const float* __restrict__ ws_m, const float* __restrict__ ws_S, int64_t n,
+                                    int64_t KP, int tile_pts, int grid, const int64_t* __restrict__ list,
                                     const unsigned long long* __restrict__ list_n, float add, float* __restrict__ out) {
-  const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;   // position inside this tier
-  int64_t cnt = static_cast<int64_t>(*list_n) < n ? static_cast<int64_t>(*list_n) : n;
-  cnt -= k_begin;
-  if (cnt > k_count) cnt = k_count;
-  if (k >= cnt) return;
-  float M = kNegBig;
-  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, ws_m[s * k_count + k]);
-  float S = 0.f;
-  for (int s = 0; s < nsplit; ++s) S += ws_S[s * k_count + k] * ex2(ws_m[s * k_count + k] - M);
-  out[list[k_begin + k]] = lse_finish(M, S) + add;
+  const SubsetPlan plan = subset_plan(list_n, n, KP, tile_pts, grid);
+  if (plan.nsp == 1) return;   // written directly
+  const int64_t stride = plan.tiles * tile_pts;
+  // one warp per list entry (up to kSubsetMaxSplit partials each): lanes stride over the splits
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); k < plan.cnt; k += nwarps) {
+    float M = kNegBig;
+    for (int s = lane; s < plan.nsp; s += 32) M = fmaxf(M, ws_m[s * stride + k]);
+    M = warp_max(M);
+    float S = 0.f;
+    for (int s = lane; s < plan.nsp; s += 32) S += ws_S[s * stride + k] * ex2(ws_m[s * stride + k] - M);
+    S = warp_sum(S);
+    if (lane == 0) out[list[k]] = lse_finish(M, S) + add;
+  }
 }
 
-// Exact re-evaluation tiers: the first kSubsetCapA list entries with the component range split kSubsetSplitA ways (a
-// list of a few thousand points is 6 point tiles: unsplit, or split 64 ways, the re-evaluation ran for 58 / 2.7 ms on an
-// otherwise idle GPU -- a fixed cost that does not shrink with the number of ranks), the next kSubsetCapB entries split
-// kSubsetSplitB ways, the rest (almost everything listed: the machine is full anyway) unsplit. The tiers run back to back
-// and share one partials buffer of kSubsetWs floats per array.
-constexpr int64_t kSubsetCapA = 1 << 13;
-constexpr int kSubsetSplitA = 256;
-constexpr int64_t kSubsetCapB = 1 << 16;
-constexpr int kSubsetSplitB = 32;
-constexpr int64_t kSubsetWs = kSubsetCapA * kSubsetSplitA > kSubsetCapB * kSubsetSplitB ? kSubsetCapA * kSubsetSplitA
-                                                                                        : kSubsetCapB * kSubsetSplitB;
 // Interleaved component splits of the fast kernel. A CTA (one warp, 128 points) that swept all 1e6 components would run
 // for ~100 ms, and CTAs differ 3-4x in how much they fold: with few, long CTAs the SMs drain unevenly at the end of the
 // launch (measured: +3.7 ms on a 190 ms launch at 5 splits; at full size 375.2 / 373.0 / 373.3 / 374.8 ms with 3 / 5 / 8 / 16
-// splits). The grid is therefore cut until it has kFastWaves waves of
-// resident CTAs (capped at kFastMaxSplit: every split starts its running maxima from scratch, +0.5 % folds per split).
-constexpr int kFastMaxSplit = 16;
+// splits). The grid is therefore cut until it has kFastWaves waves of resident CTAs, capped at kFastMaxSplit (the
+// splits exchange their running minima, so a split costs a partial (m, S, u2) record per point and little else).
+// A rank of an 8-GPU job holds 125 000 points = 981 tiles: at 16 splits that is 6.6 waves of 7 ms CTAs and the SMs
+// idle ~2 ms of a 48 ms launch at its end; at 48 splits the waves are 20 and a third as long.
+constexpr int kFastMaxSplit = 64;
 constexpr int kFastWaves = 20;
+constexpr int64_t kFastCtaTarget = 148 * 16 * kFastWaves;   // B200: 148 SMs x 16 resident single-warp CTAs
+
+// Most splits a launch over n points asks for (sizes the scratch buffer; independent of the mixture)
+static int64_t fast_split_cap(int64_t n) {
+  const int64_t ntiles = (n + kScreenThreads * 4 - 1) / (kScreenThreads * 4);
+  int64_t want = ntiles > 0 ? (kFastCtaTarget + ntiles - 1) / ntiles : 1;
+  if (want > kFastMaxSplit) want = kFastMaxSplit;
+  return want < 1 ? 1 : want;
+}
 
 // h_j = ||b_j||^2 / (2 a) per packed component (padding rows included) and, behind the vector, max_{j < K} ||b_j||^2
 __global__ void kde_screen_pack_kernel(const float* __restrict__ rows, int64_t K, int64_t KP, int DP, float inv2a,
@@ -565,37 +598,16 @@ static int launch_fast_t(const float* x, int64_t n, const PassArgs& mix, int nsp
                                                                               mix.uniform_offset, out, list, list_n);
     AISB_LAUNCH_CHECK("fast_merge_kernel");
   }
-  // exact re-evaluation of the listed points (no-op launches when the list is empty), in tiers (see kSubsetCapA)
+  // exact re-evaluation of the listed points: one fixed-size launch that plans itself from the list length on the device
+  // (CTAs without work exit at once) and its merge
   if (!(dbg & 4)) {
     constexpr size_t smem_x = pass_smem_bytes(AISB_COV_ISO_SHARED, DP, false);
-    const int64_t tile_pts = kThreads * E;
-    const int64_t units = mix.KP / AISB_COMP_ALIGN;
-    int64_t k0 = 0;
-    const int64_t caps[2] = {kSubsetCapA, kSubsetCapB};
-    const int splits[2] = {kSubsetSplitA, kSubsetSplitB};
-    for (int tier = 0; tier < 2 && k0 < n; ++tier) {
-      const int64_t cap = n - k0 < caps[tier] ? n - k0 : caps[tier];
-      int64_t nsp = units / 8;                       // >= 256 components per split
-      nsp = nsp < 1 ? 1 : (nsp > splits[tier] ? splits[tier] : nsp);
-      const int64_t cps = (units + nsp - 1) / nsp * AISB_COMP_ALIGN;
-      nsp = (mix.KP + cps - 1) / cps;
-      const int64_t tiles = (cap + tile_pts - 1) / tile_pts;
-      logpdf_subset_kernel<DP><<<static_cast<unsigned>(tiles * nsp), kThreads, smem_x, st>>>(
-          x, n, mix, list, list_n, k0, cap, static_cast<int>(nsp), cps, tiles, sub_m, sub_S, out);
-      AISB_LAUNCH_CHECK("logpdf_subset_kernel");
-      if (nsp > 1) {
-        subset_merge_kernel<<<static_cast<unsigned>((cap + 255) / 256), 256, 0, st>>>(
-            sub_m, sub_S, static_cast<int>(nsp), k0, cap, n, list, list_n, mix.uniform_offset, out);
-        AISB_LAUNCH_CHECK("subset_merge_kernel");
-      }
-      k0 += cap;
-    }
-    if (k0 < n) {
-      const int64_t tiles = (n - k0 + tile_pts - 1) / tile_pts;
-      logpdf_subset_kernel<DP><<<static_cast<unsigned>(tiles), kThreads, smem_x, st>>>(
-          x, n, mix, list, list_n, k0, n - k0, 1, mix.KP, tiles, nullptr, nullptr, out);
-      AISB_LAUNCH_CHECK("logpdf_subset_kernel(rest)");
-    }
+    static_assert(kThreads * E <= kThreads * 4, "kSubsetWs assumes at most 4 points per thread");
+    logpdf_subset_kernel<DP><<<kSubsetGrid, kThreads, smem_x, st>>>(x, n, mix, list, list_n, sub_m, sub_S, out);
+    AISB_LAUNCH_CHECK("logpdf_subset_kernel");
+    subset_merge_kernel<<<256, 256, 0, st>>>(sub_m, sub_S, n, mix.KP, kThreads * E, kSubsetGrid, list, list_n,
+                                            mix.uniform_offset, out);
+    AISB_LAUNCH_CHECK("subset_merge_kernel");
   }
   if (stats) {
     AISB_CUDA_CHECK(cudaMemcpyAsync(stats + 2, list_n, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
@@ -870,7 +882,8 @@ extern "C" int aisb_mixture_logpdf_screened_f32(const float* d_x, int64_t n, con
 extern "C" size_t aisb_kde_fast_scratch_bytes(int64_t n) {
   if (n < 0) return 0;
   return static_cast<size_t>(n) * (sizeof(int64_t) + sizeof(float)) + 2 * sizeof(float) * kSubsetWs +
-         2 * sizeof(float) * kFastMaxSplit * static_cast<size_t>(n) + sizeof(uint32_t) * static_cast<size_t>(n) + 1024;
+         2 * sizeof(float) * static_cast<size_t>(fast_split_cap(n)) * static_cast<size_t>(n) +
+         sizeof(uint32_t) * static_cast<size_t>(n) + 1024;
 }
 
 extern "C" int aisb_mixture_logpdf_fast_f32(const float* d_x, int64_t n, const aisb_packed_mixture* mix,
@@ -898,13 +911,13 @@ extern "C" int aisb_mixture_logpdf_fast_f32(const float* d_x, int64_t n, const a
   const int64_t KPc = aisb_padded_components(mix->K);
   const int64_t ntiles = (n + kScreenThreads * 4 - 1) / (kScreenThreads * 4);
   const int64_t nchunks = (KPc + kScreenChunk - 1) / kScreenChunk;
-  int64_t want = (static_cast<int64_t>(sm_count()) * 16 * kFastWaves + ntiles - 1) / ntiles;
+  const int64_t cap = fast_split_cap(n);
+  int64_t want = cap;
   if (want > nchunks / 16) want = nchunks / 16;
-  if (want > kFastMaxSplit) want = kFastMaxSplit;
   if (want < 1) want = 1;
   if (const char* e = getenv("AISB_SCREEN_NSPLIT")) {  // timing experiments
     const int64_t v = atoll(e);
-    if (v >= 1 && v <= kFastMaxSplit && v <= nchunks) want = v;
+    if (v >= 1 && v <= cap && v <= nchunks) want = v;
   }
   const int nsplit = static_cast<int>(want);
   (void)d_workspace;
@@ -918,8 +931,8 @@ extern "C" int aisb_mixture_logpdf_fast_f32(const float* d_x, int64_t n, const a
   float* sub_S = sub_m + kSubsetWs;
   Workspace ws{};
   ws.ws_m = sub_S + kSubsetWs;
-  ws.ws_S = ws.ws_m + static_cast<size_t>(kFastMaxSplit) * n;
-  uint32_t* gmin = reinterpret_cast<uint32_t*>(ws.ws_S + static_cast<size_t>(kFastMaxSplit) * n);
+  ws.ws_S = ws.ws_m + static_cast<size_t>(cap) * n;
+  uint32_t* gmin = reinterpret_cast<uint32_t*>(ws.ws_S + static_cast<size_t>(cap) * n);
   const PassArgs a = pass_args(mix);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (DP) {
