@@ -6,6 +6,7 @@ falls back to the CPU: without a CUDA device or without the built library the ca
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -74,14 +75,37 @@ def to_device_points(x, dims):
 HOST_CAST_MAX = 1 << 16   # elements up to which a float64 -> float32 cast on the host is cheaper than moving 8-byte values
 
 
-def upload_f32(x):
-    """numpy array -> float32 contiguous CUDA tensor. The reference hands over float64 (README.md:41-43): small arrays
-    are cast on the host; large ones are uploaded as they are and cast by the device (numpy's single-threaded astype
-    runs at ~1.5 GB/s, an order of magnitude below the host link, and would otherwise dominate a 1e6 x 8 evaluation)."""
+def _upload_threads():
+    """Host threads of the staged uploader: AISB_UPLOAD_THREADS, else the cores this rank can claim (at most 4: the
+    narrowing loop saturates the host link from 3-4 cores)."""
+    env = os.environ.get("AISB_UPLOAD_THREADS")
+    if env:
+        return max(1, min(8, int(env)))
+    local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return max(1, min(4, (os.cpu_count() or 1) // local))
+
+
+def upload_f32(x, out=None):
+    """numpy array -> float32 contiguous CUDA tensor (`out`: a contiguous float32 CUDA tensor of the same size to fill
+    instead of a new one). The reference hands over float64 (README.md:41-43): small arrays are cast on the host and
+    copied by torch; large float arrays go through the library's staged uploader (aisb_upload_as_f32: several host
+    threads narrow chunks into pinned staging buffers while the previous chunks are in flight -- numpy's
+    single-threaded astype runs at ~1.5 GB/s and a pageable copy at 7-15 GB/s, either would dominate a 1e6 x 8
+    evaluation)."""
     x = np.ascontiguousarray(x)
-    if x.dtype == np.float32 or x.size <= HOST_CAST_MAX or x.dtype.kind != "f":
-        return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(device(), non_blocking=False)
-    return torch.from_numpy(x).to(device(), non_blocking=False).to(torch.float32)
+    if out is not None:
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == x.size
+    if x.size <= HOST_CAST_MAX or x.dtype not in (np.float64, np.float32):
+        t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(device(), non_blocking=False)
+        if out is None:
+            return t
+        out.copy_(t.reshape(out.shape))
+        return out
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float32, device=device())
+    check(_lib.load().aisb_upload_as_f32(x.ctypes.data, 1 if x.dtype == np.float64 else 0, x.size, _ptr(out),
+                                         _upload_threads(), stream_ptr()))
+    return out
 
 
 def from_device(t, as_numpy):
@@ -184,7 +208,6 @@ def morton_keys(x):
 def morton_order(x):
     """Permutation (int64 CUDA [n]) that puts the rows of x (float32 CUDA [n, D]) in Z-order over their bounding box:
     morton_bits(D) most significant bits per coordinate, interleaved; key kernel + one 32-bit sort. No host sync."""
-    import os
     if os.environ.get("AISB_MORTON_TORCH") == "1" or not x.is_cuda:
         return morton_order_torch(x)
     return torch.sort(morton_keys(x)).indices
@@ -266,7 +289,6 @@ def kde_mode():
     "fast" (default)  recentred expanded form + exact re-evaluation of the points whose error estimate is too large
     "screen"          expanded-form screen + exact centred refinement of every group that matters
     "ordered"         centred form for every pair, fold skipping only (the round-1 kernel)"""
-    import os
     return os.environ.get("AISB_KDE_MODE", "fast")
 
 

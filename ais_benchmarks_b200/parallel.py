@@ -61,6 +61,28 @@ def spatial_shard(x, rank=None, world_size=None):
     return x[mine], mine
 
 
+def upload_replicated(a):
+    """float32 CUDA copy of a numpy array that is IDENTICAL on every rank (an SPMD caller's KDE samples, say): every
+    rank pushes only its 1/world slice through the host link (_device.upload_f32) and the slices are exchanged with an
+    in-place all-gather over NVLink. The ranks of a node share the host's memory bandwidth and cores: 8 ranks each
+    staging the same 64 MB of float64 took 14 ms of a 61 ms configs[3] step, against 47 ms with everything resident.
+    Falls back to a plain upload without a process group, under gloo, or for small arrays. The result is bit-identical
+    to _device.upload_f32(a) -- provided the caller's promise holds."""
+    a = np.ascontiguousarray(a)
+    rank, ws = world()
+    if ws == 1 or dist.get_backend() != "nccl" or a.size < ws * _device.HOST_CAST_MAX:
+        return _device.upload_f32(a)
+    flat = a.reshape(-1)
+    per = (flat.size + ws - 1) // ws
+    out = torch.empty(ws * per, dtype=torch.float32, device=_device.device())
+    lo, hi = min(flat.size, rank * per), min(flat.size, (rank + 1) * per)
+    mine = out[rank * per:(rank + 1) * per]
+    if hi > lo:
+        _device.upload_f32(flat[lo:hi], out=mine[:hi - lo])
+    dist.all_gather_into_tensor(out, mine)            # in place: this rank's slice already sits where it belongs
+    return out[:flat.size].reshape(a.shape)
+
+
 def _comm_device():
     if dist.get_backend() == "nccl":
         return _device.device()

@@ -24,6 +24,8 @@ class CSamplingMethod(metaclass=ABCMeta):
         self._name = params["name"] if "name" in params.keys() else "GenericSamplingMethod"
         # True: importance_sample()/sample() return CUDA tensors instead of numpy arrays
         self.device_outputs = bool(params.get("device_outputs", False))
+        # multi-GPU SPMD callers: `samples` assigned through the numpy setter are identical on every rank (see setter)
+        self.replicated_samples = bool(params.get("replicated_samples", False))
 
         assert self.space_max.shape == self.space_min.shape
         assert self.ndims == len(self.space_max)
@@ -60,7 +62,13 @@ class CSamplingMethod(metaclass=ABCMeta):
         self._samples_np = val
         if val.size:
             _device.require_cuda()
-            self._samples_dev = _device.upload_f32(val.reshape(-1, self.ndims))
+            rows = val.reshape(-1, self.ndims)
+            if getattr(self, "replicated_samples", False):
+                # SPMD caller's promise: every rank assigns the SAME array -> each stages a slice, NVLink does the rest
+                from .. import parallel
+                self._samples_dev = parallel.upload_replicated(rows)
+            else:
+                self._samples_dev = _device.upload_f32(rows)
         else:
             self._samples_dev = None
 

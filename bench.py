@@ -236,9 +236,10 @@ def run_cuda(args):
 
     def kde_step_numpy():
         np.random.seed(1234)       # the KDE resampling draws its seed from numpy: every rank must build the same KDE
-        q = _KdeSampler({"space_min": sup[0], "space_max": sup[1], "dims": D, "n_samples_kde": n_c})
+        q = _KdeSampler({"space_min": sup[0], "space_max": sup[1], "dims": D, "n_samples_kde": n_c,
+                         "replicated_samples": world > 1})               # every rank assigns the same array
         q.bw = c["bw"]
-        q.samples = centres_np                                           # H2D of n_c x 8 float64 + device cast
+        q.samples = centres_np       # H2D: N = 1 the whole array; N > 1 a 1/N slice per rank + all-gather over NVLink
         return metric_np.compute_from_samples(target, q, x_np)           # H2D of the points, KDE build, kernels, D2H
 
     for _ in range(args.warmup):
@@ -526,18 +527,24 @@ def run_cuda(args):
                              "%.0f MB of points are read once" % (n_c * 30.0 / 8 / 4, n_c * D * 4 / 1e6, n_e * D * 4 / 1e6),
                        "kld": kld_val, "scale": scale},
             "e2e": {"value": total_pairs / (kde_e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(centres_np.nbytes + x_np.nbytes), "d2h_bytes_per_step": 64,
+                    # per rank, bytes crossing the host link: the float64 arrays are narrowed to float32 by the staged
+                    # uploader on the way (aisb_upload_as_f32); at N > 1 each rank stages 1/N of the centres and the ranks
+                    # all-gather the rest over NVLink (replicated_samples)
+                    "h2d_bytes_per_step": int(centres_np.nbytes // 2 // world + x_np.nbytes // 2),
+                    "d2h_bytes_per_step": 64,
+                    "host_bytes_read_per_step": int(centres_np.nbytes // world + x_np.nbytes),
                     "ms_per_step": kde_e2e_ms,
-                    "api": "sampler.samples = centres (numpy float64); CKLDivergence().compute_from_samples(target, "
-                           "sampler, x) with x numpy float64 -- pageable host memory, per rank its shard of x"},
+                    "api": "sampler.samples = centres (numpy float64, the same array on every rank); "
+                           "CKLDivergence().compute_from_samples(target, sampler, x) with x numpy float64 -- pageable "
+                           "host memory, per rank its shard of x"},
             "e2e_pinned_f32": {"value": total_pairs / (kde_pinned_ms * 1e-3), "unit": UNIT,
                                "h2d_bytes_per_step": int(centres_pin.numel() * 4 + x_pin.numel() * 4),
                                "d2h_bytes_per_step": 64, "ms_per_step": kde_pinned_ms},
             # kernels of libais_b200.so per resident step (profiles/r2_launches_bench_final.csv): bounding box + Morton keys
-            # for the centres and for the points (4), kde_pack, logpdf_fast, fast_merge, 3 x logpdf_subset + 2 x
-            # subset_merge (exact re-evaluation tiers), target logpdf, kld_partials + its merge; torch adds a radix sort
-            # and a gather per side
-            "gpu_launches": 15 * args.steps,
+            # for the centres and for the points (4), kde_pack, logpdf_fast, fast_merge, logpdf_subset + subset_merge
+            # (exact re-evaluation of the listed points), target logpdf, kld_partials + its merge; torch adds a radix
+            # sort and a gather per side
+            "gpu_launches": 12 * args.steps,
             "clocks": clock_info,
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp32_peak_tflops,

@@ -382,6 +382,14 @@ int aisb_morton_keys_f32(const float* d_x, int64_t n, int32_t D, int32_t bits, c
  *      path of every KDE evaluation on every rank. */
 int aisb_morton_keys_auto_f32(const float* d_x, int64_t n, int32_t D, int32_t bits, uint32_t* d_box, int32_t* d_keys,
                               void* stream);
+/*  aisb_upload_as_f32: h_src (HOST, pageable or pinned; `count` float64 values if src_is_f64 else float32) -> d_dst
+ *      (DEVICE, float32 [count]). The reference-facing classes are handed numpy float64 (README.md:41-43,
+ *      benchmark/CBenchmark.py:483-517 pass float64 samples and evaluation points); this replaces the pageable
+ *      cudaMemcpy + cast kernel behind `to_device_points`: `threads` host threads (1..8) narrow their chunks into their own
+ *      pinned staging buffers and queue the DMA of one buffer while filling the other. Ordered after the work already
+ *      queued on `stream`; when the call returns h_src has been read completely and the data is in HBM. */
+int aisb_upload_as_f32(const void* h_src, int32_t src_is_f64, int64_t count, float* d_dst, int32_t threads,
+                       void* stream);
 /*  aisb_sample_mixture_f32: ancestral draws from a full-covariance Gaussian mixture, given the component of every draw:
  *      out[i, :] = means[idx[i], :] + chol[idx[i]] z_i,  z_i ~ N(0, I)   (chol: lower-triangular factors, row-major
  *      [K, D, D]). Replaces CMixtureModel.sample (CMixtureModel.py:79-89) over CMultivariateNormal.sample

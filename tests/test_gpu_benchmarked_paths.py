@@ -222,3 +222,36 @@ def test_lais_config3_shape_against_reference_iteration():
     s.mcmc_step(target, torch.from_numpy(g["l_delta"]).cuda().float(), torch.from_numpy(g["l_u"]).cuda().float())
     after = s.proposal_means().cpu().numpy()
     assert np.allclose(after, g["l_after"], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_staged_upload_is_numpy_astype_float32(dtype, monkeypatch):
+    """aisb_upload_as_f32 (the host -> HBM leg of every numpy call: reference arrays are float64, README.md:41-43) is
+    bit-identical to numpy's astype(float32) for every thread count, chunk boundary and special value, keeps the
+    ordering contract with the caller's stream, and leaves the source untouched."""
+    from ais_benchmarks_b200 import _device
+    rs = np.random.RandomState(11)
+    chunk = 1 << 20
+    for count in (_device.HOST_CAST_MAX + 1, chunk - 1, chunk, chunk + 1, 3 * chunk + 12345, 9 * chunk + 7):
+        x = (rs.standard_normal(count) * 10.0 ** rs.randint(-30, 30, count)).astype(dtype)
+        x[:8] = [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, 3.4028235e38, 1e300 if dtype == np.float64 else 1e30]
+        keep = x.copy()
+        with np.errstate(over="ignore"):
+            want = x.astype(np.float32)
+        for threads in (1, 2, 3, 5, 8):
+            monkeypatch.setenv("AISB_UPLOAD_THREADS", str(threads))
+            got = _device.upload_f32(x).cpu().numpy()
+            assert got.dtype == np.float32 and got.shape == x.shape
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (count, threads)
+        assert np.array_equal(x.view(np.uint8), keep.view(np.uint8))
+    # 2-D points through the public entry point, queued behind work on the caller's stream that uses the same memory
+    pts = rs.rand(300_000, 8)
+    scratch = torch.empty(300_000, 8, device="cuda")
+    for _ in range(3):
+        scratch.normal_()                      # pending kernel on the current stream; its block may be handed out again
+        del scratch
+        dev, was_numpy = _device.to_device_points(pts, 8)
+        assert was_numpy and torch.equal(dev.cpu(), torch.from_numpy(pts.astype(np.float32)))
+        scratch = torch.empty(300_000, 8, device="cuda")
+    with pytest.raises(_device.AisbError):
+        _device.check(_device._lib.load().aisb_upload_as_f32(None, 1, 10, _device._ptr(scratch), 2, None))
