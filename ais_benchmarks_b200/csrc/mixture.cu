@@ -144,8 +144,14 @@ __device__ __forceinline__ bool fast_needs_exact(float u2, float t_max, float lo
   return eps > kFastTol * fmaxf(1.f, fabsf(logp));   // NaN / inf results compare false: nothing to refine there
 }
 
+#ifndef AISB_FAST_CTAS
+// resident single-warp CTAs per SM the fast kernel is compiled for (DP <= 8). 16 -> 128 registers, no spills. Measured
+// with 20 (96 registers, 72 B of spills, 21 resident): 368.1 vs 366.0 ms at configs[3] -- more warps do not help, the
+// four warps of a scheduler already queue for its FMA pipe (math_pipe_throttle is the top stall).
+#define AISB_FAST_CTAS 16
+#endif
 template <int DP, bool COUNT>
-__global__ void __launch_bounds__(kScreenThreads, DP <= 8 ? 16 : 8)
+__global__ void __launch_bounds__(kScreenThreads, DP <= 8 ? AISB_FAST_CTAS : 8)
     logpdf_fast_kernel(const float* __restrict__ x, int64_t n, PassArgs mix, float marg, int nsplit, int64_t ntiles,
                        float* __restrict__ out, float* __restrict__ ws_m, float* __restrict__ ws_S,
                        float* __restrict__ ws_u2, int64_t* __restrict__ list, unsigned long long* __restrict__ list_n,

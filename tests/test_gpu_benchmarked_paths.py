@@ -255,3 +255,56 @@ def test_staged_upload_is_numpy_astype_float32(dtype, monkeypatch):
         scratch = torch.empty(300_000, 8, device="cuda")
     with pytest.raises(_device.AisbError):
         _device.check(_device._lib.load().aisb_upload_as_f32(None, 1, 10, _device._ptr(scratch), 2, None))
+
+
+def test_fast_kde_exact_reevaluation_plans_itself(monkeypatch):
+    """aisb_mixture_logpdf_fast_f32 lists the points whose error estimate is too large and re-evaluates them with ONE
+    fixed-size launch that plans itself from the list length on the device (csrc/mixture.cu: subset_plan). Every plan
+    is exercised against the exact kernel on the same points: nothing or little listed; every point listed with fewer
+    point tiles than CTAs (split component range + merge) and with MORE tiles than CTAs (the CTAs stride over the tiles
+    and write directly). `AISB_FAST_DEBUG=2` (no recentring) on data far from the origin lists every point."""
+    from ais_benchmarks_b200 import _device, _lib
+    from ais_benchmarks_b200._device import _ptr, stream_ptr, check
+    lib = _lib.load()
+    rs = np.random.RandomState(77)
+    D, K, bw = 8, (1 << 16) + 129, 0.02
+    modes = rs.uniform(0.2, 0.8, size=(5, D))
+
+    def draw(m, spread):
+        return (modes[rs.randint(0, 5, size=m)] + spread * rs.standard_normal((m, D))).astype(np.float32)
+
+    def run(n, offset, debug):
+        c = draw(K, 0.1) + np.float32(offset)
+        x = draw(n, 0.2) + np.float32(offset)
+        cd, xd = torch.from_numpy(c).cuda(), torch.from_numpy(x).cuda()
+        mix = _device.DeviceMixture.kde(cd, None, K, bw)
+        assert mix.spatially_ordered
+        xs = xd[_device.morton_order(xd)].contiguous()
+        ws, sc = _device.workspace_for(n, K, D), _device._kde_fast_scratch(n)
+        fast, exact = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
+        stats = torch.zeros(3, dtype=torch.int64, device="cuda")
+        if debug:
+            monkeypatch.setenv("AISB_FAST_DEBUG", str(debug))
+        else:
+            monkeypatch.delenv("AISB_FAST_DEBUG", raising=False)
+        check(lib.aisb_mixture_logpdf_fast_f32(_ptr(xs), n, mix.ref(), _ptr(fast), _ptr(ws), ws.numel(), _ptr(sc),
+                                               sc.numel(), _ptr(stats), stream_ptr()))
+        monkeypatch.delenv("AISB_FAST_DEBUG", raising=False)
+        check(lib.aisb_mixture_logpdf_f32(_ptr(xs), n, mix.ref(), _ptr(exact), _ptr(ws), ws.numel(), stream_ptr()))
+        torch.cuda.synchronize()
+        a, b = fast.double().cpu().numpy(), exact.double().cpu().numpy()
+        fin = np.isfinite(b)
+        assert np.array_equal(np.isfinite(a), fin)
+        dev = float(np.max(np.abs(a[fin] - b[fin]) / np.maximum(1.0, np.abs(b[fin])))) if fin.any() else 0.0
+        return int(stats[2]), dev
+
+    tile = 512                                   # points per CTA of the re-evaluation kernel at D = 8
+    listed, dev = run(70_000, 0.0, 0)            # data at the origin: next to nothing listed
+    assert listed < 70_000 // 20 and dev < 5e-6, (listed, dev)
+    listed, dev = run(70_000, 100.0, 2)          # all listed, 137 tiles < 4096 CTAs: 29-way split + merge
+    assert listed == 70_000 and dev < 2e-6, (listed, dev)
+    listed, dev = run(tile + 1, 100.0, 2)        # two tiles, the second with one point: 1024-way split (the cap)
+    assert listed == tile + 1 and dev < 2e-6, (listed, dev)
+    n_big = 4096 * tile + 3 * tile + 17          # more tiles than CTAs: unsplit, strided
+    listed, dev = run(n_big, 100.0, 2)
+    assert listed == n_big and dev < 2e-6, (listed, dev)
