@@ -266,6 +266,7 @@ def test_fast_kde_exact_reevaluation_plans_itself(monkeypatch):
     from ais_benchmarks_b200 import _device, _lib
     from ais_benchmarks_b200._device import _ptr, stream_ptr, check
     lib = _lib.load()
+    monkeypatch.setattr(_device, "MORTON_MIN_ROWS", 1 << 16)
     rs = np.random.RandomState(77)
     D, K, bw = 8, (1 << 16) + 129, 0.02
     modes = rs.uniform(0.2, 0.8, size=(5, D))
@@ -299,8 +300,8 @@ def test_fast_kde_exact_reevaluation_plans_itself(monkeypatch):
         return int(stats[2]), dev
 
     tile = 512                                   # points per CTA of the re-evaluation kernel at D = 8
-    listed, dev = run(70_000, 0.0, 0)            # data at the origin: next to nothing listed
-    assert listed < 70_000 // 20 and dev < 5e-6, (listed, dev)
+    listed, dev = run(70_000, 0.0, 0)            # recentred: a small minority listed (sparse warps: 5 % here)
+    assert 0 < listed < 70_000 // 5 and dev < 5e-6, (listed, dev)
     listed, dev = run(70_000, 100.0, 2)          # all listed, 137 tiles < 4096 CTAs: 29-way split + merge
     assert listed == 70_000 and dev < 2e-6, (listed, dev)
     listed, dev = run(tile + 1, 100.0, 2)        # two tiles, the second with one point: 1024-way split (the cap)
