@@ -85,6 +85,18 @@ def _upload_threads():
     return max(1, min(4, (os.cpu_count() or 1) // local))
 
 
+def gather_rows(x, idx):
+    """x[idx] for a float32 CUDA matrix and an int64 CUDA index vector (aisb_gather_rows_f32). The caller vouches for
+    the indices (permutations and shard positions computed here); torch's own indexing spends one block per row."""
+    if x.dim() != 2 or x.dtype != torch.float32 or idx.dtype != torch.int64 or not x.is_cuda:
+        return x[idx]
+    x, idx = x.contiguous(), idx.contiguous()
+    out = torch.empty((idx.shape[0], x.shape[1]), dtype=torch.float32, device=x.device)
+    check(_lib.load().aisb_gather_rows_f32(_ptr(x), x.shape[0], x.shape[1], _ptr(idx), idx.shape[0], _ptr(out), None,
+                                           stream_ptr()), "aisb_gather_rows_f32")
+    return out
+
+
 def upload_f32(x, out=None):
     """numpy array -> float32 contiguous CUDA tensor (`out`: a contiguous float32 CUDA tensor of the same size to fill
     instead of a new one). The reference hands over float64 (README.md:41-43): small arrays are cast on the host and
@@ -353,7 +365,7 @@ def mixture_logpdf(x, mix, out=None, points_ordered=False, stats=None):
     if getattr(mix, "spatially_ordered", False) and n >= (1 << 16) and float(n) * mix.K >= MORTON_MIN_PAIRS:
         # components are packed in Z-order: evaluate the points in Z-order too (warp-coherent fold skipping), scatter back
         perm = morton_order(x)
-        xs = x[perm]
+        xs = gather_rows(x, perm)
         tmp = torch.empty(n, dtype=torch.float32, device=x.device)
         _logpdf_ordered(lib, xs, n, mix, tmp, ws, stats)
         out[perm] = tmp

@@ -373,6 +373,58 @@ extern "C" int aisb_morton_keys_auto_f32(const float* d_x, int64_t n, int32_t D,
   return AISB_OK;
 }
 
+// out[i, :] = x[idx[i], :]: one thread per 16-byte piece of a row when rows are whole float4s (D % 4 == 0 and aligned
+// bases), else one thread per element. (torch's index kernel launches one block per ROW for this shape: 0.5 ms for the
+// 1e6 x 8 points of configs[3] under ncu, on the serial path of every KDE evaluation.)
+__global__ void gather_rows_vec_kernel(const float4* __restrict__ x, const int64_t* __restrict__ idx, int64_t m, int q,
+                                       int64_t n_src, float4* __restrict__ out, int* __restrict__ err) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= m * q) return;
+  const int64_t i = t / q;
+  const int c = static_cast<int>(t - i * q);
+  const int64_t r = idx[i];
+  if (r < 0 || r >= n_src) {
+    if (err) atomicAdd(err, 1);
+    return;
+  }
+  out[t] = __ldg(x + r * q + c);
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, int64_t m, int D,
+                                   int64_t n_src, float* __restrict__ out, int* __restrict__ err) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= m * D) return;
+  const int64_t i = t / D;
+  const int d = static_cast<int>(t - i * D);
+  const int64_t r = idx[i];
+  if (r < 0 || r >= n_src) {
+    if (err) atomicAdd(err, 1);
+    return;
+  }
+  out[t] = __ldg(x + r * D + d);
+}
+
+extern "C" int aisb_gather_rows_f32(const float* d_x, int64_t n_src, int32_t D, const int64_t* d_idx, int64_t m,
+                                    float* d_out, int* d_err, void* stream) {
+  if (m < 0 || n_src < 0 || D < 1 || (m > 0 && (!d_x || !d_idx || !d_out))) {
+    set_error("gather_rows: invalid argument (m=%lld n_src=%lld D=%d)", static_cast<long long>(m),
+              static_cast<long long>(n_src), D);
+    return AISB_ERR_INVALID;
+  }
+  if (m == 0) return AISB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool vec = D % 4 == 0 && reinterpret_cast<uintptr_t>(d_x) % 16 == 0 && reinterpret_cast<uintptr_t>(d_out) % 16 == 0;
+  if (vec) {
+    const int q = D / 4;
+    gather_rows_vec_kernel<<<static_cast<unsigned>((m * q + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(d_x), d_idx, m, q, n_src, reinterpret_cast<float4*>(d_out), d_err);
+  } else {
+    gather_rows_kernel<<<static_cast<unsigned>((m * D + 255) / 256), 256, 0, st>>>(d_x, d_idx, m, D, n_src, d_out, d_err);
+  }
+  AISB_LAUNCH_CHECK("gather_rows_kernel");
+  return AISB_OK;
+}
+
 extern "C" int aisb_sample_iso_ctr_f32(const float* d_means, int64_t K, int32_t D, int64_t per, double var,
                                        uint64_t* d_state, float* d_out, void* stream) {
   uint64_t* d_counter = d_state;

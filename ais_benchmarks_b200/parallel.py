@@ -51,14 +51,14 @@ def spatial_shard(x, rank=None, world_size=None):
         rank, world_size = world()
     perm = _device.morton_order(x)
     if world_size == 1:
-        return x[perm], perm
+        return _device.gather_rows(x, perm), perm
     n = x.shape[0]
     nblocks = (n + SPATIAL_BLOCK - 1) // SPATIAL_BLOCK
     mine_blocks = torch.arange(rank, nblocks, world_size, device=x.device)
     pos = (mine_blocks[:, None] * SPATIAL_BLOCK + torch.arange(SPATIAL_BLOCK, device=x.device)[None, :]).reshape(-1)
     pos = pos[pos < n]
     mine = perm[pos]
-    return x[mine], mine
+    return _device.gather_rows(x, mine), mine
 
 
 def upload_replicated(a):

@@ -382,6 +382,11 @@ int aisb_morton_keys_f32(const float* d_x, int64_t n, int32_t D, int32_t bits, c
  *      path of every KDE evaluation on every rank. */
 int aisb_morton_keys_auto_f32(const float* d_x, int64_t n, int32_t D, int32_t bits, uint32_t* d_box, int32_t* d_keys,
                               void* stream);
+/*  aisb_gather_rows_f32: d_out[i, :] = d_x[d_idx[i], :] for i < m (rows of D floats; d_x has n_src rows). Puts point
+ *      sets in Z-order (`x[perm]`) and deals out a rank's block-cyclic share; indices outside [0, n_src) are skipped and
+ *      counted in *d_err (device int, may be null). No reference counterpart (numpy fancy indexing on the host). */
+int aisb_gather_rows_f32(const float* d_x, int64_t n_src, int32_t D, const int64_t* d_idx, int64_t m, float* d_out,
+                         int* d_err, void* stream);
 /*  aisb_upload_as_f32: h_src (HOST, pageable or pinned; `count` float64 values if src_is_f64 else float32) -> d_dst
  *      (DEVICE, float32 [count]). The reference-facing classes are handed numpy float64 (README.md:41-43,
  *      benchmark/CBenchmark.py:483-517 pass float64 samples and evaluation points); this replaces the pageable

@@ -309,3 +309,26 @@ def test_fast_kde_exact_reevaluation_plans_itself(monkeypatch):
     n_big = 4096 * tile + 3 * tile + 17          # more tiles than CTAs: unsplit, strided
     listed, dev = run(n_big, 100.0, 2)
     assert listed == n_big and dev < 2e-6, (listed, dev)
+
+
+def test_gather_rows_kernel():
+    """aisb_gather_rows_f32 (Z-ordering of point sets, block-cyclic shards) equals torch indexing for vector and scalar
+    row widths, repeated indices and empty selections; out-of-range indices are skipped and counted."""
+    from ais_benchmarks_b200 import _device, _lib
+    from ais_benchmarks_b200._device import _ptr, stream_ptr, check
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for D in (1, 3, 4, 8, 12, 32):
+        x = torch.randn(100_003, D, device="cuda", generator=g)
+        for m in (0, 1, 77_777, 250_000):
+            idx = torch.randint(0, x.shape[0], (m,), device="cuda", generator=g)
+            assert torch.equal(_device.gather_rows(x, idx), x[idx])
+        view = x[1:]                                   # base no longer 16-byte aligned for D = 1, 3
+        idx = torch.randperm(view.shape[0], device="cuda", generator=g)
+        assert torch.equal(_device.gather_rows(view, idx), view[idx])
+    x = torch.randn(1000, 8, device="cuda", generator=g)
+    idx = torch.tensor([0, 999, 1000, -1, 5], device="cuda")
+    out = torch.full((5, 8), 7.0, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    check(_lib.load().aisb_gather_rows_f32(_ptr(x), 1000, 8, _ptr(idx), 5, _ptr(out), _ptr(err), stream_ptr()))
+    assert int(err) == 4                               # two bad rows x two float4 pieces each
+    assert torch.equal(out[[0, 1, 4]], x[[0, 999, 5]]) and bool((out[2:4] == 7.0).all())
