@@ -76,13 +76,14 @@ HOST_CAST_MAX = 1 << 16   # elements up to which a float64 -> float32 cast on th
 
 
 def _upload_threads():
-    """Host threads of the staged uploader: AISB_UPLOAD_THREADS, else the cores this rank can claim (at most 4: the
-    narrowing loop saturates the host link from 3-4 cores)."""
+    """Host threads of the staged uploader: AISB_UPLOAD_THREADS, else the cores this rank can claim, at most 8. Sources
+    larger than the host's last-level cache stream from DRAM: 64 MB of float64 take 2.6-4.0 ms with 4 threads and
+    2.0-2.3 ms with 8 on the 16-core host of the B200 box (scripts/upload_timing.py)."""
     env = os.environ.get("AISB_UPLOAD_THREADS")
     if env:
         return max(1, min(8, int(env)))
     local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-    return max(1, min(4, (os.cpu_count() or 1) // local))
+    return max(1, min(8, (os.cpu_count() or 1) // local))
 
 
 def gather_rows(x, idx):

@@ -34,3 +34,19 @@ assert torch.equal(out, ref)
 t2, _ = wall(lambda: torch.from_numpy(x32).to("cuda"))
 print("float32 source: staged 4 threads %.2f ms, torch pageable %.2f ms" % (t, t2))
 print("host cores: %d" % (os.cpu_count() or 0))
+
+# the same upload after the process has been idle / blocked on the GPU for as long as a KDE step lasts
+import ctypes
+y = np.random.RandomState(1).rand(rows, dims)
+for label, idle in (("back to back", None), ("after time.sleep(0.37)", "sleep"), ("after a 0.37 s GPU wait", "gpu")):
+    for th in (4, 8):
+        os.environ["AISB_UPLOAD_THREADS"] = str(th)
+        ts = []
+        for rep in range(4):
+            src = x if rep % 2 == 0 else y
+            if idle == "sleep":
+                time.sleep(0.37)
+            elif idle == "gpu":
+                torch.cuda._sleep(int(0.37 * 1.9e9)); torch.cuda.synchronize()
+            t0 = time.perf_counter(); out = _device.upload_f32(src); torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
+        print("%-26s %d threads: %s ms" % (label, th, " ".join("%.2f" % t for t in ts)))
