@@ -308,11 +308,12 @@ def run_cuda(args):
                         "points_reevaluated_exactly": int(st_h[2]), "points": int(xq.shape[0]),
                         "unit": "64 points x 8 components"}
         del kde_c, xq
-    kde_traffic, kde_traffic_src = None, None
+    kde_traffic, kde_traffic_src, kde_ncu = None, None, None
     try:
         with open(os.path.join(ROOT, "profiles", "r2_kde_fast_dram.json")) as f:
             tj = json.load(f)
         kde_traffic, kde_traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        kde_ncu = tj.get("ncu")           # pipe utilisation of the same committed capture (not measured in this run)
     except (OSError, KeyError, ValueError):
         pass
     total_pairs = float(n_c) * float(n_e)
@@ -552,6 +553,7 @@ def run_cuda(args):
                          # from the committed ncu --set full capture (profiles/r2_kde_fast_dram.json); algorithmic: 68 MB
                          "traffic": kde_traffic if (world == 1 and scale == 1.0) else None,
                          "traffic_source": kde_traffic_src,
+                         "ncu": kde_ncu if (world == 1 and scale == 1.0) else None,
                          # kernel_ms brackets kde.log_prob: the Z-order sort of the evaluation points, the pairwise
                          # kernel (> 99.5 % of the bracket), the split merge, the exact re-evaluation of the listed points
                          # and the scatter back
