@@ -121,14 +121,23 @@ def upload_f32(x, out=None):
     return out
 
 
+def download(t, dtype=np.float64):
+    """float32 CUDA tensor -> fresh numpy array of `dtype` (float64: the reference's dtype; or float32). Large tensors
+    go through the library's staged downloader (aisb_download_f32: host threads pull chunks through pinned buffers and
+    widen them into the destination, first-touching its pages in parallel); small ones through torch."""
+    t = t.detach()
+    if t.numel() <= HOST_CAST_MAX or t.dtype != torch.float32 or not t.is_cuda:
+        return t.cpu().numpy().astype(dtype)
+    t = t.contiguous()
+    out = np.empty(tuple(t.shape), dtype=dtype)
+    check(_lib.load().aisb_download_f32(_ptr(t), t.numel(), out.ctypes.data, 1 if dtype == np.float64 else 0,
+                                        _upload_threads(), stream_ptr()), "aisb_download_f32")
+    return out
+
+
 def from_device(t, as_numpy):
     """float32 device vector -> numpy float64 (reference dtype) or the tensor itself."""
-    if as_numpy:
-        t = t.detach()
-        if t.numel() > HOST_CAST_MAX:
-            return t.double().cpu().numpy()          # widen on the device, copy 8-byte values
-        return t.cpu().numpy().astype(np.float64)
-    return t
+    return download(t) if as_numpy else t
 
 
 def exp_from_device(t, as_numpy):

@@ -77,6 +77,7 @@ PROTOTYPES = {
     "aisb_morton_keys_f32": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     "aisb_morton_keys_auto_f32": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "aisb_gather_rows_f32": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "aisb_download_f32": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp]),
     "aisb_upload_as_f32": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _vp]),
     "aisb_sample_mixture_f32": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _u64, _u64, _vp, _vp]),
     "aisb_sample_iso_ctr_f32": (C.c_int, [_vp, _i64, _i32, _i64, _dbl, _vp, _vp, _vp]),

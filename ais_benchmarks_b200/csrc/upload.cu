@@ -4,7 +4,8 @@
 // 13 ms for the 128 MB an e2e step of BASELINE configs[3] moves, 24 % of the step on a rank of an 8-GPU job). This
 // uploader does the staging itself, on several host threads: each narrows its chunks to float32 straight into its own
 // pinned staging buffers (so the host link carries 4-byte values and no cast kernel runs) and queues the DMA of one
-// buffer while it fills the other. No kernels here.
+// buffer while it fills the other. aisb_download_f32 is the way back (float32 in HBM -> the float64 numpy arrays the
+// reference's API returns). No kernels here.
 #include <stdint.h>
 
 #include <mutex>
@@ -118,10 +119,98 @@ int upload_t(const T* h_src, int64_t count, float* d_dst, int threads, cudaStrea
   return AISB_OK;
 }
 
+template <class T>
+void widen(const float* __restrict__ src, T* __restrict__ dst, int64_t count) {
+  for (int64_t i = 0; i < count; ++i) dst[i] = static_cast<T>(src[i]);
+}
+
+// The way back: chunks lane, lane + nlanes, ... of a device float32 array into a host array (float64 or float32). The
+// DMA of chunk k+1 into one staging buffer runs while the lane widens chunk k out of the other -- and touches the
+// destination pages for the first time (a fresh numpy array is untouched memory: one thread faulting in 2.5 GB is
+// most of a second, which is what the single-threaded copy behind Tensor.cpu() pays).
+template <class T>
+cudaError_t lane_fetch(Lane& l, int dev, int lane, int nlanes, const float* d_src, int64_t count, T* h_dst) {
+  cudaError_t e = cudaSetDevice(dev);
+  if (e != cudaSuccess) return e;
+  const int64_t nchunks = (count + kStageElems - 1) / kStageElems;
+  auto span = [&](int64_t c, int64_t& off, int64_t& len) {
+    off = c * kStageElems;
+    len = count - off < kStageElems ? count - off : kStageElems;
+  };
+  auto fetch = [&](int64_t c, int b) -> cudaError_t {
+    int64_t off, len;
+    span(c, off, len);
+    cudaError_t e2 = cudaMemcpyAsync(l.stage[b], d_src + off, sizeof(float) * len, cudaMemcpyDeviceToHost, l.stream);
+    if (e2 != cudaSuccess) return e2;
+    return cudaEventRecord(l.drained[b], l.stream);   // here: the buffer has been FILLED
+  };
+  int used = 0;
+  if (lane < nchunks) {
+    e = fetch(lane, 0);
+    if (e != cudaSuccess) return e;
+  }
+  for (int64_t c = lane; c < nchunks; c += nlanes, ++used) {
+    const int b = used % kStageBufs;
+    if (c + nlanes < nchunks) {
+      e = fetch(c + nlanes, (used + 1) % kStageBufs);   // that buffer was consumed in the previous round
+      if (e != cudaSuccess) return e;
+    }
+    e = cudaEventSynchronize(l.drained[b]);
+    if (e != cudaSuccess) return e;
+    int64_t off, len;
+    span(c, off, len);
+    widen(l.stage[b], h_dst + off, len);
+  }
+  return cudaSuccess;
+}
+
+template <class T>
+int download_t(const float* d_src, int64_t count, T* h_dst, int threads, cudaStream_t st) {
+  int dev = 0;
+  AISB_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) {
+    set_error("download: device index %d out of range", dev);
+    return AISB_ERR_INVALID;
+  }
+  const int64_t nchunks = (count + kStageElems - 1) / kStageElems;
+  int nlanes = threads < 1 ? 1 : (threads > kUploadMaxThreads ? kUploadMaxThreads : threads);
+  if (nlanes > nchunks) nlanes = static_cast<int>(nchunks);
+  std::lock_guard<std::mutex> lock(g_upload_mu);
+  Pool& pool = g_pools[dev];
+  if (!pool.start) AISB_CUDA_CHECK(cudaEventCreateWithFlags(&pool.start, cudaEventDisableTiming));
+  for (int t = 0; t < nlanes; ++t) AISB_CUDA_CHECK(lane_init(pool.lanes[t]));
+  // the copies queue behind whatever produces d_src on the caller's stream
+  AISB_CUDA_CHECK(cudaEventRecord(pool.start, st));
+  for (int t = 0; t < nlanes; ++t) AISB_CUDA_CHECK(cudaStreamWaitEvent(pool.lanes[t].stream, pool.start, 0));
+  cudaError_t errs[kUploadMaxThreads];
+  for (int t = 0; t < nlanes; ++t) errs[t] = cudaSuccess;
+  std::vector<std::thread> workers;
+  workers.reserve(nlanes);
+  for (int t = 1; t < nlanes; ++t)
+    workers.emplace_back([&, t] { errs[t] = lane_fetch(pool.lanes[t], dev, t, nlanes, d_src, count, h_dst); });
+  errs[0] = lane_fetch(pool.lanes[0], dev, 0, nlanes, d_src, count, h_dst);
+  for (auto& w : workers) w.join();
+  for (int t = 0; t < nlanes; ++t)
+    if (errs[t] != cudaSuccess) return cuda_fail(errs[t], "download lane");
+  return AISB_OK;
+}
+
 }  // namespace
 }  // namespace aisb
 
 using namespace aisb;
+
+extern "C" int aisb_download_f32(const float* d_src, int64_t count, void* h_dst, int32_t dst_is_f64, int32_t threads,
+                                 void* stream) {
+  if (count == 0) return AISB_OK;
+  if (!h_dst || !d_src || count < 0) {
+    set_error("download_f32: null pointer or negative count");
+    return AISB_ERR_INVALID;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dst_is_f64) return download_t(d_src, count, static_cast<double*>(h_dst), threads, st);
+  return download_t(d_src, count, static_cast<float*>(h_dst), threads, st);
+}
 
 extern "C" int aisb_upload_as_f32(const void* h_src, int32_t src_is_f64, int64_t count, float* d_dst, int32_t threads,
                                   void* stream) {

@@ -163,7 +163,7 @@ class CMixtureModel(CDistribution):
                 parts.append(_device.box_mixture_logpdf(x, gpacked[0], gpacked[1], gpacked[2], open_upper=False))
         for m, w in others:                              # foreign components: their own log_prob, wherever it runs
             lp = m.log_prob(x) if getattr(type(m), "__module__", "").startswith("ais_benchmarks_b200") else \
-                m.log_prob(x.double().cpu().numpy())
+                m.log_prob(_device.download(x))
             lp = lp if _device.is_tensor(lp) else torch.from_numpy(np.asarray(lp, dtype=np.float64).reshape(-1))
             parts.append(lp.to(x.device, torch.float32) + float(np.log(w)))
         if not parts:
@@ -196,7 +196,7 @@ class CMixtureModel(CDistribution):
                     draw = self.models[k].sample(int(cnt))
                     draw = draw if _device.is_tensor(draw) else torch.from_numpy(np.asarray(draw, dtype=np.float64))
                     x[idx == k] = draw.to(dev, torch.float32).reshape(int(cnt), self.dims)
-            return x if as_tensor else x.cpu().numpy().astype(np.float64)
+            return x if as_tensor else _device.download(x)
         if kind == "gauss":
             means, cov, ckind = gaussian_pack_args(self.models)
             z = _device.sample_iso(torch.zeros((1, self.dims), dtype=torch.float32, device=dev), n, 1.0)
@@ -213,7 +213,7 @@ class CMixtureModel(CDistribution):
             u = _device.uniform_box(torch.zeros(self.dims, dtype=torch.float32, device=dev),
                                     torch.ones(self.dims, dtype=torch.float32, device=dev), n)
             x = lo[idx] + (hi[idx] - lo[idx]) * u
-        return x if as_tensor else x.cpu().numpy().astype(np.float64)
+        return x if as_tensor else _device.download(x)
 
     def condition(self, dist):
         raise NotImplementedError

@@ -81,7 +81,7 @@ class CMultivariateNormal(CDistribution):
             L = torch.from_numpy(np.linalg.cholesky(0.5 * (self._scale + self._scale.T))).to(dev, torch.float32)
             x = z @ L.T
         x = x + torch.from_numpy(self._loc.reshape(1, -1)).to(dev, torch.float32)
-        return x if as_tensor else x.cpu().numpy().astype(np.float64)
+        return x if as_tensor else _device.download(x)
 
     def log_prob(self, samples):
         x, as_numpy = _device.to_device_points(samples, self.dims)

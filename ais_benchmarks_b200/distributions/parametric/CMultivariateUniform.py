@@ -59,7 +59,7 @@ class CMultivariateUniform(CDistribution):
     def sample(self, n_samples=1, as_tensor=False):
         lo, hi, _ = self._device_box()
         x = _device.uniform_box(lo[0].contiguous(), hi[0].contiguous(), int(n_samples))
-        return x if as_tensor else x.cpu().numpy().astype(np.float64)
+        return x if as_tensor else _device.download(x)
 
     def log_prob(self, samples):
         x, as_numpy = _device.to_device_points(samples, self.dims)

@@ -65,7 +65,7 @@ def device_log_probs(p, q, samples):
 
     def x_np():
         if "x" not in cache:
-            cache["x"] = samples if was_numpy else x_dev.cpu().numpy().astype(np.float64)
+            cache["x"] = samples if was_numpy else _device.download(x_dev)
         return cache["x"]
 
     return x_dev, _log_prob_device(p, x_dev, x_np), _log_prob_device(q, x_dev, x_np)

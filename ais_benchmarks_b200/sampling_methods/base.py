@@ -53,7 +53,7 @@ class CSamplingMethod(metaclass=ABCMeta):
     def samples(self):
         if self._samples_np is None:
             self._samples_np = (np.array([]) if self._samples_dev is None
-                                else self._samples_dev.cpu().numpy().astype(np.float64))
+                                else _device.download(self._samples_dev))
         return self._samples_np
 
     @samples.setter
@@ -253,7 +253,7 @@ class CDeviceKDE(CDistribution):
         c = self.centres()
         pick = torch.randint(0, c.shape[0], (int(n_samples),), device=c.device)
         x = _device.sample_iso(c[pick].contiguous(), 1, self.bw)
-        return x if as_tensor else x.cpu().numpy().astype(np.float64)
+        return x if as_tensor else _device.download(x)
 
     def condition(self, dist):
         raise NotImplementedError
@@ -333,7 +333,7 @@ def target_device_mixture(target_d):
 def foreign_target_logp(target_d, x_dev):
     """log pi(x) of a target that is not one of this package's Gaussian classes: the caller's own log_prob/prob
     runs wherever it runs (typically numpy on the host); the result is uploaded for the weight kernel."""
-    x_np = x_dev.cpu().numpy().astype(np.float64)
+    x_np = _device.download(x_dev)
     if hasattr(target_d, "log_prob"):
         lp = np.asarray(target_d.log_prob(x_np), dtype=np.float64).reshape(-1)
     else:

@@ -85,7 +85,7 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
 
     def _build_objects(self):
         if self._objects is None:
-            means = self._means_host if self._means_host is not None else self._means.cpu().numpy().astype(np.float64)
+            means = self._means_host if self._means_host is not None else _device.download(self._means)
             cov = np.diag(np.array([self.sigma] * self.ndims, dtype=np.float64))
             props = [CMultivariateNormal({"mean": m, "sigma": cov.copy()}) for m in means]
             model = CMixtureModel({"models": props, "weights": np.array([1 / len(props)] * len(props)),
@@ -124,7 +124,7 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
         means = self.proposal_means()
         pick = torch.randint(0, self.N, (int(n_samples),), device=means.device)
         x = _device.sample_iso(means[pick].contiguous(), 1, float(self.sigma))
-        return x if self.device_outputs else x.cpu().numpy().astype(np.float64)
+        return x if self.device_outputs else _device.download(x)
 
     # -- the adapt loop ----------------------------------------------------------------------------
     def weigh(self, new_samples, target_d, hint=None):
@@ -294,7 +294,7 @@ class CDeterministicMixtureAIS(CMixtureISSamplingMethod):
         self._check_pending_records()
         # weights / weights.sum() over ALL iterations (dm_ais.py:86) -- and all ranks
         norm_w = _device.normalize_weights(self._logw_dev, self._global_partials())
-        return self._out(self._samples_dev), (norm_w if self.device_outputs else norm_w.double().cpu().numpy())
+        return self._out(self._samples_dev), (norm_w if self.device_outputs else _device.download(norm_w))
 
     def _update_model(self):
         pass

@@ -106,4 +106,4 @@ class CLayeredAIS(CDeterministicMixtureAIS):
             elapsed_time = time.time() - t_ini
         self._check_pending_records()
         norm_w = _device.normalize_weights(self._logw_dev, self._global_partials())
-        return self._out(self._samples_dev), (norm_w if self.device_outputs else norm_w.double().cpu().numpy())
+        return self._out(self._samples_dev), (norm_w if self.device_outputs else _device.download(norm_w))

@@ -157,7 +157,7 @@ class CMixturePMC(CMixtureISSamplingMethod):
     def sample(self, n_samples):
         self._num_q_samples += n_samples
         x = self._sample_device(n_samples)
-        return x if self.device_outputs else x.cpu().numpy().astype(np.float64)
+        return x if self.device_outputs else _device.download(x)
 
     # -- one M-PMC iteration on a given batch (also the parity-test entry point) -------------------
     def weigh(self, new_samples, target_d):

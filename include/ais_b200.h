@@ -395,6 +395,14 @@ int aisb_gather_rows_f32(const float* d_x, int64_t n_src, int32_t D, const int64
  *      queued on `stream`; when the call returns h_src has been read completely and the data is in HBM. */
 int aisb_upload_as_f32(const void* h_src, int32_t src_is_f64, int64_t count, float* d_dst, int32_t threads,
                        void* stream);
+/*  aisb_download_f32: d_src (DEVICE, float32 [count]) -> h_dst (HOST, pageable or pinned; float64 if dst_is_f64 else
+ *      float32). The reference's API returns float64 numpy arrays (`importance_sample` -> samples, weights:
+ *      sampling_methods/dm_ais.py:86, base.py:21-35); this replaces device-side widening + a pageable cudaMemcpy into
+ *      untouched memory: `threads` host threads (1..8) pull chunks through their pinned staging buffers and widen them
+ *      into the destination, touching its pages in parallel. Ordered after the work already queued on `stream`;
+ *      synchronous: when the call returns h_dst is complete. */
+int aisb_download_f32(const float* d_src, int64_t count, void* h_dst, int32_t dst_is_f64, int32_t threads,
+                      void* stream);
 /*  aisb_sample_mixture_f32: ancestral draws from a full-covariance Gaussian mixture, given the component of every draw:
  *      out[i, :] = means[idx[i], :] + chol[idx[i]] z_i,  z_i ~ N(0, I)   (chol: lower-triangular factors, row-major
  *      [K, D, D]). Replaces CMixtureModel.sample (CMixtureModel.py:79-89) over CMultivariateNormal.sample

@@ -332,3 +332,36 @@ def test_gather_rows_kernel():
     check(_lib.load().aisb_gather_rows_f32(_ptr(x), 1000, 8, _ptr(idx), 5, _ptr(out), _ptr(err), stream_ptr()))
     assert int(err) == 4                               # two bad rows x two float4 pieces each
     assert torch.equal(out[[0, 1, 4]], x[[0, 999, 5]]) and bool((out[2:4] == 7.0).all())
+
+
+def test_staged_download_is_exact_widening(monkeypatch):
+    """aisb_download_f32 (HBM float32 -> the float64 / float32 numpy arrays the reference's API returns) is the exact
+    widening of the device values for every thread count and chunk boundary, waits for the producing kernel on the
+    caller's stream, and does not write outside the destination."""
+    from ais_benchmarks_b200 import _device
+    g = torch.Generator(device="cuda").manual_seed(21)
+    chunk = 1 << 20
+    for count in (_device.HOST_CAST_MAX + 1, chunk - 1, chunk + 1, 3 * chunk + 12345, 9 * chunk + 7):
+        t = torch.randn(count, device="cuda", generator=g) * 1e3
+        t[:5] = torch.tensor([0.0, -0.0, float("inf"), float("nan"), 1e-45], device="cuda")
+        want = t.cpu().numpy()
+        for threads in (1, 2, 3, 5, 8):
+            monkeypatch.setenv("AISB_UPLOAD_THREADS", str(threads))
+            for dt in (np.float64, np.float32):
+                got = _device.download(t, dt)
+                assert got.dtype == dt and got.shape == (count,)
+                assert np.array_equal(got.view(np.uint64 if dt == np.float64 else np.uint32),
+                                      want.astype(dt).view(np.uint64 if dt == np.float64 else np.uint32)), (count, threads)
+    # ordering with the producing kernel + 2-D shape + guard bytes around a caller-owned destination
+    lib = _device._lib.load()
+    src = torch.empty(700_000, 8, device="cuda")
+    for rep in range(3):
+        src.normal_(generator=g)                                     # still running when the download is queued
+        got = _device.from_device(src, True)
+        assert got.shape == (700_000, 8) and np.array_equal(got, src.cpu().numpy().astype(np.float64))
+    buf = np.full(src.numel() + 16, 7.0)
+    _device.check(lib.aisb_download_f32(_device._ptr(src), src.numel(), buf[8:].ctypes.data, 1, 4, _device.stream_ptr()))
+    assert (buf[:8] == 7.0).all() and (buf[-8:] == 7.0).all()
+    assert np.array_equal(buf[8:-8], src.cpu().numpy().astype(np.float64).reshape(-1))
+    with pytest.raises(_device.AisbError):
+        _device.check(lib.aisb_download_f32(_device._ptr(src), 10, None, 1, 2, None))
