@@ -659,13 +659,20 @@ __device__ __forceinline__ void mixture_pass_screen(const float* __restrict__ g_
 // ---------------------------------------------------------------------------------------------
 constexpr float kPosBig = 3.0e38f;
 
+#ifndef AISB_FAST_UNROLL
+#define AISB_FAST_UNROLL 2
+#endif
+// groups of JJ components per trip of the fast kernel's inner loop: 2 halves its address arithmetic, compare and branch
+// (365.6 -> 356.4 ms at configs[3]); 4 is no faster and spills
+constexpr int kFastUnroll = AISB_FAST_UNROLL;
+
 template <int DP, int EP, int JJ, bool COUNT>
 __device__ __forceinline__ void accumulate_chunk_fast(const float* __restrict__ srows, const float* __restrict__ sh,
                                                       int cnt, float n2a, float two_a, float dthr,
                                                       const float2 (&x2)[EP][DP], float2 (&ms)[EP], float2 (&cr)[EP],
                                                       float2 (&S2)[EP], float2 (&thr)[EP], const float2 (&gbest)[EP],
                                                       unsigned (&nfolded)) {
-#pragma unroll 1
+#pragma unroll kFastUnroll
   for (int j0 = 0; j0 < cnt; j0 += JJ) {
     float h[JJ];
     lds_vec<JJ>(sh + j0, h);
