@@ -542,10 +542,10 @@ def run_cuda(args):
                                "h2d_bytes_per_step": int(centres_pin.numel() * 4 + x_pin.numel() * 4),
                                "d2h_bytes_per_step": 64, "ms_per_step": kde_pinned_ms},
             # kernels of libais_b200.so per resident step (profiles/r2_launches_bench_final.csv): bounding box + Morton keys
-            # for the centres and for the points (4), kde_pack, logpdf_fast, fast_merge, logpdf_subset + subset_merge
-            # (exact re-evaluation of the listed points), target logpdf, kld_partials + its merge; torch adds a radix
-            # sort and a gather per side
-            "gpu_launches": 12 * args.steps,
+            # for the centres and for the points (4), kde_pack, gather_rows (points into Z-order), logpdf_fast, fast_merge,
+            # logpdf_subset + subset_merge (exact re-evaluation of the listed points), target logpdf, kld_partials + its
+            # merge; torch adds a radix sort per side and the scatter of the result
+            "gpu_launches": 13 * args.steps,
             "clocks": clock_info,
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp32_peak_tflops,
