@@ -294,7 +294,7 @@ class DeviceMixture:
         ordered = n_c >= MORTON_MIN_ROWS and D <= MORTON_MAX_DIMS and spatial_order
         if ordered:
             # a mixture does not care about the order of its components: pack them along a Z-order curve
-            chosen = samples[:n_c] if idx is None else samples[idx]
+            chosen = samples[:n_c] if idx is None else gather_rows(samples, idx)
             perm = morton_order(chosen)
             idx = perm if idx is None else idx[perm]
         rows = torch.empty((KP, DP), dtype=torch.float32, device=samples.device)

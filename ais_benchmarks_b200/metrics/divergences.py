@@ -24,7 +24,14 @@ from .base import CMetric
 
 
 def _is_ours(obj):
-    return type(obj).__module__.startswith(__package__.rsplit(".", 1)[0])
+    """True if the `log_prob` this object answers with is one of this package's (device tensors in, device tensors
+    out): decided by the class that DEFINES it, so a user's subclass of a sampler or distribution (the reference's
+    own extension mechanism) stays on the device unless it overrides log_prob itself."""
+    pkg = __package__.rsplit(".", 1)[0]
+    for c in type(obj).__mro__:
+        if "log_prob" in c.__dict__:
+            return c.__module__.startswith(pkg)
+    return False
 
 
 def _log_prob_device(dist, x_dev, x_np_getter):
@@ -57,15 +64,33 @@ def evaluation_points(metric, kwargs):
     return np.random.uniform(lo, hi, size=(kwargs["nsamples"], p.dims))
 
 
-def device_log_probs(p, q, samples):
-    """(x, lp, lq) as float32 device tensors for the evaluation points `samples` (numpy or CUDA tensor)."""
+def device_log_probs(p, q, samples, deal_out=False):
+    """(x, lp, lq) as float32 device tensors for the evaluation points `samples` (numpy or CUDA tensor).
+    deal_out: `samples` is the FULL point set, identical on every rank of a multi-GPU job: every rank stages 1/N of it
+    (parallel.upload_replicated), the ranks exchange the pieces over NVLink and each keeps its block-cyclic share of the
+    Z-order curve (parallel.spatial_shard) -- the sharding the KDE kernels are fastest on (a rank's warps then hold
+    neighbours of the full set; a random 1/8 of the points costs 5 % more per pair)."""
     dims = getattr(p, "dims", None) or samples.shape[-1]
-    x_dev, was_numpy = _device.to_device_points(samples, dims)
+    if deal_out:
+        from .. import parallel
+        if _device.is_tensor(samples):
+            full, was_numpy = _device.to_device_points(samples, dims)[0], False
+        else:
+            _device.require_cuda()
+            full, was_numpy = parallel.upload_replicated(_device.check_points(np.asarray(samples), dims)), True
+        x_dev, mine = parallel.spatial_shard(full)
+    else:
+        x_dev, was_numpy = _device.to_device_points(samples, dims)
+        mine = None
     cache = {}
 
     def x_np():
+        # host copy of THIS rank's points, only built if a foreign distribution asks for numpy input
         if "x" not in cache:
-            cache["x"] = samples if was_numpy else _device.download(x_dev)
+            if not was_numpy:
+                cache["x"] = _device.download(x_dev)
+            else:
+                cache["x"] = samples if mine is None else np.asarray(samples)[mine.cpu().numpy()]
         return cache["x"]
 
     return x_dev, _log_prob_device(p, x_dev, x_np), _log_prob_device(q, x_dev, x_np)
@@ -80,6 +105,9 @@ class CDivergence(CMetric):
         self.disjoint_support = True
         # True: evaluation points are drawn by the device Philox kernel instead of np.random.uniform
         self.device_points = False
+        # multi-GPU (with `sharded`): compute_from_samples is handed the FULL point set, identical on every rank, and
+        # deals it out itself (device_log_probs, deal_out); False: the caller passes this rank's rows
+        self.replicated_points = False
         # True (under torch.distributed): `samples` are this rank's rows; the partial records are merged over the ranks
         self.sharded = False
 
@@ -110,7 +138,7 @@ class CKLDivergence(CDivergence):
 
     def compute_from_samples(self, p, q, samples):
         """divergences.py:101-108 with both log densities and the reduction on the device."""
-        _, lp, lq = device_log_probs(p, q, samples)
+        _, lp, lq = device_log_probs(p, q, samples, deal_out=self.sharded and self.replicated_points)
         return self.compute_from_device_log_probs(lp, lq)
 
     def compute_from_device_log_probs(self, lp, lq):
@@ -192,7 +220,7 @@ class CJSDivergence(CDivergence):
         self.dropped = 0
 
     def compute_from_samples(self, p, q, samples):
-        _, lp, lq = device_log_probs(p, q, samples)
+        _, lp, lq = device_log_probs(p, q, samples, deal_out=self.sharded and self.replicated_points)
         return self.compute_from_device_log_probs(lp, lq)
 
     def compute_from_device_log_probs(self, lp, lq):

@@ -230,9 +230,12 @@ def run_cuda(args):
             raise NotImplementedError
 
     centres_np = centres_h.astype(np.float64)                            # what a numpy caller owns: float64, pageable
-    x_np = x_h[start:stop].astype(np.float64)
+    # N > 1: every rank holds the same full array of evaluation points (an SPMD script) and the metric deals it out:
+    # each rank stages 1/N of it, NVLink carries the rest, each keeps its block-cyclic share of the Z-order curve
+    x_np = x_h.astype(np.float64)
     metric_np = CKLDivergence()
     metric_np.sharded = world > 1
+    metric_np.replicated_points = world > 1
 
     def kde_step_numpy():
         np.random.seed(1234)       # the KDE resampling draws its seed from numpy: every rank must build the same KDE
@@ -531,13 +534,13 @@ def run_cuda(args):
                     # per rank, bytes crossing the host link: the float64 arrays are narrowed to float32 by the staged
                     # uploader on the way (aisb_upload_as_f32); at N > 1 each rank stages 1/N of the centres and the ranks
                     # all-gather the rest over NVLink (replicated_samples)
-                    "h2d_bytes_per_step": int(centres_np.nbytes // 2 // world + x_np.nbytes // 2),
+                    "h2d_bytes_per_step": int(centres_np.nbytes // 2 // world + x_np.nbytes // 2 // world),
                     "d2h_bytes_per_step": 64,
-                    "host_bytes_read_per_step": int(centres_np.nbytes // world + x_np.nbytes),
+                    "host_bytes_read_per_step": int(centres_np.nbytes // world + x_np.nbytes // world),
                     "ms_per_step": kde_e2e_ms,
                     "api": "sampler.samples = centres (numpy float64, the same array on every rank); "
-                           "CKLDivergence().compute_from_samples(target, sampler, x) with x numpy float64 -- pageable "
-                           "host memory, per rank its shard of x"},
+                           "CKLDivergence().compute_from_samples(target, sampler, x) with x numpy float64 (N > 1: the "
+                           "same full array on every rank, replicated_points) -- pageable host memory"},
             "e2e_pinned_f32": {"value": total_pairs / (kde_pinned_ms * 1e-3), "unit": UNIT,
                                "h2d_bytes_per_step": int(centres_pin.numel() * 4 + x_pin.numel() * 4),
                                "d2h_bytes_per_step": 64, "ms_per_step": kde_pinned_ms},

@@ -135,6 +135,11 @@ def run_checks(rank, world, use_oracle=True):
         if ness is not None:
             same_on_all_ranks(torch.tensor([ness]), name + " NESS")
         kld1 = metric.compute_from_samples(target, s, x_eval)
+        # the same metric with the points dealt out over the ranks by the metric itself (full array on every rank)
+        dealt = CKLDivergence()
+        dealt.sharded, dealt.replicated_points = True, True
+        kld1_dealt = dealt.compute_from_samples(target, s, x_eval)
+        ensure(abs(kld1_dealt - kld1) < 2e-5 * max(1.0, abs(kld1)), (name, "dealt-out KLD", kld1_dealt, kld1))
         lines.append("%-8s world %d: %d samples over %d iterations, local rows %d, weight parity %.1e, NESS %s, "
                      "KLD(target || proposal) %.3f -> %.3f" % (name, world, iters * per_iter, iters, x.shape[0], err,
                                                              "%.4g" % ness if ness is not None else "per batch",

@@ -347,3 +347,31 @@ def test_peer_exchange_is_off_without_nccl():
     parallel.PeerRecordExchange._disabled = False
     assert parallel.PeerRecordExchange.get() is None        # single process, no process group: NCCL path / no exchange
     parallel.PeerRecordExchange._disabled = False
+
+
+def test_device_path_follows_the_class_that_defines_log_prob():
+    """metrics.divergences keeps an object's log_prob on the device iff the method it will call is this package's:
+    a user's subclass (the reference's extension mechanism: samplers and distributions are subclassed by callers) must
+    not be demoted to the numpy round trip, an override or a foreign class must."""
+    from ais_benchmarks_b200.metrics.divergences import _is_ours
+    from ais_benchmarks_b200.sampling_methods.base import CMixtureSamplingMethod
+    from ais_benchmarks_b200.distributions import CMultivariateNormal
+
+    class UserSampler(CMixtureSamplingMethod):
+        def importance_sample(self, target_d, n_samples, timeout):
+            raise NotImplementedError
+
+    class UserNormal(CMultivariateNormal):
+        def log_prob(self, x):
+            return np.zeros(len(x))
+
+    class Foreign:
+        def log_prob(self, x):
+            return np.zeros(len(x))
+
+    params = {"space_min": np.zeros(2), "space_max": np.ones(2), "dims": 2, "n_samples_kde": 10}
+    assert _is_ours(UserSampler(params))
+    assert _is_ours(CMultivariateNormal({"mean": np.zeros(2), "sigma": np.eye(2)}))
+    assert not _is_ours(UserNormal({"mean": np.zeros(2), "sigma": np.eye(2)}))
+    assert not _is_ours(Foreign())
+    assert not _is_ours(object())
