@@ -915,7 +915,6 @@ extern "C" int aisb_mixture_logpdf_fast_f32(const float* d_x, int64_t n, const a
   // single-warp CTAs, up to 16 resident per SM: interleaved split of the component range (see kFastWaves), >= 16 chunks
   // per CTA; the partial (m, S) of the splits live in the scratch buffer
   const int64_t KPc = aisb_padded_components(mix->K);
-  const int64_t ntiles = (n + kScreenThreads * 4 - 1) / (kScreenThreads * 4);
   const int64_t nchunks = (KPc + kScreenChunk - 1) / kScreenChunk;
   const int64_t cap = fast_split_cap(n);
   int64_t want = cap;

@@ -53,6 +53,25 @@ cudaError_t lane_init(Lane& l) {
   return cudaSuccess;
 }
 
+// Lane t runs on its own thread (lane 0 on the caller's). No exception may cross the C ABI: a lane whose thread cannot
+// be started (resource limits) runs on the calling thread instead, after the others.
+template <class Fn>
+void run_lanes(int nlanes, cudaError_t* errs, Fn&& work) {
+  std::vector<std::thread> workers;
+  std::vector<int> inline_lanes;
+  workers.reserve(nlanes > 0 ? nlanes - 1 : 0);
+  for (int t = 1; t < nlanes; ++t) {
+    try {
+      workers.emplace_back([&errs, &work, t] { errs[t] = work(t); });
+    } catch (...) {
+      inline_lanes.push_back(t);
+    }
+  }
+  errs[0] = work(0);
+  for (int t : inline_lanes) errs[t] = work(t);
+  for (auto& w : workers) w.join();
+}
+
 template <class T>
 void narrow(const T* __restrict__ src, float* __restrict__ dst, int64_t count) {
   for (int64_t i = 0; i < count; ++i) dst[i] = static_cast<float>(src[i]);
@@ -103,14 +122,12 @@ int upload_t(const T* h_src, int64_t count, float* d_dst, int threads, cudaStrea
   for (int t = 0; t < nlanes; ++t) AISB_CUDA_CHECK(cudaStreamWaitEvent(pool.lanes[t].stream, pool.start, 0));
   cudaError_t errs[kUploadMaxThreads];
   for (int t = 0; t < nlanes; ++t) errs[t] = cudaSuccess;
-  std::vector<std::thread> workers;
-  workers.reserve(nlanes);
-  for (int t = 1; t < nlanes; ++t)
-    workers.emplace_back([&, t] { errs[t] = lane_run(pool.lanes[t], dev, t, nlanes, h_src, count, d_dst); });
-  errs[0] = lane_run(pool.lanes[0], dev, 0, nlanes, h_src, count, d_dst);
-  for (auto& w : workers) w.join();
+  run_lanes(nlanes, errs, [&](int t) { return lane_run(pool.lanes[t], dev, t, nlanes, h_src, count, d_dst); });
   for (int t = 0; t < nlanes; ++t)
-    if (errs[t] != cudaSuccess) return cuda_fail(errs[t], "upload lane");
+    if (errs[t] != cudaSuccess) {
+      for (int u = 0; u < nlanes; ++u) cudaStreamSynchronize(pool.lanes[u].stream);   // leave no copy in flight
+      return cuda_fail(errs[t], "upload lane");
+    }
   // ... and whatever the caller queues next on its stream sees the data (the lanes have drained: this only orders it)
   for (int t = 0; t < nlanes; ++t) {
     AISB_CUDA_CHECK(cudaEventRecord(pool.lanes[t].finished, pool.lanes[t].stream));
@@ -184,14 +201,12 @@ int download_t(const float* d_src, int64_t count, T* h_dst, int threads, cudaStr
   for (int t = 0; t < nlanes; ++t) AISB_CUDA_CHECK(cudaStreamWaitEvent(pool.lanes[t].stream, pool.start, 0));
   cudaError_t errs[kUploadMaxThreads];
   for (int t = 0; t < nlanes; ++t) errs[t] = cudaSuccess;
-  std::vector<std::thread> workers;
-  workers.reserve(nlanes);
-  for (int t = 1; t < nlanes; ++t)
-    workers.emplace_back([&, t] { errs[t] = lane_fetch(pool.lanes[t], dev, t, nlanes, d_src, count, h_dst); });
-  errs[0] = lane_fetch(pool.lanes[0], dev, 0, nlanes, d_src, count, h_dst);
-  for (auto& w : workers) w.join();
+  run_lanes(nlanes, errs, [&](int t) { return lane_fetch(pool.lanes[t], dev, t, nlanes, d_src, count, h_dst); });
   for (int t = 0; t < nlanes; ++t)
-    if (errs[t] != cudaSuccess) return cuda_fail(errs[t], "download lane");
+    if (errs[t] != cudaSuccess) {
+      for (int u = 0; u < nlanes; ++u) cudaStreamSynchronize(pool.lanes[u].stream);   // leave no copy in flight
+      return cuda_fail(errs[t], "download lane");
+    }
   return AISB_OK;
 }
 
