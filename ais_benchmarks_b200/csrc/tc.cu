@@ -283,6 +283,20 @@ __global__ void tc_pack_kernel(const float* __restrict__ rows, int64_t K, int D,
   }
 }
 
+// Epilogue loop shapes (config 5, un-adapted proposals, same box): 64-column loop rolled / accumulator-tile loop
+// rolled 3.16 ms; 64-column loop fully unrolled (2 trips) 2.98 ms -- the TMEM load of the next half is hoisted over the
+// fold of this one and 112 B fewer spills; two accumulator tiles per trip as well 2.95 ms (the buffer index and
+// barrier parity become compile-time per copy). Crowded proposals (many exact refinements per sample, a regime the
+// dispatcher keeps on the CUDA cores) lose ~10 % to the larger loop body.
+#ifndef AISB_TC_EPI_UNROLL
+#define AISB_TC_EPI_UNROLL 2
+#endif
+#ifndef AISB_TC_TILE_UNROLL
+#define AISB_TC_TILE_UNROLL 2
+#endif
+constexpr int kTcTileUnroll = AISB_TC_TILE_UNROLL;   // accumulator tiles per trip of the epilogue's tile loop
+constexpr int kTcEpiUnroll = AISB_TC_EPI_UNROLL;     // trips of the epilogue's 64-column loop unrolled (kTcN / 64 = 2 in all)
+
 struct TcBars {
   uint64_t full[4], empty[4], tfull[2], tempty[2], a_ready;  // tfull/tempty index = accumulator buffer (both row tiles)
   uint32_t tmem_base;
@@ -451,6 +465,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       // ---- epilogue: screened sum over the accumulator tiles, TMEM loads one chunk ahead of the arithmetic ----
       bool ok = true;
       const int build_at = ntiles_n > 1 ? 1 : 0;  // the next iteration's A tile is built in the shadow of this sweep
+#pragma unroll kTcTileUnroll
       for (int tn = 0; tn < ntiles_n && ok; ++tn, ++itn) {
         const uint32_t b = itn & 1u, bph = (itn >> 1) & 1u;
         if (!tc_wait(&bars.tfull[b], bph, abort_flag)) {
@@ -463,7 +478,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         uint32_t r0[32], r1[32];
         tc_ld32_issue(taddr, r0);
         tc_ld_wait();
-#pragma unroll 1
+#pragma unroll kTcEpiUnroll
         for (int c0 = 0; c0 < kTcN; c0 += 64) {
           tc_ld32_issue(taddr + c0 + 32, r1);
           const float m0 = m;
