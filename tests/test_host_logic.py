@@ -375,3 +375,26 @@ def test_device_path_follows_the_class_that_defines_log_prob():
     assert not _is_ours(UserNormal({"mean": np.zeros(2), "sigma": np.eye(2)}))
     assert not _is_ours(Foreign())
     assert not _is_ours(object())
+
+
+def test_upload_thread_count_policy(monkeypatch):
+    """Host threads of the staged uploader / downloader: explicit override clamped to the library's 1..8 lanes, else
+    the cores one local rank can claim (torchrun's LOCAL_WORLD_SIZE), at most 8, never 0."""
+    import os
+    from ais_benchmarks_b200 import _device
+    monkeypatch.delenv("AISB_UPLOAD_THREADS", raising=False)
+    monkeypatch.setattr(os, "cpu_count", lambda: 16)
+    monkeypatch.delenv("LOCAL_WORLD_SIZE", raising=False)
+    assert _device._upload_threads() == 8
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert _device._upload_threads() == 2
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "64")
+    assert _device._upload_threads() == 1
+    monkeypatch.setattr(os, "cpu_count", lambda: None)
+    assert _device._upload_threads() == 1
+    monkeypatch.setenv("AISB_UPLOAD_THREADS", "5")
+    assert _device._upload_threads() == 5
+    monkeypatch.setenv("AISB_UPLOAD_THREADS", "99")
+    assert _device._upload_threads() == 8
+    monkeypatch.setenv("AISB_UPLOAD_THREADS", "0")
+    assert _device._upload_threads() == 1
