@@ -72,6 +72,17 @@ void run_lanes(int nlanes, cudaError_t* errs, Fn&& work) {
   for (auto& w : workers) w.join();
 }
 
+// Elements per chunk: a lane should see several chunks (so that the DMA of one overlaps the narrowing of the next) but
+// no chunk smaller than 64 K elements (per-copy overheads) or larger than a staging buffer. A rank of an 8-GPU job
+// stages 1M elements with 2 threads: one 1M-element chunk would leave the second thread idle and nothing overlapped.
+int64_t chunk_elems(int64_t count, int threads) {
+  int64_t c = count / (static_cast<int64_t>(threads < 1 ? 1 : threads) * 4);
+  c = (c + 4095) / 4096 * 4096;
+  if (c < (1 << 16)) c = 1 << 16;
+  if (c > kStageElems) c = kStageElems;
+  return c;
+}
+
 template <class T>
 void narrow(const T* __restrict__ src, float* __restrict__ dst, int64_t count) {
   for (int64_t i = 0; i < count; ++i) dst[i] = static_cast<float>(src[i]);
@@ -79,10 +90,11 @@ void narrow(const T* __restrict__ src, float* __restrict__ dst, int64_t count) {
 
 // chunks lane, lane + nlanes, ... of the array
 template <class T>
-cudaError_t lane_run(Lane& l, int dev, int lane, int nlanes, const T* h_src, int64_t count, float* d_dst) {
+cudaError_t lane_run(Lane& l, int dev, int lane, int nlanes, const T* h_src, int64_t count, int64_t chunk,
+                     float* d_dst) {
   cudaError_t e = cudaSetDevice(dev);
   if (e != cudaSuccess) return e;
-  const int64_t nchunks = (count + kStageElems - 1) / kStageElems;
+  const int64_t nchunks = (count + chunk - 1) / chunk;
   int used = 0;
   for (int64_t c = lane; c < nchunks; c += nlanes, ++used) {
     const int b = used % kStageBufs;
@@ -90,8 +102,8 @@ cudaError_t lane_run(Lane& l, int dev, int lane, int nlanes, const T* h_src, int
       e = cudaEventSynchronize(l.drained[b]);
       if (e != cudaSuccess) return e;
     }
-    const int64_t off = c * kStageElems;
-    const int64_t len = count - off < kStageElems ? count - off : kStageElems;
+    const int64_t off = c * chunk;
+    const int64_t len = count - off < chunk ? count - off : chunk;
     narrow(h_src + off, l.stage[b], len);
     e = cudaMemcpyAsync(d_dst + off, l.stage[b], sizeof(float) * len, cudaMemcpyHostToDevice, l.stream);
     if (e != cudaSuccess) return e;
@@ -110,8 +122,9 @@ int upload_t(const T* h_src, int64_t count, float* d_dst, int threads, cudaStrea
     set_error("upload: device index %d out of range", dev);
     return AISB_ERR_INVALID;
   }
-  const int64_t nchunks = (count + kStageElems - 1) / kStageElems;
   int nlanes = threads < 1 ? 1 : (threads > kUploadMaxThreads ? kUploadMaxThreads : threads);
+  const int64_t chunk = chunk_elems(count, nlanes);
+  const int64_t nchunks = (count + chunk - 1) / chunk;
   if (nlanes > nchunks) nlanes = static_cast<int>(nchunks);
   std::lock_guard<std::mutex> lock(g_upload_mu);
   Pool& pool = g_pools[dev];
@@ -122,7 +135,7 @@ int upload_t(const T* h_src, int64_t count, float* d_dst, int threads, cudaStrea
   for (int t = 0; t < nlanes; ++t) AISB_CUDA_CHECK(cudaStreamWaitEvent(pool.lanes[t].stream, pool.start, 0));
   cudaError_t errs[kUploadMaxThreads];
   for (int t = 0; t < nlanes; ++t) errs[t] = cudaSuccess;
-  run_lanes(nlanes, errs, [&](int t) { return lane_run(pool.lanes[t], dev, t, nlanes, h_src, count, d_dst); });
+  run_lanes(nlanes, errs, [&](int t) { return lane_run(pool.lanes[t], dev, t, nlanes, h_src, count, chunk, d_dst); });
   for (int t = 0; t < nlanes; ++t)
     if (errs[t] != cudaSuccess) {
       for (int u = 0; u < nlanes; ++u) cudaStreamSynchronize(pool.lanes[u].stream);   // leave no copy in flight
@@ -146,13 +159,14 @@ void widen(const float* __restrict__ src, T* __restrict__ dst, int64_t count) {
 // destination pages for the first time (a fresh numpy array is untouched memory: one thread faulting in 2.5 GB is
 // most of a second, which is what the single-threaded copy behind Tensor.cpu() pays).
 template <class T>
-cudaError_t lane_fetch(Lane& l, int dev, int lane, int nlanes, const float* d_src, int64_t count, T* h_dst) {
+cudaError_t lane_fetch(Lane& l, int dev, int lane, int nlanes, const float* d_src, int64_t count, int64_t chunk,
+                       T* h_dst) {
   cudaError_t e = cudaSetDevice(dev);
   if (e != cudaSuccess) return e;
-  const int64_t nchunks = (count + kStageElems - 1) / kStageElems;
+  const int64_t nchunks = (count + chunk - 1) / chunk;
   auto span = [&](int64_t c, int64_t& off, int64_t& len) {
-    off = c * kStageElems;
-    len = count - off < kStageElems ? count - off : kStageElems;
+    off = c * chunk;
+    len = count - off < chunk ? count - off : chunk;
   };
   auto fetch = [&](int64_t c, int b) -> cudaError_t {
     int64_t off, len;
@@ -189,8 +203,9 @@ int download_t(const float* d_src, int64_t count, T* h_dst, int threads, cudaStr
     set_error("download: device index %d out of range", dev);
     return AISB_ERR_INVALID;
   }
-  const int64_t nchunks = (count + kStageElems - 1) / kStageElems;
   int nlanes = threads < 1 ? 1 : (threads > kUploadMaxThreads ? kUploadMaxThreads : threads);
+  const int64_t chunk = chunk_elems(count, nlanes);
+  const int64_t nchunks = (count + chunk - 1) / chunk;
   if (nlanes > nchunks) nlanes = static_cast<int>(nchunks);
   std::lock_guard<std::mutex> lock(g_upload_mu);
   Pool& pool = g_pools[dev];
@@ -201,7 +216,7 @@ int download_t(const float* d_src, int64_t count, T* h_dst, int threads, cudaStr
   for (int t = 0; t < nlanes; ++t) AISB_CUDA_CHECK(cudaStreamWaitEvent(pool.lanes[t].stream, pool.start, 0));
   cudaError_t errs[kUploadMaxThreads];
   for (int t = 0; t < nlanes; ++t) errs[t] = cudaSuccess;
-  run_lanes(nlanes, errs, [&](int t) { return lane_fetch(pool.lanes[t], dev, t, nlanes, d_src, count, h_dst); });
+  run_lanes(nlanes, errs, [&](int t) { return lane_fetch(pool.lanes[t], dev, t, nlanes, d_src, count, chunk, h_dst); });
   for (int t = 0; t < nlanes; ++t)
     if (errs[t] != cudaSuccess) {
       for (int u = 0; u < nlanes; ++u) cudaStreamSynchronize(pool.lanes[u].stream);   // leave no copy in flight
