@@ -27,9 +27,12 @@ struct PassArgs {
 // ---------------------------------------------------------------------------------------------
 // SKIP: the warp-uniform fold skip of pairwise.cuh (points and components spatially ordered by the caller); that
 // variant needs ~120 registers at DP <= 8, hence 4 resident CTAs instead of 5.
+// (DIAG at DP = 8 holds a and b rows: at 5 CTAs per SM it spilled 296 B, so it is compiled for 4 as well.)
 template <int KIND, int DP, bool HAS_C, bool SKIP = false>
 __global__ void __launch_bounds__(kThreads,
-                                  (KIND != AISB_COV_FULL && DP <= 8) ? (SKIP ? 4 : AISB_MIN_CTAS_SMALL) : 1)
+                                  (KIND != AISB_COV_FULL && DP <= 8)
+                                      ? ((SKIP || (KIND == AISB_COV_DIAG && DP == 8)) ? 4 : AISB_MIN_CTAS_SMALL)
+                                      : 1)
     logpdf_kernel(const float* __restrict__ x, int64_t n, int D, int vec_ok, PassArgs mix, int nsplit,
                   int64_t comps_per_split, int64_t ntiles, float* __restrict__ out, float* __restrict__ ws_m,
                   float* __restrict__ ws_S) {
@@ -250,7 +253,7 @@ __device__ __forceinline__ SubsetPlan subset_plan(const unsigned long long* __re
 }
 
 template <int DP>
-__global__ void __launch_bounds__(kThreads, DP <= 8 ? AISB_MIN_CTAS_SMALL : 1)
+__global__ void __launch_bounds__(kThreads, DP <= 8 ? 4 : 1)   // 5 CTAs per SM (96 registers) spilled 164 B at DP = 8
     logpdf_subset_kernel(const float* __restrict__ x, int64_t n, PassArgs mix, const int64_t* __restrict__ list,
                          const unsigned long long* __restrict__ list_n, float* __restrict__ ws_m,
                          float* __restrict__ ws_S, float* __restrict__ out) {
