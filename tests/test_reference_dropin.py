@@ -71,3 +71,47 @@ def test_reference_tests_and_cbenchmark_run_on_b200_classes():
     # the adaptive samplers end close to the target on the easy 1-D Normal (reference run: 0.06 .. 0.25)
     assert bm["final"]["TP_AISr_ESS90/normal01D"]["KLD"] < 0.5
     assert bm["final"]["dm_ais/normal01D"]["KLD"] < 1.0
+
+
+def test_reference_tpais_dm_and_mixture_methods_cannot_run():
+    """Why CTreePyramidSampling here offers method="simple" only (VERDICT r1 "missing" 5): with the
+    `np.int` alias the reference's own "dm" / "mixture" weighting (tree_pyramid.py:363-419) still dies -- the first
+    `find_unique` after the root has been split recurses without bound in `CTreePyramid.find` (:140-155) -- for both
+    kernels. There is no reference behaviour to reproduce; ours raises NotImplementedError and says so."""
+    _ensure_ref()
+    probe = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+from oracle import build_ref
+build_ref.load()
+np.int = int
+from ais_benchmarks.sampling_methods import CTreePyramidSampling
+from ais_benchmarks.distributions import CGaussianMixtureModel
+tgt = CGaussianMixtureModel({"means": np.array([[0.2, 0.3], [-0.4, -0.1]]), "sigmas": np.array([[0.02, 0.02], [0.03, 0.03]]),
+                             "weights": np.array([0.5, 0.5]), "support": np.array([[-1., -1.], [1., 1.]])})
+for method in ("mixture", "dm", "simple"):
+    for kernel in ("haar", "normal"):
+        np.random.seed(0)
+        try:
+            s = CTreePyramidSampling({"space_min": np.array([-1., -1.]), "space_max": np.array([1., 1.]), "dims": 2,
+                                      "method": method, "resampling": "none", "kernel": kernel, "ess_target": 0.5,
+                                      "n_min": 5, "parallel_samples": 4})
+            x, w = s.importance_sample(tgt, 40, timeout=20)
+            print("PROBE", method, kernel, "ok", len(x))
+        except BaseException as e:
+            print("PROBE", method, kernel, type(e).__name__)
+''' % ROOT
+    proc = subprocess.run([sys.executable, "-W", "ignore", "-c", probe], cwd=ROOT, capture_output=True, text=True,
+                          timeout=600)
+    got = {tuple(ln.split()[1:3]): ln.split()[3] for ln in proc.stdout.splitlines() if ln.startswith("PROBE ")}
+    assert len(got) == 6, (proc.stdout[-2000:], proc.stderr[-2000:])
+    for kernel in ("haar", "normal"):
+        assert got[("simple", kernel)] == "ok"
+        assert got[("mixture", kernel)] == "RecursionError" and got[("dm", kernel)] == "RecursionError", got
+    # ours: refuses at construction, with the explanation
+    from ais_benchmarks_b200.sampling_methods import CTreePyramidSampling
+    import numpy as np
+    with pytest.raises(NotImplementedError, match="np.int"):
+        CTreePyramidSampling({"space_min": np.array([-1., -1.]), "space_max": np.array([1., 1.]), "dims": 2,
+                              "method": "mixture", "resampling": "none", "kernel": "haar", "ess_target": 0.5,
+                              "n_min": 5, "parallel_samples": 4})
